@@ -1,0 +1,663 @@
+// communicator.cpp — see communicator.h.
+#include "communicator.h"
+
+#include <c10/cuda/CUDAStream.h>
+#include <cuda_runtime.h>
+
+#include <cstring>
+#include <sstream>
+#include <stdexcept>
+
+namespace dear {
+
+#define DEAR_CHECK(cond, msg)                                                        \
+  do {                                                                               \
+    if (!(cond)) {                                                                   \
+      std::ostringstream _oss;                                                       \
+      _oss << "dear: " << msg;                                                       \
+      throw std::runtime_error(_oss.str());                                          \
+    }                                                                                \
+  } while (0)
+
+#define DEAR_CUDA(expr)                                                              \
+  do {                                                                               \
+    cudaError_t _e = (expr);                                                         \
+    if (_e != cudaSuccess) {                                                         \
+      std::ostringstream _oss;                                                       \
+      _oss << "dear: CUDA error '" << cudaGetErrorString(_e) << "' in " #expr " ("   \
+           << __FILE__ << ":" << __LINE__ << ")";                                    \
+      throw std::runtime_error(_oss.str());                                          \
+    }                                                                                \
+  } while (0)
+
+static inline cudaStream_t S(void* p) { return reinterpret_cast<cudaStream_t>(p); }
+static inline cudaEvent_t E(void* p) { return reinterpret_cast<cudaEvent_t>(p); }
+
+static cudaStream_t current_stream(int device) {
+  return c10::cuda::getCurrentCUDAStream(static_cast<c10::DeviceIndex>(device)).stream();
+}
+
+static bool is_capturing(cudaStream_t s) {
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(s, &st) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return st != cudaStreamCaptureStatusNone;
+}
+
+static cudaStream_t make_priority_stream() {
+  int lo = 0, hi = 0;
+  DEAR_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  cudaStream_t s;
+  DEAR_CUDA(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, hi));
+  return s;
+}
+
+static cudaEvent_t make_event() {
+  cudaEvent_t e;
+  DEAR_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  return e;
+}
+
+int dtype_of(const torch::Tensor& t) {
+  switch (t.scalar_type()) {
+    case torch::kFloat: return DT_F32;
+    case torch::kBFloat16: return DT_BF16;
+    case torch::kHalf: return DT_F16;
+    default: return -1;
+  }
+}
+
+static torch::ScalarType scalar_of(int dt) {
+  switch (dt) {
+    case DT_F32: return torch::kFloat;
+    case DT_BF16: return torch::kBFloat16;
+    case DT_F16: return torch::kHalf;
+    default: throw std::runtime_error("dear: bad dtype");
+  }
+}
+
+// ===========================================================================
+// Communicator
+// ===========================================================================
+ArenaOptions Communicator::arena_options() const {
+  ArenaOptions a;
+  a.provider = is_cuda() ? static_cast<Provider>(opt_.provider) : Provider::HOST_SHM;
+  a.want_multicast = opt_.multicast;
+  a.device = opt_.device;
+  a.timeout_s = opt_.rendezvous_timeout_s;
+  return a;
+}
+
+std::string Communicator::unique_key(const std::string& what) {
+  return name_ + "/" + what + "/" + std::to_string(key_seq_++);
+}
+
+Communicator::Communicator(int rank, int world, c10::intrusive_ptr<c10d::Store> store, std::string name,
+                           CommOptions opt)
+    : rank_(rank), world_(world), store_(std::move(store)), name_(std::move(name)), opt_(opt) {
+  DEAR_CHECK(opt_.nstreams >= 1 && opt_.nstreams <= 16, "nstreams must be in [1,16]");
+  if (is_cuda()) {
+    DEAR_CHECK(cuda_runtime_usable(), "CUDA device requested but no CUDA runtime/driver is usable");
+    DEAR_CUDA(cudaSetDevice(opt_.device));
+  }
+  general_ = SymmArena::create(static_cast<size_t>(opt_.staging_bytes) * opt_.nstreams, rank_, world_, store_,
+                               unique_key("general"), arena_options());
+  slots_.resize(opt_.nstreams);
+  if (is_cuda()) {
+    for (auto& s : slots_) {
+      s.stream = make_priority_stream();
+      s.ev_in = make_event();
+      s.ev_out = make_event();
+    }
+  }
+  (void)status_word_host();
+}
+
+Communicator::~Communicator() {
+  if (is_cuda()) {
+    for (auto& s : slots_) {
+      if (s.stream) {
+        cudaStreamSynchronize(S(s.stream));
+        cudaStreamDestroy(S(s.stream));
+      }
+      if (s.ev_in) cudaEventDestroy(E(s.ev_in));
+      if (s.ev_out) cudaEventDestroy(E(s.ev_out));
+    }
+    cudaGetLastError();
+  }
+}
+
+int Communicator::next_slot() {
+  int s = cur_slot_;
+  cur_slot_ = (cur_slot_ + 1) % static_cast<int>(slots_.size());
+  return s;
+}
+
+void Communicator::check_status() {
+  uint32_t* st = status_word_host();
+  uint32_t v = __atomic_load_n(st, __ATOMIC_ACQUIRE);
+  if (v != ST_OK) {
+    __atomic_store_n(st, 0u, __ATOMIC_RELEASE);
+    static const char* names[] = {"ok", "reduce-scatter: peers never packed", "reduce-scatter: peers never released the bucket",
+                                  "all-gather: peers never arrived", "all-gather: peers never pushed", "general collective"};
+    std::ostringstream oss;
+    oss << "dear: rank " << rank_ << ": cross-GPU wait timed out (" << (v < 6 ? names[v] : "?") << ", code " << v
+        << "); a peer is missing, crashed, or issued collectives in a different order";
+    throw std::runtime_error(oss.str());
+  }
+}
+
+void Communicator::gen_chunked(int slot, int op, const char* src, char* dst, uint64_t nelems, int dtype,
+                               uint32_t elem_bytes, int root_or_peer, float scale, uint64_t dst_stride_elems) {
+  const size_t stage_off = static_cast<size_t>(slot) * opt_.staging_bytes;
+  GenParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.stage = general_->data_table(stage_off);
+  p.mc_stage = nullptr;
+  p.op = op;
+  p.root_or_peer = root_or_peer;
+  p.scale = scale;
+  p.ready_chan = 1 + 2 * slot;
+  p.done_chan = 2 + 2 * slot;
+  p.sig = general_->sig_table();
+  p.ctrl = general_->ctrl();
+  p.rank = rank_;
+  p.world = world_;
+  p.dtype = dtype < 0 ? DT_F32 : dtype;
+  p.elem_bytes = elem_bytes;
+  p.status = is_cuda() ? status_word_device() : status_word_host();
+  p.timeout_ns = timeout_ns();
+  p.dst_stride_bytes = dst_stride_elems * elem_bytes;
+
+  const uint64_t max_elems = (static_cast<uint64_t>(opt_.staging_bytes) / elem_bytes) & ~uint64_t(15);
+  uint64_t done = 0;
+  do {
+    const uint64_t n = std::min<uint64_t>(nelems - done, max_elems);
+    p.src = src ? src + done * elem_bytes : nullptr;
+    p.dst = dst ? dst + done * elem_bytes : nullptr;
+    p.nelems = n;
+    if (is_cuda()) {
+      int grid = static_cast<int>(std::min<uint64_t>(std::max<uint64_t>(1, (n * elem_bytes) / (16 * 512 * 4)), opt_.gen_grid));
+      launch_gen(p, grid, S(slots_[slot].stream));
+    } else {
+      emu_gen(p);
+    }
+    count_launch();
+    done += n;
+  } while (done < nelems);
+}
+
+int Communicator::run_gen(int op, const void* src, void* dst, uint64_t nelems, int dtype, uint32_t elem_bytes,
+                          int root_or_peer, float scale) {
+  const int slot = next_slot();
+  cudaStream_t cur = nullptr;
+  if (is_cuda()) {
+    cur = current_stream(opt_.device);
+    DEAR_CUDA(cudaEventRecord(E(slots_[slot].ev_in), cur));
+    DEAR_CUDA(cudaStreamWaitEvent(S(slots_[slot].stream), E(slots_[slot].ev_in), 0));
+  }
+  gen_chunked(slot, op, reinterpret_cast<const char*>(src), reinterpret_cast<char*>(dst), nelems, dtype, elem_bytes,
+              root_or_peer, scale, 0);
+  if (is_cuda()) DEAR_CUDA(cudaEventRecord(E(slots_[slot].ev_out), S(slots_[slot].stream)));
+  return slot;
+}
+
+static void check_tensor(const torch::Tensor& t, bool cuda, int device, const char* what) {
+  DEAR_CHECK(t.is_contiguous(), what << ": tensor must be contiguous");
+  if (cuda) {
+    DEAR_CHECK(t.is_cuda() && t.device().index() == device, what << ": tensor must live on cuda:" << device);
+  } else {
+    DEAR_CHECK(t.device().is_cpu(), what << ": tensor must be a CPU tensor for the host-emulation backend");
+  }
+}
+
+int Communicator::allreduce_(torch::Tensor t, double scale) {
+  check_tensor(t, is_cuda(), opt_.device, "allreduce");
+  const int dt = dtype_of(t);
+  DEAR_CHECK(dt >= 0, "allreduce: dtype must be float32/bfloat16/float16");
+  return run_gen(GEN_ALLREDUCE, t.data_ptr(), t.data_ptr(), t.numel(), dt, t.element_size(), 0, static_cast<float>(scale));
+}
+
+int Communicator::reduce_(torch::Tensor t, int root, double scale) {
+  check_tensor(t, is_cuda(), opt_.device, "reduce");
+  const int dt = dtype_of(t);
+  DEAR_CHECK(dt >= 0, "reduce: dtype must be float32/bfloat16/float16");
+  DEAR_CHECK(root >= 0 && root < world_, "reduce: bad root");
+  return run_gen(GEN_REDUCE, t.data_ptr(), t.data_ptr(), t.numel(), dt, t.element_size(), root, static_cast<float>(scale));
+}
+
+int Communicator::bcast_(torch::Tensor t, int root) {
+  check_tensor(t, is_cuda(), opt_.device, "bcast");
+  DEAR_CHECK(root >= 0 && root < world_, "bcast: bad root");
+  // raw byte move: any dtype (fp32, int64 for BN num_batches_tracked, ...)
+  return run_gen(GEN_BCAST, t.data_ptr(), rank_ == root ? nullptr : t.data_ptr(), t.numel(), DT_F32, t.element_size(), root, 1.f);
+}
+
+int Communicator::sendrecv(torch::Tensor send, torch::Tensor recv, int peer) {
+  check_tensor(send, is_cuda(), opt_.device, "sendrecv(send)");
+  check_tensor(recv, is_cuda(), opt_.device, "sendrecv(recv)");
+  DEAR_CHECK(send.numel() == recv.numel() && send.element_size() == recv.element_size(), "sendrecv: size mismatch");
+  DEAR_CHECK(peer >= 0 && peer < world_, "sendrecv: bad peer");
+  return run_gen(GEN_SENDRECV, send.data_ptr(), recv.data_ptr(), send.numel(), DT_F32, send.element_size(), peer, 1.f);
+}
+
+int Communicator::device_barrier() { return run_gen(GEN_BARRIER, nullptr, nullptr, 0, DT_F32, 4, 0, 1.f); }
+
+int Communicator::allgather(torch::Tensor send, torch::Tensor recv) {
+  check_tensor(send, is_cuda(), opt_.device, "allgather(send)");
+  check_tensor(recv, is_cuda(), opt_.device, "allgather(recv)");
+  DEAR_CHECK(recv.numel() == send.numel() * world_ && send.element_size() == recv.element_size(),
+             "allgather: recv must hold world*send elements");
+  const int slot = next_slot();
+  if (is_cuda()) {
+    DEAR_CUDA(cudaEventRecord(E(slots_[slot].ev_in), current_stream(opt_.device)));
+    DEAR_CUDA(cudaStreamWaitEvent(S(slots_[slot].stream), E(slots_[slot].ev_in), 0));
+  }
+  gen_chunked(slot, GEN_ALLGATHER, reinterpret_cast<const char*>(send.data_ptr()), reinterpret_cast<char*>(recv.data_ptr()),
+              send.numel(), DT_F32, send.element_size(), 0, 1.f, send.numel());
+  if (is_cuda()) DEAR_CUDA(cudaEventRecord(E(slots_[slot].ev_out), S(slots_[slot].stream)));
+  return slot;
+}
+
+int Communicator::reduce_scatter(torch::Tensor send, torch::Tensor recv, double scale) {
+  check_tensor(send, is_cuda(), opt_.device, "reduce_scatter(send)");
+  check_tensor(recv, is_cuda(), opt_.device, "reduce_scatter(recv)");
+  const int dt = dtype_of(send);
+  DEAR_CHECK(dt >= 0 && dtype_of(recv) == dt, "reduce_scatter: dtype must be float32/bfloat16/float16");
+  DEAR_CHECK(send.numel() == recv.numel() * world_, "reduce_scatter: send must hold world*recv elements");
+  const int slot = next_slot();
+  const uint64_t per = recv.numel();
+  const uint32_t eb = send.element_size();
+  const char* sp = reinterpret_cast<const char*>(send.data_ptr());
+  char* rp = reinterpret_cast<char*>(recv.data_ptr());
+  char* stage = general_->local_data() + static_cast<size_t>(slot) * opt_.staging_bytes;
+  cudaStream_t st = is_cuda() ? S(slots_[slot].stream) : nullptr;
+  if (is_cuda()) {
+    DEAR_CUDA(cudaEventRecord(E(slots_[slot].ev_in), current_stream(opt_.device)));
+    DEAR_CUDA(cudaStreamWaitEvent(st, E(slots_[slot].ev_in), 0));
+  }
+  // chunk over the shard so that world*chunk fits the staging buffer
+  const uint64_t max_chunk = ((static_cast<uint64_t>(opt_.staging_bytes) / eb / world_) & ~uint64_t(15));
+  DEAR_CHECK(max_chunk > 0, "staging buffer too small");
+  for (uint64_t a = 0; a < per || a == 0; a += max_chunk) {
+    const uint64_t n = std::min<uint64_t>(per - a, max_chunk);
+    if (n == 0) break;
+    // gather the P row-chunks contiguously into my staging buffer
+    // NOTE: the previous op on this slot may still be read by peers; the
+    // kernel's step (0) waits for them, so the staging copy must happen inside
+    // the same stream AFTER a device barrier on the done flags: we run a
+    // zero-size barrier op first to inherit that guarantee.
+    gen_chunked(slot, GEN_BARRIER, nullptr, nullptr, 0, DT_F32, 4, 0, 1.f, 0);
+    for (int q = 0; q < world_; ++q) {
+      const char* s = sp + (uint64_t(q) * per + a) * eb;
+      char* d = stage + uint64_t(q) * n * eb;
+      if (is_cuda()) DEAR_CUDA(cudaMemcpyAsync(d, s, n * eb, cudaMemcpyDeviceToDevice, st));
+      else std::memcpy(d, s, n * eb);
+    }
+    gen_chunked(slot, GEN_REDUCE_SCATTER, nullptr, rp + a * eb, n * world_, dt, eb, 0, static_cast<float>(scale), 0);
+  }
+  if (is_cuda()) DEAR_CUDA(cudaEventRecord(E(slots_[slot].ev_out), st));
+  return slot;
+}
+
+int Communicator::allreduce_rsag_(torch::Tensor t, double scale) {
+  // all-reduce as reduce-scatter followed by all-gather (reference communicator.cpp:198-235)
+  const int64_t n = t.numel();
+  if (n < world_ || n % world_ != 0) return allreduce_(t, scale);   // the reference pads; we fall back
+  auto flat = t.view({-1});
+  const int64_t per = n / world_;
+  auto shard = flat.narrow(0, rank_ * per, per);
+  auto tmp = torch::empty_like(shard);
+  const int h = reduce_scatter(flat, tmp, scale);
+  wait_stream(h);
+  const int h2 = allgather(tmp, flat);
+  wait_stream(h2);   // `tmp` is freed in current-stream order, i.e. after the all-gather consumed it
+  return h2;
+}
+
+int Communicator::allreduce_rb_(torch::Tensor t, double scale) {
+  // all-reduce as reduce(root 0) + broadcast(root 0) (reference communicator.cpp:185-196)
+  int h = reduce_(t, 0, scale);
+  wait_stream(h);
+  return bcast_(t, 0);
+}
+
+void Communicator::synchronize() {
+  if (is_cuda())
+    for (auto& s : slots_) DEAR_CUDA(cudaStreamSynchronize(S(s.stream)));
+  check_status();
+}
+
+void Communicator::sync_stream(int handle) {
+  DEAR_CHECK(handle >= 0 && handle < static_cast<int>(slots_.size()), "bad stream handle");
+  if (is_cuda()) DEAR_CUDA(cudaStreamSynchronize(S(slots_[handle].stream)));
+  check_status();
+}
+
+void Communicator::wait_stream(int handle) {
+  DEAR_CHECK(handle >= 0 && handle < static_cast<int>(slots_.size()), "bad stream handle");
+  if (is_cuda()) DEAR_CUDA(cudaStreamWaitEvent(current_stream(opt_.device), E(slots_[handle].ev_out), 0));
+}
+
+int Communicator::num_free_streams() {
+  if (!is_cuda()) return static_cast<int>(slots_.size());
+  int n = 0;
+  for (auto& s : slots_) {
+    cudaError_t e = cudaStreamQuery(S(s.stream));
+    if (e == cudaSuccess) ++n; else if (e != cudaErrorNotReady) DEAR_CUDA(e);
+  }
+  cudaGetLastError();
+  return n;
+}
+
+void Communicator::barrier() {
+  if (world_ == 1) return;
+  const std::string base = name_ + "/hostbar/" + std::to_string(barrier_seq_++) + "/";
+  store_->set(base + std::to_string(rank_), std::vector<uint8_t>{1});
+  std::vector<std::string> keys;
+  for (int r = 0; r < world_; ++r) keys.push_back(base + std::to_string(r));
+  store_->wait(keys, std::chrono::milliseconds(static_cast<int64_t>(opt_.rendezvous_timeout_s * 1000)));
+}
+
+// ===========================================================================
+// BucketSet
+// ===========================================================================
+BucketSet::BucketSet(std::shared_ptr<Communicator> comm, std::vector<int64_t> padded_numels, int dtype,
+                     bool with_grad_buckets)
+    : comm_(std::move(comm)), dtype_(dtype), with_grad_(with_grad_buckets) {
+  const int world = comm_->size();
+  const size_t es = dtype_size(dtype);
+  DEAR_CHECK(static_cast<int>(padded_numels.size()) * kChannelsPerBucket + kGeneralChannels <= kNumChannels,
+             "too many buckets (" << padded_numels.size() << ")");
+  size_t off = 0;
+  for (int64_t n : padded_numels) {
+    DEAR_CHECK(n > 0 && n % world == 0, "bucket size must be a positive multiple of the world size");
+    const int64_t shard = n / world;
+    DEAR_CHECK((shard * es) % 16 == 0, "shard bytes must be a multiple of 16");
+    Bucket b;
+    b.padded = n;
+    b.shard = shard;
+    b.param_off = off;
+    off += (n * es + 255) / 256 * 256;
+    if (with_grad_) {
+      b.grad_off = off;
+      off += (n * es + 255) / 256 * 256;
+    }
+    buckets_.push_back(std::move(b));
+  }
+  arena_ = SymmArena::create(off, comm_->rank(), world, comm_->store(), comm_->unique_key("buckets"),
+                             comm_->arena_options());
+  if (comm_->is_cuda()) {
+    stream_ = make_priority_stream();
+    ev_fence_ = make_event();
+    for (auto& b : buckets_) {
+      b.ev_in = make_event();
+      b.rs_done = make_event();
+      b.ag_done = make_event();
+      b.pinned_ev[0] = make_event();
+      b.pinned_ev[1] = make_event();
+    }
+  }
+}
+
+BucketSet::~BucketSet() {
+  if (comm_->is_cuda()) {
+    if (stream_) cudaStreamSynchronize(S(stream_));
+    for (auto& b : buckets_) {
+      for (void* e : {b.ev_in, b.rs_done, b.ag_done, b.pinned_ev[0], b.pinned_ev[1]})
+        if (e) cudaEventDestroy(E(e));
+      if (b.pack_dev) cudaFree(b.pack_dev);
+      if (b.hyper_dev) cudaFree(b.hyper_dev);
+      for (void* p : b.pinned) if (p) cudaFreeHost(p);
+    }
+    if (ev_fence_) cudaEventDestroy(E(ev_fence_));
+    if (stream_) cudaStreamDestroy(S(stream_));
+    cudaGetLastError();
+  }
+}
+
+static torch::Tensor wrap(char* ptr, int64_t numel, int dtype, bool cuda, int device, std::shared_ptr<SymmArena> keep) {
+  auto opts = torch::TensorOptions().dtype(scalar_of(dtype));
+  if (cuda) opts = opts.device(torch::kCUDA, device);
+  return torch::from_blob(ptr, {numel}, [keep](void*) mutable { keep.reset(); }, opts);
+}
+
+torch::Tensor BucketSet::param_buffer(int g) {
+  auto& b = buckets_.at(g);
+  return wrap(arena_->local_data() + b.param_off, b.padded, dtype_, comm_->is_cuda(), comm_->options().device, arena_);
+}
+
+torch::Tensor BucketSet::grad_buffer(int g) {
+  DEAR_CHECK(with_grad_, "this BucketSet has no gradient buckets");
+  auto& b = buckets_.at(g);
+  return wrap(arena_->local_data() + b.grad_off, b.padded, dtype_, comm_->is_cuda(), comm_->options().device, arena_);
+}
+
+void BucketSet::set_shards(int g, torch::Tensor grad_shard, std::optional<torch::Tensor> mom,
+                           std::optional<torch::Tensor> master) {
+  auto& b = buckets_.at(g);
+  auto chk = [&](const torch::Tensor& t, const char* what) {
+    DEAR_CHECK(t.scalar_type() == torch::kFloat && t.is_contiguous() && t.numel() == b.shard,
+               what << " must be a contiguous float32 tensor of " << b.shard << " elements");
+    DEAR_CHECK(t.is_cuda() == comm_->is_cuda(), what << " is on the wrong device type");
+  };
+  chk(grad_shard, "grad_shard");
+  b.grad_shard = grad_shard;
+  b.mom = torch::Tensor();
+  b.master = torch::Tensor();
+  if (mom.has_value() && mom->defined()) { chk(*mom, "momentum shard"); b.mom = *mom; }
+  if (master.has_value() && master->defined()) { chk(*master, "master shard"); b.master = *master; }
+  DEAR_CHECK(dtype_ == DT_F32 || b.master.defined(), "low-precision parameter buckets need an fp32 master shard");
+}
+
+void BucketSet::upload(Bucket& b, const void* host, size_t bytes, void** dev, size_t* cap) {
+  if (bytes == 0) return;
+  if (*cap < bytes) {
+    // the old table may still be read by an in-flight kernel on the comm stream
+    DEAR_CUDA(cudaStreamSynchronize(S(stream_)));
+    if (*dev) DEAR_CUDA(cudaFree(*dev));
+    size_t ncap = std::max<size_t>(bytes * 2, 4096);
+    DEAR_CUDA(cudaMalloc(dev, ncap));
+    *cap = ncap;
+  }
+  const int slot = b.pinned_next;
+  b.pinned_next ^= 1;
+  const bool capturing = is_capturing(S(stream_));
+  if (b.pinned_cap[slot] < bytes) {
+    if (b.pinned[slot]) {
+      if (!capturing) DEAR_CUDA(cudaEventSynchronize(E(b.pinned_ev[slot])));
+      DEAR_CUDA(cudaFreeHost(b.pinned[slot]));
+    }
+    size_t ncap = std::max<size_t>(bytes * 2, 4096);
+    DEAR_CUDA(cudaHostAlloc(&b.pinned[slot], ncap, cudaHostAllocDefault));
+    b.pinned_cap[slot] = ncap;
+  } else if (!capturing) {
+    DEAR_CUDA(cudaEventSynchronize(E(b.pinned_ev[slot])));   // normally long complete
+  }
+  std::memcpy(b.pinned[slot], host, bytes);
+  DEAR_CUDA(cudaMemcpyAsync(*dev, b.pinned[slot], bytes, cudaMemcpyHostToDevice, S(stream_)));
+  if (!capturing) DEAR_CUDA(cudaEventRecord(E(b.pinned_ev[slot]), S(stream_)));
+}
+
+bool BucketSet::set_pack(int g, const std::vector<int64_t>& src_ptrs, const std::vector<int64_t>& dst_off_bytes,
+                         const std::vector<int64_t>& nbytes, const std::vector<int64_t>& flags) {
+  auto& b = buckets_.at(g);
+  const size_t n = src_ptrs.size();
+  DEAR_CHECK(dst_off_bytes.size() == n && nbytes.size() == n && flags.size() == n, "set_pack: ragged arguments");
+  const size_t es = dtype_size(dtype_);
+  std::vector<PackSeg> segs;
+  segs.reserve(n);
+  uint32_t tiles = 0;
+  for (size_t i = 0; i < n; ++i) {
+    if (nbytes[i] == 0) continue;
+    if (src_ptrs[i] == 0 && !(flags[i] & SEG_ZERO_FILL)) continue;   // in place: nothing to do
+    PackSeg s;
+    s.src = reinterpret_cast<const void*>(static_cast<uintptr_t>(src_ptrs[i]));
+    s.dst_off = static_cast<uint64_t>(dst_off_bytes[i]);
+    s.nbytes = static_cast<uint64_t>(nbytes[i]);
+    s.tile_begin = tiles;
+    s.flags = static_cast<uint32_t>(flags[i]);
+    DEAR_CHECK(s.dst_off % 16 == 0, "set_pack: destination offsets must be 16-byte aligned");
+    DEAR_CHECK((reinterpret_cast<uintptr_t>(s.src) % 16) == 0, "set_pack: gradient storage must be 16-byte aligned");
+    DEAR_CHECK(s.nbytes % 2 == 0 && s.dst_off + s.nbytes <= static_cast<uint64_t>(b.padded) * es, "set_pack: segment out of range");
+    tiles += static_cast<uint32_t>((s.nbytes + kPackTileBytes - 1) / kPackTileBytes);
+    segs.push_back(s);
+  }
+  const bool same = segs.size() == b.pack_host.size() &&
+                    (segs.empty() || std::memcmp(segs.data(), b.pack_host.data(), segs.size() * sizeof(PackSeg)) == 0);
+  if (same) return false;
+  b.pack_host = std::move(segs);
+  b.ntiles = tiles;
+  if (comm_->is_cuda())
+    upload(b, b.pack_host.data(), b.pack_host.size() * sizeof(PackSeg), reinterpret_cast<void**>(&b.pack_dev), &b.pack_cap);
+  return true;
+}
+
+bool BucketSet::set_hyper(int g, const std::vector<int64_t>& ends, const std::vector<double>& lr,
+                          const std::vector<double>& wd, const std::vector<double>& mom,
+                          const std::vector<double>& damp, const std::vector<int64_t>& nesterov) {
+  auto& b = buckets_.at(g);
+  const size_t n = ends.size();
+  DEAR_CHECK(n >= 1 && lr.size() == n && wd.size() == n && mom.size() == n && damp.size() == n && nesterov.size() == n,
+             "set_hyper: ragged arguments");
+  std::vector<HyperSeg> segs(n);
+  for (size_t i = 0; i < n; ++i) {
+    segs[i].end = static_cast<uint64_t>(ends[i]);
+    segs[i].lr = static_cast<float>(lr[i]);
+    segs[i].weight_decay = static_cast<float>(wd[i]);
+    segs[i].momentum = static_cast<float>(mom[i]);
+    segs[i].dampening = static_cast<float>(damp[i]);
+    segs[i].nesterov = nesterov[i] ? 1u : 0u;
+    segs[i].reserved = 0;
+    DEAR_CHECK(i == 0 || segs[i].end > segs[i - 1].end, "set_hyper: segment ends must increase");
+  }
+  DEAR_CHECK(segs.back().end >= static_cast<uint64_t>(b.padded), "set_hyper: segments must cover the bucket");
+  const bool same = segs.size() == b.hyper_host.size() &&
+                    std::memcmp(segs.data(), b.hyper_host.data(), segs.size() * sizeof(HyperSeg)) == 0;
+  if (same) return false;
+  b.hyper_host = std::move(segs);
+  if (comm_->is_cuda())
+    upload(b, b.hyper_host.data(), b.hyper_host.size() * sizeof(HyperSeg), reinterpret_cast<void**>(&b.hyper_dev), &b.hyper_cap);
+  return true;
+}
+
+int BucketSet::grid_for(int64_t bytes, int max_grid) const {
+  int64_t g = (bytes + (512 * 16 * 8) - 1) / (512 * 16 * 8);
+  if (g < 1) g = 1;
+  if (g > max_grid) g = max_grid;
+  return static_cast<int>(g);
+}
+
+void BucketSet::fence_current_to_comm() {
+  if (!comm_->is_cuda()) return;
+  DEAR_CUDA(cudaEventRecord(E(ev_fence_), current_stream(comm_->options().device)));
+  DEAR_CUDA(cudaStreamWaitEvent(S(stream_), E(ev_fence_), 0));
+}
+
+void BucketSet::reduce_scatter(int g, bool pack) {
+  auto& b = buckets_.at(g);
+  DEAR_CHECK(with_grad_, "reduce_scatter needs gradient buckets");
+  DEAR_CHECK(b.grad_shard.defined(), "set_shards() must be called before reduce_scatter()");
+  RSParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.grad = arena_->data_table(b.grad_off);
+  p.mc_grad = arena_->has_multicast() ? arena_->mc_data() + b.grad_off : nullptr;
+  p.out = b.grad_shard.data_ptr<float>();
+  p.shard_elems = static_cast<uint64_t>(b.shard);
+  p.scale = 1.0f / static_cast<float>(comm_->size());
+  const bool cuda = comm_->is_cuda();
+  if (pack && !b.pack_host.empty()) {
+    p.segs = cuda ? b.pack_dev : b.pack_host.data();
+    p.nseg = static_cast<uint32_t>(b.pack_host.size());
+    p.ntiles = b.ntiles;
+  }
+  p.sig = arena_->sig_table();
+  p.ctrl = arena_->ctrl();
+  p.bucket = static_cast<uint32_t>(g);
+  p.rank = comm_->rank();
+  p.world = comm_->size();
+  p.dtype = dtype_;
+  p.status = cuda ? status_word_device() : status_word_host();
+  p.timeout_ns = comm_->timeout_ns();
+  if (cuda) {
+    DEAR_CUDA(cudaEventRecord(E(b.ev_in), current_stream(comm_->options().device)));
+    DEAR_CUDA(cudaStreamWaitEvent(S(stream_), E(b.ev_in), 0));
+    launch_rs(p, grid_for(b.padded * static_cast<int64_t>(dtype_size(dtype_)), comm_->options().rs_grid), S(stream_));
+    DEAR_CUDA(cudaEventRecord(E(b.rs_done), S(stream_)));
+  } else {
+    emu_rs(p);
+  }
+  b.rs_pending = true;
+  comm_->count_launch();
+}
+
+void BucketSet::allgather_update(int g, bool do_update, bool first_step, bool entry_barrier, bool zero_grad) {
+  auto& b = buckets_.at(g);
+  const bool cuda = comm_->is_cuda();
+  AGParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.param = arena_->data_table(b.param_off);
+  p.mc_param = arena_->has_multicast() ? arena_->mc_data() + b.param_off : nullptr;
+  if (do_update) {
+    DEAR_CHECK(b.grad_shard.defined(), "set_shards() must be called before allgather_update()");
+    DEAR_CHECK(!b.hyper_host.empty(), "set_hyper() must be called before allgather_update()");
+    p.grad_shard = b.grad_shard.data_ptr<float>();
+    p.mom_shard = b.mom.defined() ? b.mom.data_ptr<float>() : nullptr;
+    p.hyper = cuda ? b.hyper_dev : b.hyper_host.data();
+    p.nhyper = static_cast<uint32_t>(b.hyper_host.size());
+  }
+  p.master_shard = b.master.defined() ? b.master.data_ptr<float>() : nullptr;
+  DEAR_CHECK(dtype_ == DT_F32 || p.master_shard != nullptr, "low-precision parameter buckets need an fp32 master shard");
+  if (zero_grad && with_grad_) {
+    p.zero_grad = arena_->local_data() + b.grad_off;
+    p.zero_bytes = static_cast<uint64_t>(b.padded) * dtype_size(dtype_);
+  }
+  p.shard_elems = static_cast<uint64_t>(b.shard);
+  p.first_step = first_step ? 1u : 0u;
+  p.entry_barrier = entry_barrier ? 1u : 0u;
+  p.do_update = do_update ? 1u : 0u;
+  p.sig = arena_->sig_table();
+  p.ctrl = arena_->ctrl();
+  p.bucket = static_cast<uint32_t>(g);
+  p.rank = comm_->rank();
+  p.world = comm_->size();
+  p.dtype = dtype_;
+  p.status = cuda ? status_word_device() : status_word_host();
+  p.timeout_ns = comm_->timeout_ns();
+  if (cuda) {
+    launch_ag(p, grid_for(b.shard * 16, comm_->options().ag_grid), S(stream_));
+    DEAR_CUDA(cudaEventRecord(E(b.ag_done), S(stream_)));
+  } else {
+    emu_ag(p);
+  }
+  b.ag_pending = true;
+  comm_->count_launch();
+}
+
+void BucketSet::wait_bucket(int g) {
+  auto& b = buckets_.at(g);
+  if (comm_->is_cuda() && b.ag_pending)
+    DEAR_CUDA(cudaStreamWaitEvent(current_stream(comm_->options().device), E(b.ag_done), 0));
+}
+
+void BucketSet::wait_rs(int g) {
+  auto& b = buckets_.at(g);
+  if (comm_->is_cuda() && b.rs_pending)
+    DEAR_CUDA(cudaStreamWaitEvent(current_stream(comm_->options().device), E(b.rs_done), 0));
+}
+
+void BucketSet::wait_all() {
+  if (!comm_->is_cuda()) return;
+  // everything on the comm stream is ordered, so one fresh event covers all buckets
+  DEAR_CUDA(cudaEventRecord(E(ev_fence_), S(stream_)));
+  DEAR_CUDA(cudaStreamWaitEvent(current_stream(comm_->options().device), E(ev_fence_), 0));
+}
+
+void BucketSet::synchronize() {
+  if (comm_->is_cuda()) DEAR_CUDA(cudaStreamSynchronize(S(stream_)));
+  comm_->check_status();
+}
+
+}  // namespace dear

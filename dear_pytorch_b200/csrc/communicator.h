@@ -1,0 +1,180 @@
+// communicator.h — native communication runtime of the DeAR engine.
+//
+// `Communicator` is the B200 counterpart of the reference's NCCL+MPI
+// `Communicator` class (common/comm_core/src/communicator.h:52-96): it owns the
+// communication streams/events and exposes the same family of operations
+// (bcast, reduce, allReduce, allReduceRB, allReduceRSAG, reduceScatter,
+// allGather, sendrecv, synchronize, syncStream, getNumOfFreeStreams, barrier),
+// but every operation is one of OUR kernels running over peer-mapped memory.
+//
+// `BucketSet` is the per-plan fused engine: symmetric parameter / gradient
+// buckets plus the two fused kernels (reduce-scatter+scale in backward,
+// SGD+all-gather in forward) that implement the decoupled all-reduce of
+// dear/dear_dopt.py:242-372 without NCCL and without per-parameter kernels.
+#pragma once
+#include <torch/extension.h>
+#include <cuda_runtime_api.h>
+
+#include <atomic>
+#include <memory>
+#include <optional>
+#include <string>
+#include <vector>
+
+#include "dear_common.h"
+#include "symm_mem.h"
+
+namespace dear {
+
+struct CommOptions {
+  int provider = static_cast<int>(Provider::CUDA_IPC);
+  bool multicast = false;
+  int device = -1;                       // -1 => host emulation
+  int64_t staging_bytes = 32ll << 20;    // per stream slot
+  int nstreams = 1;
+  double spin_timeout_s = 20.0;          // in-kernel bounded spin
+  double rendezvous_timeout_s = 120.0;
+  int rs_grid = 16;
+  int ag_grid = 16;
+  int gen_grid = 8;
+};
+
+class Communicator : public std::enable_shared_from_this<Communicator> {
+ public:
+  Communicator(int rank, int world, c10::intrusive_ptr<c10d::Store> store, std::string name,
+               CommOptions opt);
+  ~Communicator();
+
+  int rank() const { return rank_; }
+  int size() const { return world_; }
+  bool is_cuda() const { return opt_.device >= 0; }
+  bool has_multicast() const { return general_ && general_->has_multicast(); }
+  const CommOptions& options() const { return opt_; }
+  const c10::intrusive_ptr<c10d::Store>& store() const { return store_; }
+  const std::string& name() const { return name_; }
+
+  // ---- collective ops (return the stream-slot "handle" like the reference) ----
+  int allreduce_(torch::Tensor t, double scale);
+  int allreduce_rsag_(torch::Tensor t, double scale);
+  int allreduce_rb_(torch::Tensor t, double scale);
+  int bcast_(torch::Tensor t, int root);
+  int reduce_(torch::Tensor t, int root, double scale);
+  int reduce_scatter(torch::Tensor send, torch::Tensor recv, double scale);
+  int allgather(torch::Tensor send, torch::Tensor recv);
+  int sendrecv(torch::Tensor send, torch::Tensor recv, int peer);
+  int device_barrier();
+
+  // ---- stream sync API (reference communicator.cpp:97-128) ----
+  void synchronize();                 // host blocks on every comm stream
+  void sync_stream(int handle);       // host blocks on one comm stream
+  void wait_stream(int handle);       // current stream waits (no host block)
+  int num_free_streams();
+  void barrier();                     // host-side barrier through the store
+
+  // Throws if a kernel flagged a spin-wait timeout.
+  void check_status();
+  int64_t launches() const { return launches_.load(); }
+  void count_launch(int n = 1) { launches_.fetch_add(n); }
+
+  std::string unique_key(const std::string& what);
+  uint64_t timeout_ns() const { return static_cast<uint64_t>(opt_.spin_timeout_s * 1e9); }
+  ArenaOptions arena_options() const;
+
+ private:
+  struct Slot {
+    void* stream = nullptr;   // cudaStream_t
+    void* ev_in = nullptr;    // cudaEvent_t
+    void* ev_out = nullptr;
+  };
+  int run_gen(int op, const void* src, void* dst, uint64_t nelems, int dtype, uint32_t elem_bytes,
+              int root_or_peer, float scale);
+  int next_slot();
+  void gen_chunked(int slot, int op, const char* src, char* dst, uint64_t nelems, int dtype,
+                   uint32_t elem_bytes, int root_or_peer, float scale, uint64_t dst_stride_elems);
+
+  int rank_, world_;
+  c10::intrusive_ptr<c10d::Store> store_;
+  std::string name_;
+  CommOptions opt_;
+  std::shared_ptr<SymmArena> general_;   // staging for the general ops
+  std::vector<Slot> slots_;
+  int cur_slot_ = 0;
+  int key_seq_ = 0;
+  int barrier_seq_ = 0;
+  std::atomic<int64_t> launches_{0};
+};
+
+class BucketSet {
+ public:
+  BucketSet(std::shared_ptr<Communicator> comm, std::vector<int64_t> padded_numels, int dtype,
+            bool with_grad_buckets);
+  ~BucketSet();
+
+  int num_buckets() const { return static_cast<int>(buckets_.size()); }
+  torch::Tensor param_buffer(int g);
+  torch::Tensor grad_buffer(int g);
+  bool has_multicast() const { return arena_->has_multicast(); }
+
+  void set_shards(int g, torch::Tensor grad_shard, std::optional<torch::Tensor> mom,
+                  std::optional<torch::Tensor> master);
+  // Gradient sources for the fused pack.  Returns true if the device table was re-uploaded.
+  bool set_pack(int g, const std::vector<int64_t>& src_ptrs, const std::vector<int64_t>& dst_off_bytes,
+                const std::vector<int64_t>& nbytes, const std::vector<int64_t>& flags);
+  bool set_hyper(int g, const std::vector<int64_t>& ends, const std::vector<double>& lr,
+                 const std::vector<double>& wd, const std::vector<double>& mom,
+                 const std::vector<double>& damp, const std::vector<int64_t>& nesterov);
+
+  void reduce_scatter(int g, bool pack);
+  void allgather_update(int g, bool do_update, bool first_step, bool entry_barrier, bool zero_grad);
+  void fence_current_to_comm();
+  void wait_bucket(int g);
+  void wait_rs(int g);
+  void wait_all();
+  void synchronize();
+  int64_t comm_stream_handle() const { return reinterpret_cast<int64_t>(stream_); }
+
+ private:
+  struct Bucket {
+    int64_t padded = 0;
+    int64_t shard = 0;
+    size_t param_off = 0, grad_off = 0;
+    torch::Tensor grad_shard, mom, master;
+    std::vector<PackSeg> pack_host;
+    std::vector<HyperSeg> hyper_host;
+    uint32_t ntiles = 0;
+    PackSeg* pack_dev = nullptr;
+    size_t pack_cap = 0;
+    HyperSeg* hyper_dev = nullptr;
+    size_t hyper_cap = 0;
+    void* pinned[2] = {nullptr, nullptr};
+    size_t pinned_cap[2] = {0, 0};
+    void* pinned_ev[2] = {nullptr, nullptr};
+    int pinned_next = 0;
+    void* ev_in = nullptr;
+    void* rs_done = nullptr;
+    void* ag_done = nullptr;
+    bool ag_pending = false, rs_pending = false;
+  };
+  void upload(Bucket& b, const void* host, size_t bytes, void** dev, size_t* cap);
+  int grid_for(int64_t shard_elems, int max_grid) const;
+
+  std::shared_ptr<Communicator> comm_;
+  std::shared_ptr<SymmArena> arena_;
+  std::vector<Bucket> buckets_;
+  int dtype_;
+  bool with_grad_;
+  void* stream_ = nullptr;   // cudaStream_t (high priority)
+  void* ev_fence_ = nullptr;
+};
+
+// device launchers (kernels.cu) and host emulation (emu.cpp)
+void launch_rs(const RSParams& p, int grid, cudaStream_t s);
+void launch_ag(const AGParams& p, int grid, cudaStream_t s);
+void launch_gen(const GenParams& p, int grid, cudaStream_t s);
+void emu_rs(const RSParams& p);
+void emu_ag(const AGParams& p);
+void emu_gen(const GenParams& p);
+
+int dtype_of(const torch::Tensor& t);
+
+}  // namespace dear

@@ -1,0 +1,722 @@
+// kernels.cu — sm_100a device code of the DeAR runtime.
+//
+// Kernel A (rs_kernel):   gradient pack + reduce-scatter + fp32 accumulate + 1/P scale
+//                         replaces: bucket copy_ (dear/dear_dopt.py:265), ncclReduceScatter
+//                         (common/comm_core/src/communicator.cpp:157-169) and div_ (:306).
+// Kernel B (ag_kernel):   sharded SGD/momentum update + all-gather (push) of the updated
+//                         parameter shard, replaces ncclAllGather (communicator.cpp:171-183),
+//                         the copy-out / div_ / _sgd / fill_ per-parameter loop
+//                         (dear/dear_dopt.py:293-336).
+// gen_kernel:             small one-shot all-reduce / broadcast / reduce / sendrecv /
+//                         all-gather / barrier on a symmetric staging buffer
+//                         (communicator.cpp:130-155,185-242,287-304).
+//
+// Cross-GPU protocol: every rank owns a "signal pad" (uint32 flags indexed
+// [channel][source rank]) inside its symmetric arena.  A producer publishes
+// data with  stores -> bar.sync -> fence.sys -> st.release.sys(flag@peer, epoch)
+// and a consumer observes it with ld.acquire.sys(flag@local) >= epoch followed
+// by plain loads.  Epochs live in device memory (ctrl block) and are advanced
+// by the last CTA of each kernel, so launches carry no host-side sequence
+// number and are CUDA-graph replayable.  Spin waits are bounded: on timeout a
+// status word in host-mapped memory is set and the kernel exits.
+//
+// Data moves over NVLink with 128-bit peer loads (pull, Kernel A) and 128-bit
+// peer stores (push, Kernel B); when an NVLS multicast alias of the bucket is
+// available the same kernels switch to multimem.ld_reduce / multimem.st so the
+// NVSwitch performs the reduction / replication.
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdexcept>
+#include <string>
+#include "dear_common.h"
+
+namespace dear {
+
+constexpr int kThreads = 512;
+constexpr int kMaxSmemSegs = 384;     // PackSeg entries cached in shared memory (12 KiB)
+constexpr int kMaxSmemHyper = 256;    // HyperSeg entries cached in shared memory (8 KiB)
+
+// ----------------------------------------------------------------------------
+// PTX helpers
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// 128-bit load that does not allocate in L1 (peer data is never re-read).
+__device__ __forceinline__ uint4 ld_stream(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_stream(void* p, const uint4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x),
+               "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+// NVLS: the switch reduces the same offset of every bound device and returns the sum.
+__device__ __forceinline__ uint4 multimem_ld_reduce_f32(const void* mc) {
+  uint4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(mc)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ uint4 multimem_ld_reduce_bf16(const void* mc) {
+  uint4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(mc)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ uint4 multimem_ld_reduce_f16(const void* mc) {
+  uint4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.f16x2 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(mc)
+               : "memory");
+  return v;
+}
+// NVLS: one store, replicated by the switch into every bound device.
+__device__ __forceinline__ void multimem_st(void* mc, const uint4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc),
+               "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+
+__device__ __forceinline__ uint32_t* flag_at(void* sig_base, uint32_t chan, int src) {
+  return reinterpret_cast<uint32_t*>(sig_base) + size_t(chan) * kMaxRanks + src;
+}
+
+// Bounded spin until *f >= epoch (wrap-safe).  Returns false on timeout.
+__device__ __forceinline__ bool wait_flag(const uint32_t* f, uint32_t epoch, uint64_t timeout_ns,
+                                          uint32_t* status, uint32_t code) {
+  uint32_t spins = 0;
+  uint64_t t0 = 0;
+  while (static_cast<int32_t>(ld_acquire_sys(f) - epoch) < 0) {
+    ++spins;
+    if (spins > 64) __nanosleep(64);
+    if ((spins & 0xfff) == 0) {
+      uint64_t now = globaltimer_ns();
+      if (t0 == 0) {
+        t0 = now;
+      } else if (now - t0 > timeout_ns) {
+        if (status != nullptr) {
+          *reinterpret_cast<volatile uint32_t*>(status) = code;
+          __threadfence_system();
+        }
+        return false;
+      }
+    }
+  }
+  return true;
+}
+
+// Threads [0, world) each wait for one source rank's flag, then the CTA syncs.
+__device__ __forceinline__ void wait_all_peers(void* sig_local, uint32_t chan, uint32_t epoch,
+                                               int world, uint64_t timeout_ns, uint32_t* status,
+                                               uint32_t code) {
+  if (static_cast<int>(threadIdx.x) < world)
+    wait_flag(flag_at(sig_local, chan, threadIdx.x), epoch, timeout_ns, status, code);
+  __syncthreads();
+}
+
+// Threads [0, world) each publish `epoch` into one peer's pad (slot = my rank).
+// Must be called by the whole CTA after the data writes; includes the bar.sync.
+__device__ __forceinline__ void signal_all_peers(const PeerTable& sig, uint32_t chan, int rank,
+                                                 int world, uint32_t epoch) {
+  if (static_cast<int>(threadIdx.x) < world) {
+    __threadfence_system();
+    st_release_sys(flag_at(sig.ptr[threadIdx.x], chan, rank), epoch);
+  }
+}
+
+// Grid-wide arrival counter.  Returns true (CTA-uniform) for the last CTA to arrive.
+__device__ __forceinline__ bool grid_arrive_is_last(uint32_t* counter) {
+  __shared__ uint32_t s_is_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();                        // release this CTA's writes
+    uint32_t old = atomicAdd(counter, 1u);
+    __threadfence();                               // acquire the other CTAs' writes
+    s_is_last = (old == gridDim.x - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  return s_is_last != 0;
+}
+
+// ----------------------------------------------------------------------------
+// element helpers
+// ----------------------------------------------------------------------------
+template <typename T> struct ElemTraits;
+template <> struct ElemTraits<float> {
+  static constexpr int kPerVec = 4;
+  __device__ static void unpack(const uint4& v, float* f) {
+    f[0] = __uint_as_float(v.x); f[1] = __uint_as_float(v.y);
+    f[2] = __uint_as_float(v.z); f[3] = __uint_as_float(v.w);
+  }
+  __device__ static uint4 pack(const float* f) {
+    return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]),
+                      __float_as_uint(f[3]));
+  }
+  __device__ static uint4 mc_reduce(const void* mc) { return multimem_ld_reduce_f32(mc); }
+};
+template <> struct ElemTraits<__nv_bfloat16> {
+  static constexpr int kPerVec = 8;
+  __device__ static void unpack(const uint4& v, float* f) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      f[2 * i] = __uint_as_float(w[i] << 16);
+      f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+  __device__ static uint4 pack(const float* f) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  __device__ static uint4 mc_reduce(const void* mc) { return multimem_ld_reduce_bf16(mc); }
+};
+template <> struct ElemTraits<__half> {
+  static constexpr int kPerVec = 8;
+  __device__ static void unpack(const uint4& v, float* f) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __half2 h = *reinterpret_cast<const __half2*>(&w[i]);
+      float2 t = __half22float2(h);
+      f[2 * i] = t.x; f[2 * i + 1] = t.y;
+    }
+  }
+  __device__ static uint4 pack(const float* f) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __half2 h = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  __device__ static uint4 mc_reduce(const void* mc) { return multimem_ld_reduce_f16(mc); }
+};
+
+// ----------------------------------------------------------------------------
+// Kernel A — pack + reduce-scatter + scale
+// ----------------------------------------------------------------------------
+template <typename T, int W, bool MC>
+__global__ void __launch_bounds__(kThreads, 1) rs_kernel(const RSParams p) {
+  using Tr = ElemTraits<T>;
+  constexpr int EV = Tr::kPerVec;
+  __shared__ PackSeg s_segs[kMaxSmemSegs];
+
+  const int tid = threadIdx.x;
+  const int world = (W > 0) ? W : p.world;
+  void* sig_local = p.sig.ptr[p.rank];
+  const uint32_t ch_ready = bucket_channel(p.bucket, RS_READY);
+  const uint32_t ch_done = bucket_channel(p.bucket, RS_DONE);
+  uint32_t* epoch_p = p.ctrl + ch_ready;
+  uint32_t* cnt_pack = p.ctrl + kNumChannels + ch_ready;
+  uint32_t* cnt_exit = p.ctrl + kNumChannels + ch_done;
+  const uint32_t e = *reinterpret_cast<volatile uint32_t*>(epoch_p) + 1;
+
+  // (0) my bucket may still be read by a peer's previous reduce-scatter.
+  wait_all_peers(sig_local, ch_done, e - 1, world, p.timeout_ns, p.status, ST_TIMEOUT_RS_DONE);
+
+  // (1) pack: copy this rank's gradients into the symmetric bucket.
+  if (p.segs != nullptr && p.ntiles > 0) {
+    const bool in_smem = p.nseg <= kMaxSmemSegs;
+    if (in_smem) {
+      for (uint32_t i = tid; i < p.nseg; i += kThreads) s_segs[i] = p.segs[i];
+      __syncthreads();
+    }
+    const PackSeg* segs = in_smem ? s_segs : p.segs;
+    char* bucket = reinterpret_cast<char*>(p.grad.ptr[p.rank]);
+    for (uint32_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      const uint32_t si = find_pack_seg(segs, p.nseg, tile);
+      const PackSeg sg = segs[si];
+      const uint64_t off = uint64_t(tile - sg.tile_begin) * kPackTileBytes;
+      const uint64_t left = sg.nbytes - off;
+      const uint32_t nb = left < kPackTileBytes ? uint32_t(left) : kPackTileBytes;
+      char* d = bucket + sg.dst_off + off;
+      const uint32_t nvec = nb >> 4;
+      if (sg.flags & SEG_ZERO_FILL) {
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        for (uint32_t v = tid; v < nvec; v += kThreads) reinterpret_cast<uint4*>(d)[v] = z;
+        for (uint32_t b = (nvec << 4) + tid * 2; b < nb; b += kThreads * 2)
+          *reinterpret_cast<uint16_t*>(d + b) = 0;
+      } else if (sg.src != nullptr) {
+        const char* s = reinterpret_cast<const char*>(sg.src) + off;
+        for (uint32_t v = tid; v < nvec; v += kThreads)
+          reinterpret_cast<uint4*>(d)[v] = ld_stream(s + (size_t(v) << 4));
+        for (uint32_t b = (nvec << 4) + tid * 2; b < nb; b += kThreads * 2)
+          *reinterpret_cast<uint16_t*>(d + b) = *reinterpret_cast<const uint16_t*>(s + b);
+      }
+    }
+  }
+
+  // (2) publish "bucket packed" to every peer once ALL my CTAs are done packing.
+  if (grid_arrive_is_last(cnt_pack)) {
+    signal_all_peers(p.sig, ch_ready, p.rank, world, e);
+    if (tid == 0) *cnt_pack = 0;
+  }
+
+  // (3) wait until every peer's bucket is packed.
+  wait_all_peers(sig_local, ch_ready, e, world, p.timeout_ns, p.status, ST_TIMEOUT_RS_READY);
+
+  // (4) pull-reduce my shard from every peer; fp32 accumulate; fused 1/P scale.
+  {
+    const uint64_t nvec = p.shard_elems / EV;
+    const uint64_t shard_byte_off = uint64_t(p.rank) * p.shard_elems * sizeof(T);
+    const uint64_t gstride = uint64_t(gridDim.x) * kThreads;
+    const float scale = p.scale;
+    if (MC) {
+      const char* mc = reinterpret_cast<const char*>(p.mc_grad) + shard_byte_off;
+      constexpr int U = 4;
+      for (uint64_t v0 = uint64_t(blockIdx.x) * kThreads + tid; v0 < nvec; v0 += gstride * U) {
+        uint4 r[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const uint64_t v = v0 + u * gstride;
+          if (v < nvec) r[u] = Tr::mc_reduce(mc + (v << 4));
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const uint64_t v = v0 + u * gstride;
+          if (v < nvec) {
+            float f[EV];
+            Tr::unpack(r[u], f);
+#pragma unroll
+            for (int k = 0; k < EV; ++k) f[k] *= scale;
+            float4* o = reinterpret_cast<float4*>(p.out + v * EV);
+            o[0] = make_float4(f[0], f[1], f[2], f[3]);
+            if (EV == 8) o[1] = make_float4(f[4], f[5], f[6], f[7]);
+          }
+        }
+      }
+    } else {
+      constexpr int U = (W > 0 && W <= 4) ? 4 : 2;
+      for (uint64_t v0 = uint64_t(blockIdx.x) * kThreads + tid; v0 < nvec; v0 += gstride * U) {
+        float acc[U][EV];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+          for (int k = 0; k < EV; ++k) acc[u][k] = 0.f;
+        if (W > 0) {
+          uint4 r[U][W > 0 ? W : 1];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const uint64_t v = v0 + u * gstride;
+#pragma unroll
+            for (int q = 0; q < (W > 0 ? W : 1); ++q) {
+              if (v < nvec) {
+                const char* base = reinterpret_cast<const char*>(p.grad.ptr[q]) + shard_byte_off;
+                r[u][q] = ld_stream(base + (v << 4));
+              }
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const uint64_t v = v0 + u * gstride;
+            if (v < nvec) {
+#pragma unroll
+              for (int q = 0; q < (W > 0 ? W : 1); ++q) {   // fixed order => deterministic
+                float f[EV];
+                Tr::unpack(r[u][q], f);
+#pragma unroll
+                for (int k = 0; k < EV; ++k) acc[u][k] += f[k];
+              }
+            }
+          }
+        } else {
+          for (int q = 0; q < world; ++q) {
+            const char* base = reinterpret_cast<const char*>(p.grad.ptr[q]) + shard_byte_off;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              const uint64_t v = v0 + u * gstride;
+              if (v < nvec) {
+                float f[EV];
+                Tr::unpack(ld_stream(base + (v << 4)), f);
+#pragma unroll
+                for (int k = 0; k < EV; ++k) acc[u][k] += f[k];
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const uint64_t v = v0 + u * gstride;
+          if (v < nvec) {
+            float4* o = reinterpret_cast<float4*>(p.out + v * EV);
+            o[0] = make_float4(acc[u][0] * scale, acc[u][1] * scale, acc[u][2] * scale,
+                               acc[u][3] * scale);
+            if (EV == 8)
+              o[1] = make_float4(acc[u][EV - 4] * scale, acc[u][EV - 3] * scale,
+                                 acc[u][EV - 2] * scale, acc[u][EV - 1] * scale);
+          }
+        }
+      }
+    }
+  }
+
+  // (5) tell every peer I am done reading its bucket; advance the epoch.
+  if (grid_arrive_is_last(cnt_exit)) {
+    signal_all_peers(p.sig, ch_done, p.rank, world, e);
+    if (tid == 0) {
+      *cnt_exit = 0;
+      *epoch_p = e;
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------
+// Kernel B — sharded SGD + all-gather push
+// ----------------------------------------------------------------------------
+template <typename T, int W, bool MC>
+__global__ void __launch_bounds__(kThreads, 1) ag_kernel(const AGParams p) {
+  using Tr = ElemTraits<T>;
+  constexpr int EV = Tr::kPerVec;
+  __shared__ HyperSeg s_hyper[kMaxSmemHyper];
+
+  const int tid = threadIdx.x;
+  const int world = (W > 0) ? W : p.world;
+  void* sig_local = p.sig.ptr[p.rank];
+  const uint32_t ch_arrive = bucket_channel(p.bucket, AG_ARRIVE);
+  const uint32_t ch_pushed = bucket_channel(p.bucket, AG_PUSHED);
+  uint32_t* epoch_p = p.ctrl + ch_arrive;
+  uint32_t* cnt_exit = p.ctrl + kNumChannels + ch_pushed;
+  const uint32_t e = *reinterpret_cast<volatile uint32_t*>(epoch_p) + 1;
+
+  const bool hyper_smem = p.nhyper <= kMaxSmemHyper;
+  if (p.do_update && hyper_smem) {
+    for (uint32_t i = tid; i < p.nhyper; i += kThreads) s_hyper[i] = p.hyper[i];
+  }
+  const HyperSeg* hyper = hyper_smem ? s_hyper : p.hyper;
+
+  // (0) nobody may overwrite a peer's parameters before that peer finished the
+  // backward pass that still reads them: rendezvous at kernel entry.
+  if (p.entry_barrier) {
+    if (blockIdx.x == 0) signal_all_peers(p.sig, ch_arrive, p.rank, world, e);
+    wait_all_peers(sig_local, ch_arrive, e, world, p.timeout_ns, p.status, ST_TIMEOUT_AG_ARRIVE);
+  } else {
+    __syncthreads();
+  }
+
+  // (1) update my shard and push it into every rank's parameter bucket.
+  {
+    const uint64_t nvec = p.shard_elems / EV;
+    const uint64_t shard_elem_off = uint64_t(p.rank) * p.shard_elems;
+    const uint64_t gstride = uint64_t(gridDim.x) * kThreads;
+    const char* local_param = reinterpret_cast<const char*>(p.param.ptr[p.rank]);
+    for (uint64_t v = uint64_t(blockIdx.x) * kThreads + tid; v < nvec; v += gstride) {
+      const uint64_t ge = shard_elem_off + v * EV;     // element offset within the bucket
+      float pv[EV];
+      if (p.master_shard != nullptr) {
+        const float4* m = reinterpret_cast<const float4*>(p.master_shard + v * EV);
+        float4 a = m[0];
+        pv[0] = a.x; pv[1] = a.y; pv[2] = a.z; pv[3] = a.w;
+        if (EV == 8) { float4 b = m[1]; pv[EV - 4] = b.x; pv[EV - 3] = b.y; pv[EV - 2] = b.z; pv[EV - 1] = b.w; }
+      } else {
+        Tr::unpack(*reinterpret_cast<const uint4*>(local_param + ge * sizeof(T)), pv);
+      }
+      if (p.do_update) {
+        float gv[EV], mv[EV];
+        {
+          const float4* g = reinterpret_cast<const float4*>(p.grad_shard + v * EV);
+          float4 a = g[0];
+          gv[0] = a.x; gv[1] = a.y; gv[2] = a.z; gv[3] = a.w;
+          if (EV == 8) { float4 b = g[1]; gv[EV - 4] = b.x; gv[EV - 3] = b.y; gv[EV - 2] = b.z; gv[EV - 1] = b.w; }
+        }
+        const bool has_mom = p.mom_shard != nullptr;
+        if (has_mom && !p.first_step) {
+          const float4* m = reinterpret_cast<const float4*>(p.mom_shard + v * EV);
+          float4 a = m[0];
+          mv[0] = a.x; mv[1] = a.y; mv[2] = a.z; mv[3] = a.w;
+          if (EV == 8) { float4 b = m[1]; mv[EV - 4] = b.x; mv[EV - 3] = b.y; mv[EV - 2] = b.z; mv[EV - 1] = b.w; }
+        } else {
+#pragma unroll
+          for (int k = 0; k < EV; ++k) mv[k] = 0.f;
+        }
+        const HyperSeg h = hyper[p.nhyper == 1 ? 0 : find_hyper(hyper, p.nhyper, ge)];
+#pragma unroll
+        for (int k = 0; k < EV; ++k) pv[k] = sgd_update(pv[k], gv[k], mv[k], h, p.first_step != 0, has_mom);
+        if (has_mom && h.momentum > 0.f) {
+          float4* m = reinterpret_cast<float4*>(p.mom_shard + v * EV);
+          m[0] = make_float4(mv[0], mv[1], mv[2], mv[3]);
+          if (EV == 8) m[1] = make_float4(mv[EV - 4], mv[EV - 3], mv[EV - 2], mv[EV - 1]);
+        }
+        if (p.master_shard != nullptr) {
+          float4* m = reinterpret_cast<float4*>(p.master_shard + v * EV);
+          m[0] = make_float4(pv[0], pv[1], pv[2], pv[3]);
+          if (EV == 8) m[1] = make_float4(pv[EV - 4], pv[EV - 3], pv[EV - 2], pv[EV - 1]);
+        }
+      }
+      const uint4 outv = Tr::pack(pv);
+      const uint64_t boff = ge * sizeof(T);
+      if (MC) {
+        multimem_st(reinterpret_cast<char*>(p.mc_param) + boff, outv);
+      } else if (W > 0) {
+#pragma unroll
+        for (int k = 0; k < (W > 0 ? W : 1); ++k) {
+          const int q = (p.rank + k) % (W > 0 ? W : 1);   // own copy first, then rotate over peers
+          st_stream(reinterpret_cast<char*>(p.param.ptr[q]) + boff, outv);
+        }
+      } else {
+        for (int k = 0; k < world; ++k) {
+          const int q = (p.rank + k) % world;
+          st_stream(reinterpret_cast<char*>(p.param.ptr[q]) + boff, outv);
+        }
+      }
+    }
+    // zero the consumed local gradient bucket (grad-as-bucket-view mode only).
+    if (p.zero_grad != nullptr) {
+      const uint64_t zvec = p.zero_bytes >> 4;
+      const uint4 z = make_uint4(0, 0, 0, 0);
+      uint4* zp = reinterpret_cast<uint4*>(p.zero_grad);
+      for (uint64_t v = uint64_t(blockIdx.x) * kThreads + tid; v < zvec; v += gstride) zp[v] = z;
+    }
+  }
+
+  // (2) once ALL my CTAs pushed: publish, then wait until every peer's shard has
+  // landed here.  The kernel (and therefore the stream event the next forward
+  // waits on) completes only when the whole bucket is up to date on this GPU.
+  if (grid_arrive_is_last(cnt_exit)) {
+    signal_all_peers(p.sig, ch_pushed, p.rank, world, e);
+    wait_all_peers(sig_local, ch_pushed, e, world, p.timeout_ns, p.status, ST_TIMEOUT_AG_PUSHED);
+    if (tid == 0) {
+      *cnt_exit = 0;
+      *epoch_p = e;
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------
+// General ops on the symmetric staging buffer
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ void copy_bytes_grid(void* dst, const void* src, uint64_t nbytes) {
+  const uint64_t gtid = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const uint64_t gstride = uint64_t(gridDim.x) * blockDim.x;
+  const uintptr_t a = reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src);
+  if ((a & 15) == 0) {
+    const uint64_t nvec = nbytes >> 4;
+    for (uint64_t v = gtid; v < nvec; v += gstride)
+      st_stream(reinterpret_cast<char*>(dst) + (v << 4),
+                ld_stream(reinterpret_cast<const char*>(src) + (v << 4)));
+    for (uint64_t b = (nvec << 4) + gtid; b < nbytes; b += gstride)
+      reinterpret_cast<char*>(dst)[b] = reinterpret_cast<const char*>(src)[b];
+  } else if ((a & 3) == 0) {
+    const uint64_t nw = nbytes >> 2;
+    for (uint64_t v = gtid; v < nw; v += gstride)
+      reinterpret_cast<uint32_t*>(dst)[v] = reinterpret_cast<const uint32_t*>(src)[v];
+    for (uint64_t b = (nw << 2) + gtid; b < nbytes; b += gstride)
+      reinterpret_cast<char*>(dst)[b] = reinterpret_cast<const char*>(src)[b];
+  } else {
+    for (uint64_t b = gtid; b < nbytes; b += gstride)
+      reinterpret_cast<char*>(dst)[b] = reinterpret_cast<const char*>(src)[b];
+  }
+}
+
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <> __device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
+
+// dst[0:n] = scale * sum_q stage_q[src_off : src_off+n]   (fp32 accumulate, fixed order)
+template <typename T>
+__device__ __forceinline__ void reduce_from_peers(const GenParams& p, T* dst, uint64_t src_off,
+                                                  uint64_t n) {
+  using Tr = ElemTraits<T>;
+  constexpr int EV = Tr::kPerVec;
+  const uint64_t gtid = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const uint64_t gstride = uint64_t(gridDim.x) * blockDim.x;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && ((src_off * sizeof(T)) & 15) == 0;
+  uint64_t done = 0;
+  if (aligned) {
+    const uint64_t nvec = n / EV;
+    for (uint64_t v = gtid; v < nvec; v += gstride) {
+      float acc[EV];
+#pragma unroll
+      for (int k = 0; k < EV; ++k) acc[k] = 0.f;
+      for (int q = 0; q < p.world; ++q) {
+        float f[EV];
+        Tr::unpack(ld_stream(reinterpret_cast<const char*>(p.stage.ptr[q]) + (src_off + v * EV) * sizeof(T)), f);
+#pragma unroll
+        for (int k = 0; k < EV; ++k) acc[k] += f[k];
+      }
+#pragma unroll
+      for (int k = 0; k < EV; ++k) acc[k] *= p.scale;
+      *reinterpret_cast<uint4*>(dst + v * EV) = Tr::pack(acc);
+    }
+    done = nvec * EV;
+  }
+  for (uint64_t i = done + gtid; i < n; i += gstride) {
+    float acc = 0.f;
+    for (int q = 0; q < p.world; ++q)
+      acc += to_f32<T>(reinterpret_cast<const T*>(p.stage.ptr[q])[src_off + i]);
+    dst[i] = from_f32<T>(acc * p.scale);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 1) gen_kernel(const GenParams p) {
+  const int tid = threadIdx.x;
+  const int world = p.world;
+  void* sig_local = p.sig.ptr[p.rank];
+  uint32_t* epoch_p = p.ctrl + p.ready_chan;
+  uint32_t* cnt_a = p.ctrl + kNumChannels + p.ready_chan;
+  uint32_t* cnt_b = p.ctrl + kNumChannels + p.done_chan;
+  const uint32_t e = *reinterpret_cast<volatile uint32_t*>(epoch_p) + 1;
+  const uint64_t nbytes = p.nelems * p.elem_bytes;
+
+  // (0) staging buffers are free once every peer finished the previous op.
+  wait_all_peers(sig_local, p.done_chan, e - 1, world, p.timeout_ns, p.status, ST_TIMEOUT_GENERAL);
+
+  // (1) stage my contribution.
+  const bool contributes = (p.op == GEN_ALLREDUCE) || (p.op == GEN_REDUCE) || (p.op == GEN_ALLGATHER) ||
+                           (p.op == GEN_REDUCE_SCATTER) || (p.op == GEN_SENDRECV) ||
+                           (p.op == GEN_BCAST && p.rank == p.root_or_peer);
+  if (contributes && p.src != nullptr && nbytes > 0) copy_bytes_grid(p.stage.ptr[p.rank], p.src, nbytes);
+
+  // (2) publish.
+  if (grid_arrive_is_last(cnt_a)) {
+    signal_all_peers(p.sig, p.ready_chan, p.rank, world, e);
+    if (tid == 0) *cnt_a = 0;
+  }
+
+  // (3) wait for the producers this op depends on.
+  if (p.op == GEN_BCAST) {
+    if (tid == 0) wait_flag(flag_at(sig_local, p.ready_chan, p.root_or_peer), e, p.timeout_ns, p.status, ST_TIMEOUT_GENERAL);
+    __syncthreads();
+  } else if (p.op == GEN_SENDRECV) {
+    if (tid == 0) wait_flag(flag_at(sig_local, p.ready_chan, p.root_or_peer), e, p.timeout_ns, p.status, ST_TIMEOUT_GENERAL);
+    __syncthreads();
+  } else {
+    wait_all_peers(sig_local, p.ready_chan, e, world, p.timeout_ns, p.status, ST_TIMEOUT_GENERAL);
+  }
+
+  // (4) the op itself.
+  if (p.dst != nullptr && nbytes > 0) {
+    switch (p.op) {
+      case GEN_ALLREDUCE:
+        reduce_from_peers<T>(p, reinterpret_cast<T*>(p.dst), 0, p.nelems);
+        break;
+      case GEN_REDUCE:
+        if (p.rank == p.root_or_peer) reduce_from_peers<T>(p, reinterpret_cast<T*>(p.dst), 0, p.nelems);
+        break;
+      case GEN_REDUCE_SCATTER: {
+        const uint64_t per = p.nelems / world;
+        reduce_from_peers<T>(p, reinterpret_cast<T*>(p.dst), per * p.rank, per);
+        break;
+      }
+      case GEN_BCAST:
+      case GEN_SENDRECV:
+        copy_bytes_grid(p.dst, p.stage.ptr[p.root_or_peer], nbytes);
+        break;
+      case GEN_ALLGATHER:
+        for (int q = 0; q < world; ++q)
+          copy_bytes_grid(reinterpret_cast<char*>(p.dst) + uint64_t(q) * (p.dst_stride_bytes ? p.dst_stride_bytes : nbytes),
+                          p.stage.ptr[q], nbytes);
+        break;
+      default:
+        break;
+    }
+  }
+
+  // (5) done reading peers' staging; advance the epoch.
+  if (grid_arrive_is_last(cnt_b)) {
+    signal_all_peers(p.sig, p.done_chan, p.rank, world, e);
+    if (tid == 0) {
+      *cnt_b = 0;
+      *epoch_p = e;
+    }
+  }
+}
+
+// Multi-tensor fused SGD for the single-GPU path is Kernel B with world == 1.
+
+// ----------------------------------------------------------------------------
+// launchers
+// ----------------------------------------------------------------------------
+static void check_launch(const char* what) {
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess)
+    throw std::runtime_error(std::string("dear: launch of ") + what + " failed: " + cudaGetErrorString(err));
+}
+
+template <typename T, bool MC>
+static void launch_rs_w(const RSParams& p, int grid, cudaStream_t s) {
+  switch (p.world) {
+    case 1: rs_kernel<T, 1, MC><<<grid, kThreads, 0, s>>>(p); break;
+    case 2: rs_kernel<T, 2, MC><<<grid, kThreads, 0, s>>>(p); break;
+    case 4: rs_kernel<T, 4, MC><<<grid, kThreads, 0, s>>>(p); break;
+    case 8: rs_kernel<T, 8, MC><<<grid, kThreads, 0, s>>>(p); break;
+    default: rs_kernel<T, 0, MC><<<grid, kThreads, 0, s>>>(p); break;
+  }
+}
+
+void launch_rs(const RSParams& p, int grid, cudaStream_t s) {
+  const bool mc = p.mc_grad != nullptr;
+  switch (p.dtype) {
+    case DT_F32: mc ? launch_rs_w<float, true>(p, grid, s) : launch_rs_w<float, false>(p, grid, s); break;
+    case DT_BF16: mc ? launch_rs_w<__nv_bfloat16, true>(p, grid, s) : launch_rs_w<__nv_bfloat16, false>(p, grid, s); break;
+    case DT_F16: mc ? launch_rs_w<__half, true>(p, grid, s) : launch_rs_w<__half, false>(p, grid, s); break;
+    default: throw std::runtime_error("dear: unsupported gradient dtype");
+  }
+  check_launch("rs_kernel");
+}
+
+template <typename T, bool MC>
+static void launch_ag_w(const AGParams& p, int grid, cudaStream_t s) {
+  switch (p.world) {
+    case 1: ag_kernel<T, 1, MC><<<grid, kThreads, 0, s>>>(p); break;
+    case 2: ag_kernel<T, 2, MC><<<grid, kThreads, 0, s>>>(p); break;
+    case 4: ag_kernel<T, 4, MC><<<grid, kThreads, 0, s>>>(p); break;
+    case 8: ag_kernel<T, 8, MC><<<grid, kThreads, 0, s>>>(p); break;
+    default: ag_kernel<T, 0, MC><<<grid, kThreads, 0, s>>>(p); break;
+  }
+}
+
+void launch_ag(const AGParams& p, int grid, cudaStream_t s) {
+  const bool mc = p.mc_param != nullptr;
+  switch (p.dtype) {
+    case DT_F32: mc ? launch_ag_w<float, true>(p, grid, s) : launch_ag_w<float, false>(p, grid, s); break;
+    case DT_BF16: mc ? launch_ag_w<__nv_bfloat16, true>(p, grid, s) : launch_ag_w<__nv_bfloat16, false>(p, grid, s); break;
+    case DT_F16: mc ? launch_ag_w<__half, true>(p, grid, s) : launch_ag_w<__half, false>(p, grid, s); break;
+    default: throw std::runtime_error("dear: unsupported parameter dtype");
+  }
+  check_launch("ag_kernel");
+}
+
+void launch_gen(const GenParams& p, int grid, cudaStream_t s) {
+  switch (p.dtype) {
+    case DT_BF16: gen_kernel<__nv_bfloat16><<<grid, kThreads, 0, s>>>(p); break;
+    case DT_F16: gen_kernel<__half><<<grid, kThreads, 0, s>>>(p); break;
+    default: gen_kernel<float><<<grid, kThreads, 0, s>>>(p); break;
+  }
+  check_launch("gen_kernel");
+}
+
+}  // namespace dear
