@@ -1,0 +1,448 @@
+"""DeAR distributed optimizer: decoupled all-reduce with tensor fusion.
+
+Public behaviour follows the reference's ``dear.DistributedOptimizer``
+(dear/dear_dopt.py:56-398): gradients of iteration *t* are reduce-scattered per fusion
+bucket while the backward pass is still running, and the matching all-gather plus the
+SGD update are overlapped with the forward pass of iteration *t+1*.  The result is
+mathematically identical to synchronous data-parallel SGD.
+
+B200-first redesign:
+  * parameters live in flat symmetric *parameter buckets* (``p.data`` is a view) and the
+    update is **sharded**: each rank updates 1/P of every bucket (momentum and fp32 master
+    state are sharded too) and pushes the result into every peer's bucket — Kernel B;
+  * gradients are handed to Kernel A by pointer (``p.grad`` is whatever autograd produced;
+    no per-parameter copy/scale/zero kernels), reduced over NVLink and scaled by 1/P once;
+  * nothing on the hot path blocks the host: ordering is stream events and in-kernel flags.
+    The reference blocks on ``cudaStreamSynchronize`` per bucket (dear/dear_dopt.py:284,352);
+  * all parameter updates are issued at ``step()`` (asynchronously, in forward order), so the
+    last iteration's update is not lost (reference defect, dear/dear_dopt.py:371) and an
+    extra forward pass never re-applies a gradient (reference defect, :278);
+  * each parameter uses the hyper-parameters of *its own* param group (the reference loops
+    over all groups for every parameter, dear/dear_dopt.py:312-335);
+  * reduce-scatters are issued in a rank-consistent order (descending bucket index), and
+    buckets whose parameters received no gradient are flushed at ``step()`` with zeros.
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from .. import runtime
+from .backends import HyperSpec, NativeBackend, TorchBackend
+from .bucket import BucketPlan
+
+THRESHOLD = 25            # MB, reference default (dear/dear_dopt.py:43)
+NUM_NEARBY_LAYERS = 4     # reference default (dear/dear_dopt.py:42)
+
+
+def _dense_like(p: torch.Tensor) -> bool:
+    return p.is_contiguous() or p.is_contiguous(memory_format=torch.channels_last) or \
+        (p.dim() == 5 and p.is_contiguous(memory_format=torch.channels_last_3d))
+
+
+class DearEngine:
+    """Buffers, hooks and the per-bucket state machine behind ``DistributedOptimizer``."""
+
+    def __init__(self, optimizer: torch.optim.Optimizer, model: nn.Module, *, threshold=THRESHOLD,
+                 num_nearby_layers=NUM_NEARBY_LAYERS, exclude_parts: str = "", policy=None, verbose=True):
+        if not runtime.is_initialized():
+            runtime.init()
+        self.opt = optimizer
+        self.model = model
+        self.rank = runtime.rank()
+        self.world = runtime.size()
+        self.device = runtime.device()
+        self.backend_name = runtime.backend()
+        self.exclude_reducescatter = "reducescatter" in exclude_parts
+        self.exclude_allgather = "allgather" in exclude_parts
+        self.verbose = verbose and self.rank == 0
+        self.num_steps = 0
+        self.threshold = threshold
+        self.num_nearby_layers = num_nearby_layers
+        self._mom_initialised = False
+        self._hooks = []
+        self._closed = False
+        self._step_callbacks = []          # called at the re-bucketing safe point
+        self._safe_point_actions = []
+
+        for p in model.parameters():
+            if p.requires_grad and p.device.type != self.device.type:
+                raise RuntimeError("model parameters live on %s but the runtime device is %s" % (p.device, self.device))
+        self.group_of: Dict[nn.Parameter, int] = {}
+        for gi, grp in enumerate(optimizer.param_groups):
+            for p in grp["params"]:
+                self.group_of[p] = gi
+
+        self.plan = BucketPlan(model, self.world)
+        for s in self.plan.slots:
+            if s.param not in self.group_of:
+                raise ValueError("parameter %s requires grad but is not in any optimizer param group" % s.name)
+        if policy is not None:
+            self._apply_policy(policy)
+        elif threshold is not None:
+            self.plan.group_by_threshold(threshold)
+        else:
+            self.plan.group_by_nearby_layers(num_nearby_layers)
+        if self.verbose:
+            print("# of parameters: ", self.plan.num_parameters)
+        self._check_plan_consistency()
+        self._build(initial=True)
+        self._register_hooks()
+
+    # ------------------------------------------------------------------ plan / buffers
+    def _apply_policy(self, policy):
+        kind = policy[0]
+        if kind == "threshold":
+            self.plan.group_by_threshold(policy[1])
+        elif kind == "nearby":
+            self.plan.group_by_nearby_layers(policy[1])
+        elif kind == "flags":
+            self.plan.group_by_flags(policy[1])
+        elif kind == "per_module":
+            self.plan.group_per_module()
+        elif kind == "explicit":
+            self.plan.group_explicit(policy[1])
+        else:
+            raise ValueError("unknown bucketing policy %r" % (policy,))
+
+    def _check_plan_consistency(self):
+        if self.world == 1 or os.environ.get("DEAR_SKIP_PLAN_CHECK"):
+            return
+        import hashlib
+        h = hashlib.sha1(repr(self.plan.signature()).encode()).hexdigest()
+        h0 = runtime.broadcast_object(h, src=0)
+        if h != h0:
+            raise RuntimeError("rank %d built a different bucket plan than rank 0 (models differ?)" % self.rank)
+
+    def _make_backend(self):
+        if self.backend_name in ("b200", "emu"):
+            return NativeBackend(runtime.communicator(), self.plan, self.rank, self.world, self.device)
+        return TorchBackend(runtime.group(), self.plan, self.rank, self.world, self.device)
+
+    @torch.no_grad()
+    def _build(self, initial: bool, carry: Optional[dict] = None):
+        """Allocate buckets for the current plan and move parameters (and state) into them."""
+        plan = self.plan
+        self.backend = self._make_backend()
+        be = self.backend
+        self.steal = be.steal_grads
+        self._param_view: Dict[nn.Parameter, torch.Tensor] = {}
+        self._grad_view: Dict[nn.Parameter, torch.Tensor] = {}
+        for b in plan.buckets:
+            pbuf, gbuf = be.param_buffer(b.index), be.grad_buffer(b.index)
+            for s in b.slots:
+                p = s.param
+                if not _dense_like(p.data):
+                    p.data = p.data.contiguous()
+                pv = torch.as_strided(pbuf, p.shape, p.stride(), s.start)
+                gv = torch.as_strided(gbuf, p.shape, p.stride(), s.start)
+                pv.copy_(p.data)
+                p.data = pv
+                self._param_view[p] = pv
+                self._grad_view[p] = gv
+                if self.steal:
+                    p.grad = None
+                else:
+                    p.grad = gv
+        be.init_master_shards()
+        if carry is not None:
+            self._restore_state(carry)
+        nb = len(plan.buckets)
+        self._n_params = [len(b.slots) for b in plan.buckets]
+        self._arrived = [[False] * n for n in self._n_params]
+        self._n_arrived = [0] * nb
+        self._complete = [False] * nb
+        self._rs_launched = [False] * nb
+        self._next_rs = nb - 1
+        self._pending = [False] * nb
+        self._any_pending = False
+        self._inflight: List[torch.Tensor] = []
+        self._src = [[0] * n for n in self._n_params]
+        self._flags = [[0] * n for n in self._n_params]
+        self._dst_off = [[s.start * s.param.element_size() for s in b.slots] for b in plan.buckets]
+        self._nbytes = [[s.numel * s.param.element_size() for s in b.slots] for b in plan.buckets]
+        self._hyper_key = [None] * nb
+        self._module_bucket = list(plan.module_bucket)
+        if self.verbose:
+            print(plan.describe())
+
+    # ------------------------------------------------------------------ hooks
+    def _register_hooks(self):
+        if not self.exclude_allgather:
+            for mi, module in enumerate(self.plan.modules):
+                self._hooks.append(module.register_forward_pre_hook(self._make_pre_hook(mi)))
+        if not self.exclude_reducescatter:
+            for s in self.plan.slots:
+                self._hooks.append(s.param.register_post_accumulate_grad_hook(self._on_grad))
+
+    def _make_pre_hook(self, mi):
+        def hook(module, inputs):
+            if self._any_pending:
+                self._wait_bucket(self._module_bucket[mi])
+            if self._safe_point_actions and mi == len(self._module_bucket) - 1 and torch.is_grad_enabled():
+                self._run_safe_point()
+        return hook
+
+    def _wait_bucket(self, g):
+        if self._pending[g]:
+            self.backend.wait_bucket(g)
+            self._pending[g] = False
+            # every all-gather is queued behind every reduce-scatter of the same step, so once
+            # the compute stream has waited on any of them the gradients may be released
+            self._inflight.clear()
+            if not any(self._pending):
+                self._any_pending = False
+
+    def _on_grad(self, p):
+        s = self.plan.slot_of[p]
+        g, i = s.bucket, s.index_in_bucket
+        if self._rs_launched[g] or self._arrived[g][i]:
+            raise RuntimeError(
+                "gradient for %s arrived twice before step(): gradient accumulation over several "
+                "backward passes is not supported by the decoupled all-reduce (call step() after "
+                "every backward, as in the reference)" % s.name)
+        grad = p.grad
+        if self.steal:
+            if (grad.dtype == p.dtype and grad.stride() == p.stride() and grad.data_ptr() % 16 == 0
+                    and not grad.is_sparse):
+                self._src[g][i] = grad.data_ptr()
+            else:
+                self._grad_view[p].copy_(grad)
+                self._src[g][i] = 0
+            self._flags[g][i] = 0
+            self._inflight.append(grad)
+        else:
+            gv = self._grad_view[p]
+            if grad.data_ptr() != gv.data_ptr():
+                gv.copy_(grad)
+                p.grad = gv
+        self._arrived[g][i] = True
+        self._n_arrived[g] += 1
+        if self._n_arrived[g] == self._n_params[g]:
+            self._complete[g] = True
+            self._drain_rs()
+
+    def _drain_rs(self, force=False):
+        """Launch reduce-scatters in descending bucket order (identical on every rank)."""
+        while self._next_rs >= 0 and (force or self._complete[self._next_rs]):
+            g = self._next_rs
+            if not self._complete[g]:
+                for i, ok in enumerate(self._arrived[g]):
+                    if not ok:        # no gradient this iteration: contribute zeros
+                        self._src[g][i] = 0
+                        self._flags[g][i] = 1 if self.steal else 0
+            if self.steal:
+                self.backend.set_pack(g, self._src[g], self._dst_off[g], self._nbytes[g], self._flags[g])
+            self.backend.reduce_scatter(g, True)
+            self._rs_launched[g] = True
+            self._next_rs -= 1
+
+    # ------------------------------------------------------------------ hyper-parameters
+    def _refresh_hyper(self):
+        groups = self.opt.param_groups
+        key_all = tuple((g["lr"], g.get("weight_decay", 0.0), g.get("momentum", 0.0), g.get("dampening", 0.0),
+                         bool(g.get("nesterov", False))) for g in groups)
+        for b in self.plan.buckets:
+            if self._hyper_key[b.index] == key_all:
+                continue
+            segs = []
+            for end, gi in self.plan.hyper_segments(b.index, self.group_of):
+                lr, wd, mom, damp, nest = key_all[gi]
+                segs.append((int(end), float(lr), float(wd), float(mom), float(damp), bool(nest)))
+            self.backend.set_hyper(b.index, HyperSpec(segs))
+            self._hyper_key[b.index] = key_all
+
+    # ------------------------------------------------------------------ step
+    def step(self):
+        be = self.backend
+        nb = len(self.plan.buckets)
+        if not self.exclude_reducescatter:
+            self._drain_rs(force=True)
+        if not self.exclude_allgather:
+            self._refresh_hyper()
+            be.fence()
+            first = not self._mom_initialised
+            for g in range(nb):
+                be.allgather_update(g, True, first, zero_grad=not self.steal)
+                self._pending[g] = True
+            self._any_pending = True
+            self._mom_initialised = True
+        else:
+            be.wait_all()
+            self._inflight.clear()
+        if self.steal:
+            for s in self.plan.slots:
+                s.param.grad = None
+        # reset the per-iteration state machine
+        for g in range(nb):
+            if self._n_arrived[g]:
+                self._arrived[g] = [False] * self._n_params[g]
+                self._n_arrived[g] = 0
+            self._complete[g] = False
+            self._rs_launched[g] = False
+        self._next_rs = nb - 1
+        self.num_steps += 1
+        for cb in self._step_callbacks:
+            cb()
+
+    def synchronize(self, host: bool = True):
+        """Make all outstanding updates visible to the current stream (and the host)."""
+        if self._any_pending:
+            self.backend.wait_all()
+            self._pending = [False] * len(self._pending)
+            self._any_pending = False
+        self._inflight.clear()
+        if host:
+            self.backend.synchronize()
+            if self.device.type == "cuda":
+                torch.cuda.current_stream(self.device).synchronize()
+
+    # ------------------------------------------------------------------ re-bucketing
+    def request_rebucket(self, policy):
+        """Re-lay-out the buckets at the next safe point (last module's forward pre-hook of a
+        training forward; reference dear/dopt_rsag_bo.py:317-320)."""
+        self._safe_point_actions.append(policy)
+
+    def _run_safe_point(self):
+        policy = self._safe_point_actions[-1]
+        self._safe_point_actions.clear()
+        self.rebucket(policy)
+
+    @torch.no_grad()
+    def _gather_state(self) -> dict:
+        """Full (un-sharded) optimizer state per parameter name: momentum and fp32 master."""
+        from ..utils.checkpoint import gather_sharded
+        out = {"momentum": {}, "master": {}, "mom_init": self._mom_initialised}
+        for b in self.plan.buckets:
+            g = b.index
+            for kind, shard in (("momentum", self.backend.mom_shard[g]), ("master", self.backend.master_shard[g])):
+                if shard is None:
+                    continue
+                full = gather_sharded(shard, self.world)
+                for s in b.slots:
+                    out[kind][s.name] = full[s.start:s.end].clone()
+        return out
+
+    @torch.no_grad()
+    def _restore_state(self, carry: dict):
+        be = self.backend
+        self._mom_initialised = bool(carry.get("mom_init", False))
+        for b in self.plan.buckets:
+            g = b.index
+            lo, hi = self.rank * b.shard_numel, (self.rank + 1) * b.shard_numel
+            for kind in ("momentum", "master"):
+                vals = carry.get(kind, {})
+                if not any(s.name in vals for s in b.slots):
+                    continue
+                if kind == "momentum":
+                    be.ensure_momentum(g)
+                    shard = be.mom_shard[g]
+                else:
+                    shard = be.master_shard[g]
+                    if shard is None:
+                        continue
+                for s in b.slots:
+                    if s.name not in vals:
+                        continue
+                    a, z = max(s.start, lo), min(s.end, hi)
+                    if a < z:
+                        shard[a - lo:z - lo].copy_(vals[s.name].reshape(-1)[a - s.start:z - s.start])
+
+    def rebucket(self, policy):
+        """Collective: switch to a new bucketing policy, migrating parameters and sharded state."""
+        self.synchronize(host=True)
+        carry = self._gather_state()
+        old_backend = self.backend
+        self._apply_policy(policy)
+        self._build(initial=False, carry=carry)
+        del old_backend
+        runtime.barrier()
+
+    def close(self):
+        if self._closed:
+            return
+        self._closed = True
+        for h in self._hooks:
+            h.remove()
+        self._hooks.clear()
+        self.synchronize(host=True)
+
+
+# =====================================================================================
+# optimizer facade
+# =====================================================================================
+class _DistributedOptimizer(torch.optim.Optimizer):
+    """Mixed into a dynamic subclass of the user's optimizer class (the Horovod idiom the
+    reference uses, dear/dear_dopt.py:395-398)."""
+
+    def __init__(self, params, model, threshold=THRESHOLD, num_nearby_layers=NUM_NEARBY_LAYERS,
+                 exclude_parts="", policy=None, verbose=True):
+        super(self.__class__, self).__init__(params)
+        if not isinstance(self, torch.optim.SGD):
+            raise TypeError(
+                "the decoupled all-reduce fuses the SGD update (momentum / dampening / nesterov / "
+                "weight decay) into the all-gather; got %s. Use torch.optim.SGD (as the reference does, "
+                "dear/dear_dopt.py:310-336) or parallel.baselines for other optimizers."
+                % type(self).__mro__[1].__name__)
+        for g in self.param_groups:
+            if g.get("maximize", False):
+                raise ValueError("maximize=True is not supported")
+        self._dear = DearEngine(self, model, threshold=threshold, num_nearby_layers=num_nearby_layers,
+                                exclude_parts=exclude_parts, policy=policy, verbose=verbose)
+
+    # -- torch.optim.Optimizer API ---------------------------------------------------
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        self._dear.step()
+        return loss
+
+    def zero_grad(self, set_to_none: bool = True):
+        """No-op, like the reference (dear/dear_dopt.py:338-339): gradients are consumed by the
+        reduce-scatter and released by ``step()``."""
+        return None
+
+    def synchronize(self):
+        """Block until every outstanding parameter update has landed (host-visible)."""
+        self._dear.synchronize(host=True)
+
+    flush = synchronize
+
+    @property
+    def engine(self) -> DearEngine:
+        return self._dear
+
+    def state_dict(self):
+        from ..utils.checkpoint import optimizer_state_dict
+        return optimizer_state_dict(self)
+
+    def load_state_dict(self, state_dict):
+        from ..utils.checkpoint import load_optimizer_state_dict
+        return load_optimizer_state_dict(self, state_dict)
+
+
+def DistributedOptimizer(optimizer, model, compression=None, is_sparse=False, density=0.001, seq_layernames=None,
+                         layerwise_times=None, norm_clip=None, threshold=None, writer=None, gradient_path=None,
+                         fp16=False, mgwfbp=False, rdma=False, multi_job_scheduling=False, exclude_parts="",
+                         num_nearby_layers=None, policy=None, verbose=True):
+    """Wrap ``optimizer`` (an ``torch.optim.SGD``) for DeAR data-parallel training of ``model``.
+
+    Signature-compatible with the reference factory (dear/dear_dopt.py:381-398): the Horovod-era
+    keyword arguments are accepted; those that have no meaning here are ignored.  Unlike the
+    reference, ``threshold`` (MB; default 25) and ``num_nearby_layers`` are honoured instead of
+    being module constants:  ``threshold=None, num_nearby_layers=k`` selects the nearby-layer
+    policy (``k=1`` is "DeAR without tensor fusion").
+    """
+    if threshold in (None, 0) and num_nearby_layers is None:
+        threshold = float(os.environ.get("DEAR_THRESHOLD_MB", THRESHOLD))
+    elif threshold in (None, 0):
+        threshold = None
+    cls = type(optimizer.__class__.__name__, (optimizer.__class__,), dict(_DistributedOptimizer.__dict__))
+    return cls(optimizer.param_groups, model, threshold=threshold,
+               num_nearby_layers=num_nearby_layers if num_nearby_layers is not None else NUM_NEARBY_LAYERS,
+               exclude_parts=exclude_parts, policy=policy, verbose=verbose)

@@ -1,0 +1,210 @@
+"""Process-group runtime: rendezvous, device pinning, backend selection.
+
+Reference behaviour being replaced: importing ``dear`` runs ``MPI_Init``
+(dear/dear_dopt.py:37), ``dear.init()`` builds three NCCL communicators
+(dear/dear_dopt.py:45-51) and drivers pin ``rank() % 4`` (dear/imagenet_benchmark.py:65).
+
+Here:
+  * launch is ``torchrun`` / env:// (RANK, WORLD_SIZE, LOCAL_RANK, MASTER_ADDR, MASTER_PORT);
+    no MPI.  A process started without those variables is a world of one.
+  * the device is pinned from LOCAL_RANK (not a hard-coded ``% 4``).
+  * ``backend`` selects the data path of the decoupled all-reduce:
+      "b200"  our fused sm_100a kernels over peer-mapped NVLink memory  (default on GPU)
+      "emu"   the same native runtime executed on the host over POSIX shm (CPU tests)
+      "nccl"  torch.distributed NCCL collectives + eager update          (baseline)
+      "gloo"  torch.distributed gloo collectives + eager update          (CPU plumbing)
+"""
+from __future__ import annotations
+
+import datetime
+import os
+from dataclasses import dataclass, field
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+_BACKENDS = ("b200", "emu", "nccl", "gloo")
+
+
+@dataclass
+class _State:
+    backend: str
+    rank: int
+    world: int
+    local_rank: int
+    local_size: int
+    device: torch.device
+    comm: object = None            # native Communicator (b200 / emu)
+    group: object = None           # torch.distributed group (object broadcast, baselines)
+    owns_pg: bool = False
+    options: dict = field(default_factory=dict)
+
+
+_state: Optional[_State] = None
+
+
+def _env_int(name, default):
+    v = os.environ.get(name)
+    return default if v in (None, "") else int(v)
+
+
+def is_initialized() -> bool:
+    return _state is not None
+
+
+def _require() -> _State:
+    if _state is None:
+        raise RuntimeError("dear is not initialised: call dear.init() first")
+    return _state
+
+
+def init(backend: Optional[str] = None, device: Optional[torch.device] = None, *, nstreams: int = 1,
+         staging_mb: Optional[int] = None, provider: Optional[str] = None,
+         multicast: Optional[bool] = None, timeout_s: float = 600.0) -> None:
+    """Initialise the runtime (idempotent).
+
+    Must be called by every rank.  Unlike the reference there is no ordering
+    constraint with device selection: the device is pinned here.
+    """
+    global _state
+    if _state is not None:
+        return
+    rank = _env_int("RANK", 0)
+    world = _env_int("WORLD_SIZE", 1)
+    local_rank = _env_int("LOCAL_RANK", rank)
+    local_size = _env_int("LOCAL_WORLD_SIZE", world)
+
+    use_cuda = torch.cuda.is_available() and (device is None or torch.device(device).type == "cuda")
+    backend = backend or os.environ.get("DEAR_BACKEND") or ("b200" if use_cuda else "gloo")
+    if backend not in _BACKENDS:
+        raise ValueError("unknown backend %r (choose from %s)" % (backend, ", ".join(_BACKENDS)))
+    if backend in ("b200", "nccl") and not torch.cuda.is_available():
+        raise RuntimeError("backend %r needs a CUDA device" % backend)
+    if backend in ("emu", "gloo"):
+        use_cuda = False
+
+    if use_cuda:
+        if device is None:
+            device = torch.device("cuda", local_rank % torch.cuda.device_count())
+        device = torch.device(device)
+        torch.cuda.set_device(device)
+    else:
+        device = torch.device("cpu")
+
+    owns_pg = False
+    group = None
+    store = None
+    if world > 1 or dist.is_initialized():
+        if not dist.is_initialized():
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            os.environ.setdefault("MASTER_PORT", "29500")
+            # NCCL is registered for CUDA tensors but initialised lazily: the fused
+            # path never touches it, only the baselines (nccl backend, DDP, WFBP) do.
+            pg_backend = "cpu:gloo,cuda:nccl" if use_cuda else "gloo"
+            dist.init_process_group(pg_backend, rank=rank, world_size=world,
+                                    timeout=datetime.timedelta(seconds=timeout_s))
+            owns_pg = True
+        rank, world = dist.get_rank(), dist.get_world_size()
+        group = dist.group.WORLD
+        from torch.distributed.distributed_c10d import _get_default_store
+        store = _get_default_store()
+
+    comm = None
+    opts = {}
+    if backend in ("b200", "emu"):
+        C = ops.require_native()
+        if world > C.MAX_RANKS:
+            raise RuntimeError("the symmetric-memory backend spans one NVSwitch domain (<= %d ranks)" % C.MAX_RANKS)
+        o = C.CommOptions()
+        o.device = device.index if backend == "b200" else -1
+        o.nstreams = max(1, int(nstreams))
+        o.staging_bytes = int(staging_mb if staging_mb is not None else _env_int("DEAR_STAGING_MB", 32)) << 20
+        prov = (provider or os.environ.get("DEAR_PROVIDER") or "ipc").lower()
+        if prov not in ("ipc", "vmm"):
+            raise ValueError("DEAR_PROVIDER must be 'ipc' or 'vmm'")
+        o.provider = C.PROVIDER_CUDA_VMM if prov == "vmm" else C.PROVIDER_CUDA_IPC
+        if multicast is None:
+            multicast = os.environ.get("DEAR_MULTICAST", "0") not in ("0", "", "false", "False")
+        o.multicast = bool(multicast) and prov == "vmm"
+        o.spin_timeout_s = float(os.environ.get("DEAR_SPIN_TIMEOUT_S", "20"))
+        o.rendezvous_timeout_s = float(timeout_s)
+        o.rs_grid = _env_int("DEAR_RS_GRID", 16)
+        o.ag_grid = _env_int("DEAR_AG_GRID", 16)
+        o.gen_grid = _env_int("DEAR_GEN_GRID", 8)
+        comm = C.Communicator(rank, world, store, "dear%d" % _env_int("DEAR_JOB_SEQ", 0), o)
+        opts = dict(provider=prov, multicast=o.multicast, rs_grid=o.rs_grid, ag_grid=o.ag_grid)
+
+    _state = _State(backend=backend, rank=rank, world=world, local_rank=local_rank, local_size=local_size,
+                    device=device, comm=comm, group=group, owns_pg=owns_pg, options=opts)
+
+
+def shutdown() -> None:
+    """Tear the runtime down (streams, arenas, process group)."""
+    global _state
+    if _state is None:
+        return
+    st = _state
+    try:
+        if st.comm is not None:
+            st.comm.synchronize()
+    finally:
+        _state = None
+        st.comm = None
+        if st.owns_pg and dist.is_initialized():
+            dist.destroy_process_group()
+
+
+def rank() -> int:
+    return _require().rank if _state is not None else _env_int("RANK", 0)
+
+
+def size() -> int:
+    return _require().world if _state is not None else _env_int("WORLD_SIZE", 1)
+
+
+def local_rank() -> int:
+    return _require().local_rank if _state is not None else _env_int("LOCAL_RANK", 0)
+
+
+def local_size() -> int:
+    return _require().local_size if _state is not None else _env_int("LOCAL_WORLD_SIZE", 1)
+
+
+def backend() -> str:
+    return _require().backend
+
+
+def device() -> torch.device:
+    return _require().device
+
+
+def communicator():
+    """The native Communicator (``None`` for the nccl / gloo backends)."""
+    return _require().comm
+
+
+def group():
+    return _require().group
+
+
+def barrier() -> None:
+    st = _require()
+    if st.world == 1:
+        return
+    if st.comm is not None:
+        st.comm.barrier()
+    else:
+        dist.barrier()
+
+
+def broadcast_object(obj, src: int = 0):
+    """Broadcast a small picklable Python object from ``src`` (tuner decisions, flags)."""
+    st = _require()
+    if st.world == 1:
+        return obj
+    box = [obj]
+    dist.broadcast_object_list(box, src=src, group=st.group, device=torch.device("cpu"))
+    return box[0]

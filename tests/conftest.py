@@ -1,0 +1,29 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+os.environ.setdefault("PYTHONPATH", ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
+
+
+def pytest_configure(config):
+    import torch
+    torch.set_num_threads(1)      # no OpenMP pool in the parent: children are forked
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box: pytest -m gpu)")
+    config.addinivalue_line("markers", "multigpu: needs >= 2 CUDA devices")
+
+
+def pytest_collection_modifyitems(config, items):
+    try:
+        import torch
+        ngpu = torch.cuda.device_count() if torch.cuda.is_available() else 0
+    except Exception:
+        ngpu = 0
+    for item in items:
+        if "gpu" in item.keywords and ngpu == 0:
+            item.add_marker(pytest.mark.skip(reason="no CUDA device"))
+        if "multigpu" in item.keywords and ngpu < 2:
+            item.add_marker(pytest.mark.skip(reason="needs >= 2 CUDA devices"))

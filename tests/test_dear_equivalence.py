@@ -1,0 +1,99 @@
+"""DeAR data-parallel SGD == single-process SGD on the concatenated batch."""
+import copy
+
+import pytest
+import torch
+import torch.nn as nn
+
+from _mp import run_ranks
+
+
+def make_model(seed=0):
+    torch.manual_seed(seed)
+    return nn.Sequential(
+        nn.Conv2d(3, 8, 3, padding=1), nn.BatchNorm2d(8), nn.ReLU(),
+        nn.Conv2d(8, 8, 3, padding=1, bias=False), nn.ReLU(),
+        nn.AdaptiveAvgPool2d(2), nn.Flatten(),
+        nn.Linear(32, 33), nn.ReLU(), nn.Linear(33, 10))
+
+
+def data(step, n):
+    g = torch.Generator().manual_seed(1000 + step)
+    return torch.randn(n, 3, 8, 8, generator=g), torch.randint(0, 10, (n,), generator=g)
+
+
+def sgd_kwargs(case):
+    return dict(lr=0.05, **case)
+
+
+CASES = [
+    dict(),
+    dict(momentum=0.9),
+    dict(momentum=0.9, nesterov=True, weight_decay=1e-2),
+    dict(momentum=0.8, dampening=0.3, weight_decay=5e-3),
+]
+
+
+def reference_run(case, steps, world, per_rank):
+    model = make_model()
+    # BatchNorm statistics are per-rank in data parallel; use eval-mode BN so that the
+    # concatenated-batch oracle is exact.
+    model.eval()
+    opt = torch.optim.SGD(model.parameters(), **sgd_kwargs(case))
+    for t in range(steps):
+        x, y = data(t, world * per_rank)
+        opt.zero_grad()
+        nn.functional.cross_entropy(model(x), y).backward()
+        opt.step()
+    return [p.detach().clone() for p in model.parameters()]
+
+
+def dear_worker(rank, world, case, steps, per_rank, threshold, nearby):
+    import dear_pytorch_b200 as dear
+    model = make_model()
+    model.eval()
+    opt = torch.optim.SGD(model.parameters(), **sgd_kwargs(case))
+    opt = dear.DistributedOptimizer(opt, model, threshold=threshold, num_nearby_layers=nearby, verbose=False)
+    dear.broadcast_parameters(model.state_dict(), 0)
+    for t in range(steps):
+        x, y = data(t, world * per_rank)
+        x, y = x[rank * per_rank:(rank + 1) * per_rank], y[rank * per_rank:(rank + 1) * per_rank]
+        opt.zero_grad()
+        nn.functional.cross_entropy(model(x), y).backward()
+        opt.step()
+    opt.synchronize()
+    return [p.detach().clone() for p in model.parameters()], len(opt.engine.plan.buckets)
+
+
+@pytest.mark.parametrize("backend", ["gloo", "emu"])
+@pytest.mark.parametrize("case", CASES)
+def test_matches_single_process_sgd(backend, case):
+    steps, per_rank, world = 4, 4, 2
+    ref = reference_run(case, steps, world, per_rank)
+    outs = run_ranks(dear_worker, world=world, backend=backend, args=(case, steps, per_rank, 0.001, None))
+    for params, nb in outs:
+        assert nb > 1
+        for a, b in zip(params, ref):
+            torch.testing.assert_close(a, b, rtol=2e-5, atol=2e-6)
+    for a, b in zip(outs[0][0], outs[1][0]):
+        assert torch.equal(a, b)          # replicas are bit-identical
+
+
+@pytest.mark.parametrize("backend", ["gloo", "emu"])
+def test_nearby_layers_and_single_bucket(backend):
+    case = dict(momentum=0.9)
+    ref = reference_run(case, 3, 2, 4)
+    for nearby in (1, 2, -1):
+        outs = run_ranks(dear_worker, world=2, backend=backend, args=(case, 3, 4, None, nearby))
+        for params, nb in outs:
+            for a, b in zip(params, ref):
+                torch.testing.assert_close(a, b, rtol=2e-5, atol=2e-6)
+
+
+def test_world_of_three_emu():
+    case = dict(momentum=0.9, weight_decay=1e-3)
+    ref = reference_run(case, 3, 3, 2)
+    outs = run_ranks(dear_worker, world=3, backend="emu", args=(case, 3, 2, 0.002, None))
+    for params, nb in outs:
+        for a, b in zip(params, ref):
+            torch.testing.assert_close(a, b, rtol=2e-5, atol=2e-6)
