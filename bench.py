@@ -1,0 +1,216 @@
+#!/usr/bin/env python
+"""Headline benchmark: ResNet-50, batch 64 per GPU, synthetic ImageNet, DeAR with tensor fusion.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, 1 rank/GPU)
+    python bench.py --impl reference ...                     (the reference's own code path, NCCL)
+
+Metric and config follow BASELINE.json ("ResNet-50 images/sec ... bs=64/GPU synthetic ImageNet
+DeAR-TF") and the reference driver dear/imagenet_benchmark.py (SGD lr=0.01*size, synthetic
+224x224x3 batch, cross-entropy).  Timing: W untimed warm-up steps, then exactly K steps between
+CUDA events, bracketed by barrier + synchronize, max over ranks.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+BASELINE_PUBLISHED = None   # the reference publishes no throughput number
+
+
+def parse_args(argv=None):
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", choices=["dear", "reference"], default="dear")
+    ap.add_argument("--model", default="resnet50")
+    ap.add_argument("--batch-size", type=int, default=64)
+    ap.add_argument("--dtype", choices=["fp32", "bf16", "amp"], default=os.environ.get("DEAR_BENCH_DTYPE", "fp32"))
+    ap.add_argument("--channels-last", type=int, default=int(os.environ.get("DEAR_BENCH_CL", "1")))
+    ap.add_argument("--graph", type=int, default=int(os.environ.get("DEAR_BENCH_GRAPH", "0")))
+    ap.add_argument("--threshold", type=float, default=25.0)
+    ap.add_argument("--backend", default=None)
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args(argv)
+
+
+def _free_port():
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def main(argv=None):
+    args = parse_args(argv)
+    if args.gpus > 1 and "RANK" not in os.environ:
+        import subprocess
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), os.path.abspath(__file__)] + \
+              (argv if argv is not None else sys.argv[1:])
+        sys.exit(subprocess.call(cmd))
+    if args.impl == "reference":
+        from baseline.run_reference import run as run_reference
+        return run_reference(args)
+    return run_dear(args)
+
+
+def run_dear(args):
+    import torch
+    import torch.nn.functional as F
+    import dear_pytorch_b200 as dear
+    from dear_pytorch_b200.models.registry import create, input_size
+    from dear_pytorch_b200.utils.clocks import ClockSampler
+    from dear_pytorch_b200.utils.data import PinnedPrefetcher, SyntheticImages
+    from dear_pytorch_b200.utils.train import TrainStep
+
+    dear.init(backend=args.backend)
+    rank, world = dear.rank(), dear.size()
+    device = dear.device()
+    cuda = device.type == "cuda"
+    torch.backends.cudnn.benchmark = True
+    torch.manual_seed(1234)
+
+    model = create(args.model).to(device)
+    if args.channels_last:
+        model = model.to(memory_format=torch.channels_last)
+    pdtype = torch.float32
+    if args.dtype == "bf16":
+        # bf16 parameters/activations/gradients, fp32 BatchNorm, fp32 master weights + momentum
+        # (sharded) inside the optimizer
+        model = model.to(torch.bfloat16)
+        for m in model.modules():
+            if isinstance(m, torch.nn.modules.batchnorm._BatchNorm):
+                m.float()
+        pdtype = torch.bfloat16
+    model.train()
+    base = torch.optim.SGD(model.parameters(), lr=0.01 * world, momentum=0.0)
+    opt = dear.DistributedOptimizer(base, model, threshold=args.threshold, verbose=(rank == 0 and bool(os.environ.get("DEAR_VERBOSE"))))
+    dear.broadcast_parameters(model.state_dict(), 0)
+
+    size = input_size(args.model)
+    B = args.batch_size
+    autocast = args.dtype == "amp"
+
+    def loss_fn(out, y):
+        return F.cross_entropy(out.float() if out.dtype != torch.float32 else out, y)
+
+    step = TrainStep(model, opt, loss_fn, autocast_dtype=torch.bfloat16 if autocast else None,
+                     use_graph=bool(args.graph) and cuda)
+
+    # ---- device-resident synthetic batch (the reference's protocol) -------------------------
+    x = torch.randn(B, 3, size, size, device=device).to(pdtype if args.dtype == "bf16" else torch.float32)
+    if args.channels_last:
+        x = x.contiguous(memory_format=torch.channels_last)
+    y = torch.randint(0, 1000, (B,), device=device)
+
+    def sync():
+        if cuda:
+            torch.cuda.synchronize(device)
+
+    for _ in range(args.warmup):
+        step(x, y)
+    opt.engine.synchronize(host=True)
+    comm = dear.communicator()
+
+    def timed(run_one, n):
+        dear.barrier(); sync()
+        l0 = comm.launches() if comm is not None else opt.engine.backend.launches()
+        if cuda:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            run_one()
+        opt.engine.synchronize(host=False)       # the K-th update must have landed
+        if cuda:
+            e1.record()
+            sync()
+            ms = e0.elapsed_time(e1)
+        else:
+            ms = (time.perf_counter() - t0) * 1e3
+        dear.barrier()
+        l1 = comm.launches() if comm is not None else opt.engine.backend.launches()
+        return ms, l1 - l0
+
+    sampler = ClockSampler(device.index if cuda else 0).start() if (cuda and rank == 0) else None
+    wall0 = time.time()
+    ms, launches = timed(lambda: step(x, y), args.steps)
+    wall1 = time.time()
+
+    # ---- end to end: pinned host batches -> H2D every step, loss -> host every step ----------
+    e2e = None
+    if not args.no_e2e:
+        host = SyntheticImages(B, size, channels_last=bool(args.channels_last),
+                               dtype=pdtype if args.dtype == "bf16" else torch.float32, seed=rank)
+        feed = PinnedPrefetcher(host, device)
+        loss_host = torch.zeros(args.steps + args.warmup, dtype=torch.float32)
+        if cuda:
+            loss_host = loss_host.pin_memory()
+        k = [0]
+
+        def one():
+            xb, yb = next(feed)
+            loss = step(xb, yb)
+            loss_host[k[0]].copy_(loss.detach().float(), non_blocking=True)   # D2H every step
+            k[0] += 1
+        for _ in range(min(3, args.warmup)):
+            one()
+        ms_e2e, _ = timed(one, args.steps)
+        sync()
+        assert torch.isfinite(loss_host[:k[0]]).all(), "non-finite loss in the end-to-end run"
+        ms_e2e = _max_over_ranks(ms_e2e, world)
+        e2e = {"value": round(B * world * args.steps / (ms_e2e / 1e3), 2), "unit": "images/s",
+               "h2d_bytes_per_step": int(host.bytes_per_batch), "d2h_bytes_per_step": 4,
+               "ms_per_step": round(ms_e2e / args.steps, 4)}
+    clocks = sampler.stop() if sampler is not None else None
+    if sampler is not None:
+        clocks = sampler.summary(wall0, wall1)
+
+    ms = _max_over_ranks(ms, world)
+    value = B * world * args.steps / (ms / 1e3)
+    if rank == 0:
+        n_params = sum(p.numel() for p in model.parameters())
+        out = {
+            "metric": "images/sec (ResNet-50 synthetic ImageNet training, DeAR tensor fusion)" if args.model == "resnet50"
+                      else "images/sec (%s synthetic training, DeAR)" % args.model,
+            "value": round(value, 2), "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None if BASELINE_PUBLISHED is None else round(value / BASELINE_PUBLISHED, 4),
+            "dtype": {"fp32": "fp32 (TF32 convolutions, torch defaults, as the reference)", "bf16": "bf16",
+                      "amp": "bf16 autocast"}[args.dtype],
+            "data": "synthetic", "impl": "dear",
+            "config": {"model": args.model, "global_batch": B * world, "batch_per_gpu": B, "image": size,
+                       "parallelism": "dp%d" % world, "optimizer": "SGD lr=0.01*size", "threshold_mb": args.threshold,
+                       "buckets": len(opt.engine.plan.buckets), "params": n_params, "backend": dear.backend(),
+                       "channels_last": bool(args.channels_last), "cuda_graph": bool(args.graph),
+                       "l2": "no explicit flush: each step streams activations+weights far larger than the 126 MB L2"},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(out), flush=True)
+    opt.engine.close()
+    dear.shutdown()
+    return 0
+
+
+def _max_over_ranks(v, world):
+    if world == 1:
+        return v
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([v], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -115,22 +115,18 @@ class BucketPlan:
 
     # ------------------------------------------------------------------ grouping policies
     def _split_on_dtype(self, groups: Sequence[Sequence[int]]) -> List[List[int]]:
+        """A bucket never mixes dtypes: every group is partitioned into one sub-bucket per dtype
+        (module order preserved inside each).  With bf16 convolutions and fp32 BatchNorm this gives
+        one large bf16 bucket and one small fp32 bucket per group instead of a bucket per layer."""
         out: List[List[int]] = []
         for g in groups:
-            cur: List[int] = []
-            cur_dt = None
+            by_dt: Dict[torch.dtype, List[int]] = {}
             for mi in g:
                 dts = {s.param.dtype for s in self.module_params[mi]}
                 if len(dts) != 1:
                     raise ValueError("module %s mixes parameter dtypes %s" % (self.module_names[mi], dts))
-                dt = next(iter(dts))
-                if cur and dt != cur_dt:
-                    out.append(cur)
-                    cur = []
-                cur.append(mi)
-                cur_dt = dt
-            if cur:
-                out.append(cur)
+                by_dt.setdefault(next(iter(dts)), []).append(mi)
+            out.extend(by_dt.values())
         return out
 
     def group_by_threshold(self, threshold_mb: float) -> "BucketPlan":
@@ -185,9 +181,9 @@ class BucketPlan:
         return self._layout([[i] for i in range(len(self.modules))])
 
     def group_explicit(self, groups: Sequence[Sequence[int]]) -> "BucketPlan":
-        flat = [mi for g in groups for mi in g]
+        flat = sorted(mi for g in groups for mi in g)
         if flat != list(range(len(self.modules))):
-            raise ValueError("groups must cover all modules in registration order")
+            raise ValueError("groups must cover every registered module exactly once")
         self.policy = ("explicit", tuple(tuple(g) for g in groups))
         return self._layout(groups)
 

@@ -255,6 +255,20 @@ class DearEngine:
             self.backend.set_hyper(b.index, HyperSpec(segs))
             self._hyper_key[b.index] = key_all
 
+    def _hyper_key_now(self):
+        return tuple((g["lr"], g.get("weight_decay", 0.0), g.get("momentum", 0.0), g.get("dampening", 0.0),
+                      bool(g.get("nesterov", False))) for g in self.opt.param_groups)
+
+    def hyper_changed(self) -> bool:
+        key = self._hyper_key_now()
+        return any(k != key for k in self._hyper_key)
+
+    def refresh_hyper_outside_graph(self):
+        """An LR scheduler changed ``param_groups`` while the step is replayed from a CUDA graph:
+        re-upload the device hyper-parameter tables and order the replay after the upload."""
+        self._refresh_hyper()
+        self.backend.wait_all()
+
     # ------------------------------------------------------------------ step
     def step(self):
         be = self.backend
@@ -271,7 +285,12 @@ class DearEngine:
             self._any_pending = True
             self._mom_initialised = True
         else:
+            # time-breakdown mode (no all-gather): peers may still be pulling from this rank's
+            # gradient buckets, so rendezvous on the device before the next backward reuses them
             be.wait_all()
+            comm = runtime.communicator()
+            if comm is not None and self.world > 1:
+                comm.waitStream(comm.deviceBarrier())
             self._inflight.clear()
         if self.steal:
             for s in self.plan.slots:

@@ -1,0 +1,127 @@
+"""GPU tests of the fused path (run on the B200 box: pytest -m gpu).
+
+Numerics oracle: plain PyTorch fp32 SGD on the concatenated batch.  Multi-rank cases run one
+process per rank; with a single GPU all ranks share cuda:0 (CUDA IPC works between processes on one
+device), with >= 2 GPUs each rank gets its own device and the data moves over NVLink.
+"""
+import os
+
+import pytest
+import torch
+import torch.nn as nn
+
+from _mp import run_ranks
+from test_dear_equivalence import CASES, data, make_model, reference_run
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_worker(rank, world, case, steps, per_rank, threshold, dtype_name):
+    import dear_pytorch_b200 as dear
+    from dear_pytorch_b200 import ops
+    assert ops.native_path() is not None
+    dev = dear.device()
+    model = make_model().to(dev)
+    model.eval()
+    if dtype_name == "bf16":
+        model = model.to(torch.bfloat16)
+    opt = torch.optim.SGD(model.parameters(), lr=0.05, **case)
+    opt = dear.DistributedOptimizer(opt, model, threshold=threshold, verbose=False)
+    dear.broadcast_parameters(model.state_dict(), 0)
+    for t in range(steps):
+        x, y = data(t, world * per_rank)
+        x, y = x[rank * per_rank:(rank + 1) * per_rank].to(dev), y[rank * per_rank:(rank + 1) * per_rank].to(dev)
+        if dtype_name == "bf16":
+            x = x.to(torch.bfloat16)
+        opt.zero_grad()
+        nn.functional.cross_entropy(model(x).float(), y).backward()
+        opt.step()
+    opt.synchronize()
+    dear.communicator().check_status()
+    return [p.detach().float().cpu() for p in model.parameters()], dear.communicator().launches()
+
+
+def _env():
+    # several ranks may have to share one GPU on the test box
+    return {"DEAR_SPIN_TIMEOUT_S": "15"}
+
+
+@pytest.mark.parametrize("case", [CASES[0], CASES[2], CASES[3]])
+def test_single_gpu_fused_sgd_matches_torch(case):
+    ref = reference_run(case, 4, 1, 8)
+    outs = run_ranks(gpu_worker, world=1, backend="b200", args=(case, 4, 8, 0.001, "fp32"), extra_env=_env())
+    params, launches = outs[0]
+    assert launches > 0
+    for a, b in zip(params, ref):
+        torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_multi_rank_fused_matches_torch(world):
+    ngpu = torch.cuda.device_count()
+    if ngpu > 1 and ngpu < world:
+        pytest.skip("needs %d GPUs (or exactly one shared GPU)" % world)
+    case = CASES[2]
+    ref = reference_run(case, 3, world, 2)
+    outs = run_ranks(gpu_worker, world=world, backend="b200", args=(case, 3, 2, 0.001, "fp32"), extra_env=_env(),
+                     timeout=300)
+    for params, launches in outs:
+        assert launches > 0
+        for a, b in zip(params, ref):
+            torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-5)
+    for a, b in zip(outs[0][0], outs[-1][0]):
+        assert torch.equal(a, b)
+
+
+def test_bf16_params_fp32_master():
+    case = dict(momentum=0.9)
+    ref = reference_run(case, 3, 2, 4)
+    outs = run_ranks(gpu_worker, world=2 if torch.cuda.device_count() != 1 or True else 1, backend="b200",
+                     args=(case, 3, 4, 0.001, "bf16"), extra_env=_env(), timeout=300)
+    for params, _ in outs:
+        for a, b in zip(params, ref):
+            torch.testing.assert_close(a, b, rtol=5e-2, atol=5e-2)
+    for a, b in zip(outs[0][0], outs[-1][0]):
+        assert torch.equal(a, b)
+
+
+def comm_worker(rank, world):
+    import dear_pytorch_b200 as dear
+    dev = dear.device()
+    comm = dear.communicator()
+    res = {}
+    t = torch.arange(1000, device=dev, dtype=torch.float32) * (rank + 1)
+    dear.allreduce(t)
+    res["allreduce"] = t.cpu()
+    b = torch.arange(7, device=dev, dtype=torch.int64) * (rank + 5)
+    dear.broadcast_(b, world - 1)
+    res["bcast"] = b.cpu()
+    big = torch.full((3_000_001,), float(rank + 1), device=dev)
+    h = comm.allReduceRSAG(big[:3_000_000 // world * world], 1.0)
+    comm.syncStream(h)
+    res["rsag"] = big[:4].cpu()
+    g = dear.allgather(torch.full((5,), float(rank), device=dev))
+    res["allgather"] = g.cpu()
+    h = comm.allReduceRB(t, 1.0)
+    comm.syncStream(h)
+    res["rb"] = t[:3].cpu()
+    send = torch.full((9,), float(rank), device=dev)
+    recv = torch.empty_like(send)
+    h = comm.sendrecv(send, recv, (rank + 1) % world)
+    comm.syncStream(h)
+    res["sendrecv"] = recv.cpu()
+    comm.check_status()
+    return res
+
+
+def test_general_collectives():
+    world = 2
+    outs = run_ranks(comm_worker, world=world, backend="b200", extra_env=_env(), timeout=300)
+    s = sum(range(1, world + 1))
+    for r, res in enumerate(outs):
+        torch.testing.assert_close(res["allreduce"], torch.arange(1000.) * s / world)
+        assert torch.equal(res["bcast"], torch.arange(7) * (world - 1 + 5))
+        torch.testing.assert_close(res["rsag"], torch.full((4,), float(s)))
+        torch.testing.assert_close(res["allgather"], torch.arange(world).repeat_interleave(5).float())
+        torch.testing.assert_close(res["rb"], (torch.arange(1000.) * s / world)[:3] * world)
+        torch.testing.assert_close(res["sendrecv"], torch.full((9,), float((r + 1) % world)))
