@@ -1,0 +1,143 @@
+"""`bench.py --impl reference`: the reference's own DeAR optimizer (baseline/_ref/dear/dopt_rsag.py,
+tensorfusion.py — unmodified) driven exactly as its benchmark driver does
+(baseline/_ref/dear/imagenet_benchmark.py:73-136: torchvision model, SGD lr=0.01*size,
+DistributedOptimizer iff size>1, broadcast_parameters, benchmark_step incl. its
+torch.cuda.synchronize()), timed with the same protocol as the dear arm.
+"""
+import json
+import os
+import sys
+import time
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.path.join(HERE, "_ref")
+
+
+def _unavailable(why):
+    print(json.dumps({"impl": "reference", "unavailable": why}), flush=True)
+    return 0
+
+
+def run(args):
+    if not os.path.isdir(os.path.join(REF, "dear")):
+        src = "/root/reference"
+        if os.path.isdir(os.path.join(src, "dear")):
+            import shutil
+            shutil.copytree(src, REF, dirs_exist_ok=True)
+        else:
+            return _unavailable("baseline/_ref is missing and /root/reference is not mounted "
+                                "(the reference has no setup.py; comm_core needs MPI)")
+    try:
+        import torch
+        if not torch.cuda.is_available():
+            return _unavailable("the reference is CUDA-only (no CPU path)")
+        import torchvision  # noqa: F401
+    except Exception as exc:  # pragma: no cover
+        return _unavailable("missing dependency: %r" % (exc,))
+
+    sys.path.insert(0, os.path.join(REF, "dear"))
+    sys.path.insert(0, HERE)                      # comm_core stand-in (NCCL via torch.distributed)
+    import torch.backends.cudnn as cudnn
+    import torch.nn.functional as F
+    import torch.optim as optim
+    from torchvision import models
+    import comm_core
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank % torch.cuda.device_count())
+    comm_core.init()
+    import dopt_rsag as hvd                      # the reference module, unmodified
+
+    hvd.init()
+    cudnn.benchmark = True
+    rank, world = hvd.rank(), hvd.size()
+    if args.model != "resnet50" and not hasattr(models, args.model):
+        return _unavailable("model %s is not in torchvision" % args.model)
+    model = getattr(models, args.model)().cuda()
+    optimizer = optim.SGD(model.parameters(), lr=0.01 * world)
+    if world > 1:
+        optimizer = hvd.DistributedOptimizer(optimizer, model=model)
+        hvd.broadcast_parameters(model.state_dict(), root_rank=0)
+    B = args.batch_size
+    size = 224
+    data = torch.randn(B, 3, size, size).cuda()
+    target = torch.LongTensor(B).random_() % 1000
+    target = target.cuda()
+
+    def benchmark_step(d=data, t=target):
+        optimizer.zero_grad()
+        output = model(d)
+        loss = F.cross_entropy(output, t)
+        loss.backward()
+        optimizer.step()
+        torch.cuda.synchronize()
+        return loss
+
+    import torch.distributed as dist
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(args.warmup):
+        benchmark_step()
+
+    def timed(fn, n):
+        barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record(); torch.cuda.synchronize(); barrier()
+        return e0.elapsed_time(e1)
+
+    def maxr(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    from dear_pytorch_b200.utils.clocks import ClockSampler   # nvidia-smi sampler only (not on the timed path)
+    sampler = ClockSampler(torch.cuda.current_device()).start() if rank == 0 else None
+    w0 = time.time()
+    ms = maxr(timed(benchmark_step, args.steps))
+    w1 = time.time()
+
+    e2e = None
+    if not args.no_e2e:
+        hx = [torch.randn(B, 3, size, size).pin_memory() for _ in range(4)]
+        hy = [(torch.LongTensor(B).random_() % 1000).pin_memory() for _ in range(4)]
+        k = [0]
+        losses = []
+
+        def one():
+            i = k[0] % 4
+            k[0] += 1
+            d = hx[i].cuda(non_blocking=True)
+            t = hy[i].cuda(non_blocking=True)
+            losses.append(benchmark_step(d, t).item())
+        for _ in range(min(3, args.warmup)):
+            one()
+        ms_e = maxr(timed(one, args.steps))
+        e2e = {"value": round(B * world * args.steps / (ms_e / 1e3), 2), "unit": "images/s",
+               "h2d_bytes_per_step": int(hx[0].numel() * 4 + hy[0].numel() * 8), "d2h_bytes_per_step": 4,
+               "ms_per_step": round(ms_e / args.steps, 4)}
+    clocks = None
+    if sampler is not None:
+        sampler.stop()
+        clocks = sampler.summary(w0, w1)
+    if rank == 0:
+        value = B * world * args.steps / (ms / 1e3)
+        print(json.dumps({
+            "metric": "images/sec (ResNet-50 synthetic ImageNet training, DeAR tensor fusion)", "value": round(value, 2),
+            "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp32 (TF32 convolutions, torch defaults)", "data": "synthetic", "impl": "reference",
+            "config": {"model": args.model, "global_batch": B * world, "batch_per_gpu": B, "image": size,
+                       "parallelism": "dp%d" % world, "optimizer": "SGD lr=0.01*size",
+                       "path": "baseline/_ref/dear/dopt_rsag.py over NCCL (comm_core stand-in: torch.distributed)",
+                       "l2": "no explicit flush: working set far larger than L2"},
+            "e2e": e2e, "gpu_launches": 0, "clocks": clocks}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0

@@ -449,12 +449,14 @@ void BucketSet::set_shards(int g, torch::Tensor grad_shard, std::optional<torch:
   b.master = torch::Tensor();
   if (mom.has_value() && mom->defined()) { chk(*mom, "momentum shard"); b.mom = *mom; }
   if (master.has_value() && master->defined()) { chk(*master, "master shard"); b.master = *master; }
-  DEAR_CHECK(dtype_ == DT_F32 || b.master.defined(), "low-precision parameter buckets need an fp32 master shard");
+  // (low-precision buckets must have a master shard by the time allgather_update() runs)
 }
 
 void BucketSet::upload(Bucket& b, const void* host, size_t bytes, void** dev, size_t* cap) {
   if (bytes == 0) return;
   if (*cap < bytes) {
+    DEAR_CHECK(!(is_capturing(S(stream_)) || is_capturing(current_stream(comm_->options().device))),
+               "device table would have to grow during CUDA-graph capture; run a few eager steps first");
     // the old table may still be read by an in-flight kernel on the comm stream
     DEAR_CUDA(cudaStreamSynchronize(S(stream_)));
     if (*dev) DEAR_CUDA(cudaFree(*dev));
@@ -464,7 +466,8 @@ void BucketSet::upload(Bucket& b, const void* host, size_t bytes, void** dev, si
   }
   const int slot = b.pinned_next;
   b.pinned_next ^= 1;
-  const bool capturing = is_capturing(S(stream_));
+  // a capture may be in progress on the compute stream before the comm stream has joined it
+  const bool capturing = is_capturing(S(stream_)) || is_capturing(current_stream(comm_->options().device));
   if (b.pinned_cap[slot] < bytes) {
     if (b.pinned[slot]) {
       if (!capturing) DEAR_CUDA(cudaEventSynchronize(E(b.pinned_ev[slot])));

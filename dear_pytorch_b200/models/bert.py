@@ -1,0 +1,183 @@
+"""BERT for pre-training (MLM + NSP heads), base and large.
+
+The reference benchmarks HuggingFace ``BertForPreTraining`` built from ``bert_config.json`` /
+``bert_base_config.json`` with the vocabulary padded to a multiple of 8 (30522 -> 30528)
+(dear/bert_benchmark.py:72-83).  This is an independent implementation of the same architecture
+(same parameter tensors and tying: the MLM decoder shares the word-embedding matrix), written for
+Blackwell: attention goes through ``scaled_dot_product_attention`` (flash kernels) and the QKV
+projections are one fused GEMM.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+@dataclass
+class BertConfig:
+    vocab_size: int = 30522
+    hidden_size: int = 1024
+    num_hidden_layers: int = 24
+    num_attention_heads: int = 16
+    intermediate_size: int = 4096
+    max_position_embeddings: int = 512
+    type_vocab_size: int = 2
+    hidden_dropout_prob: float = 0.1
+    attention_probs_dropout_prob: float = 0.1
+    initializer_range: float = 0.02
+    layer_norm_eps: float = 1e-12
+
+    def padded_vocab(self, multiple: int = 8) -> int:
+        return (self.vocab_size + multiple - 1) // multiple * multiple
+
+
+BERT_LARGE = BertConfig()                                   # dear/bert_config.json
+BERT_BASE = BertConfig(hidden_size=768, num_hidden_layers=12, num_attention_heads=12,
+                       intermediate_size=3072)              # dear/bert_base_config.json
+
+
+class BertEmbeddings(nn.Module):
+    def __init__(self, c: BertConfig, vocab: int):
+        super().__init__()
+        self.word_embeddings = nn.Embedding(vocab, c.hidden_size)
+        self.position_embeddings = nn.Embedding(c.max_position_embeddings, c.hidden_size)
+        self.token_type_embeddings = nn.Embedding(c.type_vocab_size, c.hidden_size)
+        self.LayerNorm = nn.LayerNorm(c.hidden_size, eps=c.layer_norm_eps)
+        self.dropout = nn.Dropout(c.hidden_dropout_prob)
+
+    def forward(self, input_ids, token_type_ids=None, position_ids=None):
+        B, S = input_ids.shape
+        if position_ids is None:
+            position_ids = torch.arange(S, device=input_ids.device).unsqueeze(0)
+        if token_type_ids is None:
+            token_type_ids = torch.zeros_like(input_ids)
+        x = self.word_embeddings(input_ids) + self.position_embeddings(position_ids) + \
+            self.token_type_embeddings(token_type_ids)
+        return self.dropout(self.LayerNorm(x))
+
+
+class BertSelfAttention(nn.Module):
+    def __init__(self, c: BertConfig):
+        super().__init__()
+        self.nh = c.num_attention_heads
+        self.hd = c.hidden_size // c.num_attention_heads
+        self.qkv = nn.Linear(c.hidden_size, 3 * c.hidden_size)      # fused Q,K,V projection
+        self.p_drop = c.attention_probs_dropout_prob
+
+    def forward(self, x, attn_bias):
+        B, S, H = x.shape
+        qkv = self.qkv(x).view(B, S, 3, self.nh, self.hd).permute(2, 0, 3, 1, 4)
+        o = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2], attn_mask=attn_bias,
+                                           dropout_p=self.p_drop if self.training else 0.0)
+        return o.transpose(1, 2).reshape(B, S, H)
+
+
+class BertLayer(nn.Module):
+    def __init__(self, c: BertConfig):
+        super().__init__()
+        self.attention = BertSelfAttention(c)
+        self.attn_out = nn.Linear(c.hidden_size, c.hidden_size)
+        self.attn_norm = nn.LayerNorm(c.hidden_size, eps=c.layer_norm_eps)
+        self.intermediate = nn.Linear(c.hidden_size, c.intermediate_size)
+        self.output = nn.Linear(c.intermediate_size, c.hidden_size)
+        self.out_norm = nn.LayerNorm(c.hidden_size, eps=c.layer_norm_eps)
+        self.dropout = nn.Dropout(c.hidden_dropout_prob)
+
+    def forward(self, x, attn_bias):
+        a = self.dropout(self.attn_out(self.attention(x, attn_bias)))
+        x = self.attn_norm(x + a)
+        h = self.dropout(self.output(F.gelu(self.intermediate(x))))
+        return self.out_norm(x + h)
+
+
+class BertModel(nn.Module):
+    def __init__(self, c: BertConfig, vocab: int):
+        super().__init__()
+        self.embeddings = BertEmbeddings(c, vocab)
+        self.layers = nn.ModuleList(BertLayer(c) for _ in range(c.num_hidden_layers))
+        self.pooler = nn.Linear(c.hidden_size, c.hidden_size)
+
+    def forward(self, input_ids, token_type_ids=None, attention_mask=None, position_ids=None):
+        x = self.embeddings(input_ids, token_type_ids, position_ids)
+        bias = None
+        if attention_mask is not None:
+            # additive key-padding bias, broadcast over heads and query positions
+            bias = (1.0 - attention_mask[:, None, None, :].to(x.dtype)) * torch.finfo(x.dtype).min
+        for layer in self.layers:
+            x = layer(x, bias)
+        pooled = torch.tanh(self.pooler(x[:, 0]))
+        return x, pooled
+
+
+class BertPreTrainingHeads(nn.Module):
+    """MLM head (dense + GELU + LayerNorm, decoder tied to the word embeddings, own bias) and NSP head."""
+
+    def __init__(self, c: BertConfig, vocab: int):
+        super().__init__()
+        self.transform = nn.Linear(c.hidden_size, c.hidden_size)
+        self.transform_norm = nn.LayerNorm(c.hidden_size, eps=c.layer_norm_eps)
+        self.decoder_bias = nn.Parameter(torch.zeros(vocab))
+        self.seq_relationship = nn.Linear(c.hidden_size, 2)
+
+    def forward(self, seq, pooled, word_embedding_weight):
+        h = self.transform_norm(F.gelu(self.transform(seq)))
+        return F.linear(h, word_embedding_weight, self.decoder_bias), self.seq_relationship(pooled)
+
+
+class BertForPreTraining(nn.Module):
+    def __init__(self, config: BertConfig = BERT_LARGE, pad_vocab_to: int = 8):
+        super().__init__()
+        self.config = config
+        self.vocab_size = config.padded_vocab(pad_vocab_to)
+        self.bert = BertModel(config, self.vocab_size)
+        self.cls = BertPreTrainingHeads(config, self.vocab_size)
+        self.apply(self._init)
+
+    def _init(self, m):
+        if isinstance(m, (nn.Linear, nn.Embedding)):
+            nn.init.normal_(m.weight, 0.0, self.config.initializer_range)
+            if isinstance(m, nn.Linear) and m.bias is not None:
+                nn.init.zeros_(m.bias)
+        elif isinstance(m, nn.LayerNorm):
+            nn.init.ones_(m.weight)
+            nn.init.zeros_(m.bias)
+
+    def forward(self, input_ids, token_type_ids=None, attention_mask=None, position_ids=None):
+        seq, pooled = self.bert(input_ids, token_type_ids, attention_mask, position_ids)
+        return self.cls(seq, pooled, self.bert.embeddings.word_embeddings.weight)
+
+
+class BertPretrainingCriterion(nn.Module):
+    """CE(MLM, ignore_index=-1) + CE(NSP), as dear/bert_benchmark.py:101-112."""
+
+    def __init__(self, vocab_size: int):
+        super().__init__()
+        self.vocab_size = vocab_size
+
+    def forward(self, prediction_scores, seq_relationship_score, masked_lm_labels, next_sentence_labels):
+        mlm = F.cross_entropy(prediction_scores.view(-1, self.vocab_size).float(), masked_lm_labels.view(-1),
+                              ignore_index=-1)
+        nsp = F.cross_entropy(seq_relationship_score.view(-1, 2).float(), next_sentence_labels.view(-1),
+                              ignore_index=-1)
+        return mlm + nsp
+
+
+def bert_large(**kw): return BertForPreTraining(BERT_LARGE, **kw)
+def bert_base(**kw): return BertForPreTraining(BERT_BASE, **kw)
+
+
+def synthetic_batch(batch_size: int, seq_len: int, vocab_size: int, device, seed: int = 0):
+    """Random BERT-shaped inputs (token ids, mask, segment ids, NSP label, MLM labels)."""
+    g = torch.Generator().manual_seed(seed)
+    input_ids = torch.randint(0, min(vocab_size, 30000), (batch_size, seq_len), generator=g)
+    attention_mask = torch.ones(batch_size, seq_len, dtype=torch.long)
+    token_type_ids = torch.randint(0, 2, (batch_size, seq_len), generator=g)
+    nsp = torch.randint(0, 2, (batch_size,), generator=g)
+    mlm = torch.full((batch_size, seq_len), -1, dtype=torch.long)
+    pick = torch.rand(batch_size, seq_len, generator=g) < 0.15
+    mlm[pick] = input_ids[pick]
+    return tuple(t.to(device) for t in (input_ids, attention_mask, token_type_ids, nsp, mlm))

@@ -9,6 +9,7 @@ the communication stream, Kernel B per bucket — replays as ONE graph launch.
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, Optional
 
 import torch
@@ -28,6 +29,7 @@ class TrainStep:
         self._static_in = None
         self._static_loss = None
         self._engine = getattr(optimizer, "_dear", None)
+        self._debug = bool(os.environ.get("DEAR_GRAPH_DEBUG"))
 
     def _eager(self, *batch):
         *inputs, target = batch
@@ -42,19 +44,35 @@ class TrainStep:
         self.opt.step()
         return loss.detach()
 
+    def _log(self, msg):
+        if self._debug:
+            print("[TrainStep] " + msg, flush=True)
+
     def _capture(self, batch):
         eng = self._engine
         dev = batch[0].device
         self._static_in = tuple(torch.empty_like(t).copy_(t) for t in batch)
+        # warm up on a side stream (the PyTorch whole-network capture recipe): allocator pools,
+        # cuDNN autotuning and autograd streams all settle before the capture
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._eager(*self._static_in)
+            if eng is not None:
+                eng.synchronize(host=False)
+        torch.cuda.current_stream(dev).wait_stream(side)
         if eng is not None:
             eng.synchronize(host=True)
         torch.cuda.synchronize(dev)
+        self._log("warm-up on side stream done; capturing")
         self._graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph):
+        with torch.cuda.graph(self._graph, capture_error_mode="thread_local"):
             loss = self._eager(*self._static_in)
             if eng is not None:
                 eng.synchronize(host=False)     # join the communication stream back into the capture
             self._static_loss = loss
+        self._log("capture done; first replay")
         # the capture only records; run the iteration for real
         self._graph.replay()
         return self._static_loss
