@@ -448,20 +448,26 @@ class _DistributedOptimizer(torch.optim.Optimizer):
 def DistributedOptimizer(optimizer, model, compression=None, is_sparse=False, density=0.001, seq_layernames=None,
                          layerwise_times=None, norm_clip=None, threshold=None, writer=None, gradient_path=None,
                          fp16=False, mgwfbp=False, rdma=False, multi_job_scheduling=False, exclude_parts="",
-                         num_nearby_layers=None, policy=None, verbose=True):
+                         num_nearby_layers=None, policy=None, verbose=True, bo_tuning=False, bo_kwargs=None):
     """Wrap ``optimizer`` (an ``torch.optim.SGD``) for DeAR data-parallel training of ``model``.
 
     Signature-compatible with the reference factory (dear/dear_dopt.py:381-398): the Horovod-era
     keyword arguments are accepted; those that have no meaning here are ignored.  Unlike the
     reference, ``threshold`` (MB; default 25) and ``num_nearby_layers`` are honoured instead of
     being module constants:  ``threshold=None, num_nearby_layers=k`` selects the nearby-layer
-    policy (``k=1`` is "DeAR without tensor fusion").
+    policy (``k=1`` is "DeAR without tensor fusion").  ``bo_tuning=True`` enables the Bayesian
+    buffer-size tuner (the reference's separate ``dopt_rsag_bo`` module).
     """
     if threshold in (None, 0) and num_nearby_layers is None:
         threshold = float(os.environ.get("DEAR_THRESHOLD_MB", THRESHOLD))
     elif threshold in (None, 0):
         threshold = None
     cls = type(optimizer.__class__.__name__, (optimizer.__class__,), dict(_DistributedOptimizer.__dict__))
-    return cls(optimizer.param_groups, model, threshold=threshold,
-               num_nearby_layers=num_nearby_layers if num_nearby_layers is not None else NUM_NEARBY_LAYERS,
-               exclude_parts=exclude_parts, policy=policy, verbose=verbose)
+    opt = cls(optimizer.param_groups, model, threshold=threshold,
+              num_nearby_layers=num_nearby_layers if num_nearby_layers is not None else NUM_NEARBY_LAYERS,
+              exclude_parts=exclude_parts, policy=policy, verbose=verbose)
+    if bo_tuning:
+        # dopt_rsag_bo: Bayesian optimisation of the fusion threshold (dear/dopt_rsag_bo.py:100-101)
+        from .tuner import attach_tuner
+        attach_tuner(opt, verbose=verbose, **(bo_kwargs or {}))
+    return opt
