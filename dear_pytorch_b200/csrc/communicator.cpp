@@ -493,9 +493,10 @@ bool BucketSet::set_pack(int g, const std::vector<int64_t>& src_ptrs, const std:
   std::vector<PackSeg> segs;
   segs.reserve(n);
   uint32_t tiles = 0;
+  bool inplace = false;
   for (size_t i = 0; i < n; ++i) {
     if (nbytes[i] == 0) continue;
-    if (src_ptrs[i] == 0 && !(flags[i] & SEG_ZERO_FILL)) continue;   // in place: nothing to do
+    if (src_ptrs[i] == 0 && !(flags[i] & SEG_ZERO_FILL)) { inplace = true; continue; }   // already in the bucket
     PackSeg s;
     s.src = reinterpret_cast<const void*>(static_cast<uintptr_t>(src_ptrs[i]));
     s.dst_off = static_cast<uint64_t>(dst_off_bytes[i]);
@@ -510,6 +511,7 @@ bool BucketSet::set_pack(int g, const std::vector<int64_t>& src_ptrs, const std:
   }
   const bool same = segs.size() == b.pack_host.size() &&
                     (segs.empty() || std::memcmp(segs.data(), b.pack_host.data(), segs.size() * sizeof(PackSeg)) == 0);
+  b.pack_inplace = inplace;
   if (same) return false;
   b.pack_host = std::move(segs);
   b.ntiles = tiles;
@@ -575,6 +577,7 @@ void BucketSet::reduce_scatter(int g, bool pack) {
     p.segs = cuda ? b.pack_dev : b.pack_host.data();
     p.nseg = static_cast<uint32_t>(b.pack_host.size());
     p.ntiles = b.ntiles;
+    p.direct_out = (comm_->size() == 1 && dtype_ == DT_F32 && !b.pack_inplace) ? 1u : 0u;
   }
   p.sig = arena_->sig_table();
   p.ctrl = arena_->ctrl();

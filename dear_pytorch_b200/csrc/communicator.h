@@ -34,8 +34,8 @@ struct CommOptions {
   int nstreams = 1;
   double spin_timeout_s = 20.0;          // in-kernel bounded spin
   double rendezvous_timeout_s = 120.0;
-  int rs_grid = 16;
-  int ag_grid = 16;
+  int rs_grid = 48;
+  int ag_grid = 48;
   int gen_grid = 8;
 };
 
@@ -142,6 +142,7 @@ class BucketSet {
     std::vector<PackSeg> pack_host;
     std::vector<HyperSeg> hyper_host;
     uint32_t ntiles = 0;
+    bool pack_inplace = false;
     PackSeg* pack_dev = nullptr;
     size_t pack_cap = 0;
     HyperSeg* hyper_dev = nullptr;

@@ -28,7 +28,7 @@ constexpr int kMaxRanks = 16;            // one NVSwitch domain (8 on HGX B200)
 constexpr int kNumChannels = 4096;       // signal-pad channels per arena
 constexpr int kChannelsPerBucket = 4;    // RS_READY, RS_DONE, AG_ARRIVE, AG_PUSHED
 constexpr int kGeneralChannels = 64;     // channels [0,64) are for general ops
-constexpr uint32_t kPackTileBytes = 16384;
+constexpr uint32_t kPackTileBytes = 65536;
 constexpr size_t kSignalPadBytes = size_t(kNumChannels) * kMaxRanks * sizeof(uint32_t);
 
 // Channel ids for the general-purpose ops (all-reduce, broadcast, ...).
@@ -76,7 +76,7 @@ struct PackSeg {
   const void* src;        // local gradient storage; nullptr => nothing to copy
   uint64_t dst_off;       // byte offset inside the bucket
   uint64_t nbytes;        // bytes to copy
-  uint32_t tile_begin;    // exclusive prefix sum of 16 KiB tiles
+  uint32_t tile_begin;    // exclusive prefix sum of 64 KiB tiles
   uint32_t flags;         // bit0: zero-fill the destination (gradient absent)
 };
 constexpr uint32_t SEG_ZERO_FILL = 1u;
@@ -145,6 +145,7 @@ struct RSParams {
   PeerTable sig;           // every rank's signal pad (sig[rank] is local)
   uint32_t* ctrl;          // local control block: epoch[kNumChannels], counter[kNumChannels]
   uint32_t bucket;         // bucket id (selects channels)
+  uint32_t direct_out;     // world==1 && fp32: pack straight into `out`, skip the pull phase
   int rank;
   int world;
   int dtype;               // DType of the gradient bucket

@@ -64,9 +64,10 @@ void rs_impl(const RSParams& p) {
   uint32_t* epoch_p = p.ctrl + ch_ready;
   const uint32_t e = *epoch_p + 1;
   wait_all(sig_local, ch_done, e - 1, p.world, p.timeout_ns, p.status, ST_TIMEOUT_RS_DONE);
+  const bool direct = p.world == 1 && sizeof(T) == 4 && p.direct_out;
   // pack (tile by tile, exactly like the device kernel)
   if (p.segs != nullptr) {
-    char* bucket = reinterpret_cast<char*>(p.grad.ptr[p.rank]);
+    char* bucket = direct ? reinterpret_cast<char*>(p.out) : reinterpret_cast<char*>(p.grad.ptr[p.rank]);
     for (uint32_t tile = 0; tile < p.ntiles; ++tile) {
       const uint32_t si = find_pack_seg(p.segs, p.nseg, tile);
       const PackSeg& sg = p.segs[si];
@@ -80,7 +81,7 @@ void rs_impl(const RSParams& p) {
   signal_all(p.sig, ch_ready, p.rank, p.world, e);
   wait_all(sig_local, ch_ready, e, p.world, p.timeout_ns, p.status, ST_TIMEOUT_RS_READY);
   const uint64_t off = uint64_t(p.rank) * p.shard_elems;
-  for (uint64_t i = 0; i < p.shard_elems; ++i) {
+  for (uint64_t i = 0; i < p.shard_elems && !direct; ++i) {
     float acc = 0.f;
     for (int q = 0; q < p.world; ++q) acc += ld<T>(p.grad.ptr[q], off + i);   // fixed order
     p.out[i] = acc * p.scale;

@@ -223,6 +223,8 @@ template <> struct ElemTraits<__half> {
 // ----------------------------------------------------------------------------
 // Kernel A — pack + reduce-scatter + scale
 // ----------------------------------------------------------------------------
+constexpr int kPackVecPerThread = kPackTileBytes / 16 / kThreads;   // 8 x 128-bit per thread per tile
+
 template <typename T, int W, bool MC>
 __global__ void __launch_bounds__(kThreads, 1) rs_kernel(const RSParams p) {
   using Tr = ElemTraits<T>;
@@ -238,11 +240,15 @@ __global__ void __launch_bounds__(kThreads, 1) rs_kernel(const RSParams p) {
   uint32_t* cnt_pack = p.ctrl + kNumChannels + ch_ready;
   uint32_t* cnt_exit = p.ctrl + kNumChannels + ch_done;
   const uint32_t e = *reinterpret_cast<volatile uint32_t*>(epoch_p) + 1;
+  // single-GPU fp32 fast path: the "reduction" of one rank is a copy, so the pack writes the fp32
+  // shard (== the whole bucket) directly and the pull phase disappears.
+  const bool direct = (W == 1) && (sizeof(T) == 4) && p.direct_out;
 
   // (0) my bucket may still be read by a peer's previous reduce-scatter.
   wait_all_peers(sig_local, ch_done, e - 1, world, p.timeout_ns, p.status, ST_TIMEOUT_RS_DONE);
 
-  // (1) pack: copy this rank's gradients into the symmetric bucket.
+  // (1) pack: copy this rank's gradients into the symmetric bucket (64 KiB tiles, 8 independent
+  //     128-bit loads in flight per thread).
   if (p.segs != nullptr && p.ntiles > 0) {
     const bool in_smem = p.nseg <= kMaxSmemSegs;
     if (in_smem) {
@@ -250,7 +256,7 @@ __global__ void __launch_bounds__(kThreads, 1) rs_kernel(const RSParams p) {
       __syncthreads();
     }
     const PackSeg* segs = in_smem ? s_segs : p.segs;
-    char* bucket = reinterpret_cast<char*>(p.grad.ptr[p.rank]);
+    char* bucket = direct ? reinterpret_cast<char*>(p.out) : reinterpret_cast<char*>(p.grad.ptr[p.rank]);
     for (uint32_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
       const uint32_t si = find_pack_seg(segs, p.nseg, tile);
       const PackSeg sg = segs[si];
@@ -261,13 +267,26 @@ __global__ void __launch_bounds__(kThreads, 1) rs_kernel(const RSParams p) {
       const uint32_t nvec = nb >> 4;
       if (sg.flags & SEG_ZERO_FILL) {
         const uint4 z = make_uint4(0, 0, 0, 0);
-        for (uint32_t v = tid; v < nvec; v += kThreads) reinterpret_cast<uint4*>(d)[v] = z;
+#pragma unroll
+        for (int k = 0; k < kPackVecPerThread; ++k) {
+          const uint32_t v = tid + k * kThreads;
+          if (v < nvec) st_stream(d + (size_t(v) << 4), z);
+        }
         for (uint32_t b = (nvec << 4) + tid * 2; b < nb; b += kThreads * 2)
           *reinterpret_cast<uint16_t*>(d + b) = 0;
       } else if (sg.src != nullptr) {
         const char* s = reinterpret_cast<const char*>(sg.src) + off;
-        for (uint32_t v = tid; v < nvec; v += kThreads)
-          reinterpret_cast<uint4*>(d)[v] = ld_stream(s + (size_t(v) << 4));
+        uint4 r[kPackVecPerThread];
+#pragma unroll
+        for (int k = 0; k < kPackVecPerThread; ++k) {
+          const uint32_t v = tid + k * kThreads;
+          if (v < nvec) r[k] = ld_stream(s + (size_t(v) << 4));
+        }
+#pragma unroll
+        for (int k = 0; k < kPackVecPerThread; ++k) {
+          const uint32_t v = tid + k * kThreads;
+          if (v < nvec) st_stream(d + (size_t(v) << 4), r[k]);
+        }
         for (uint32_t b = (nvec << 4) + tid * 2; b < nb; b += kThreads * 2)
           *reinterpret_cast<uint16_t*>(d + b) = *reinterpret_cast<const uint16_t*>(s + b);
       }
@@ -284,14 +303,14 @@ __global__ void __launch_bounds__(kThreads, 1) rs_kernel(const RSParams p) {
   wait_all_peers(sig_local, ch_ready, e, world, p.timeout_ns, p.status, ST_TIMEOUT_RS_READY);
 
   // (4) pull-reduce my shard from every peer; fp32 accumulate; fused 1/P scale.
-  {
+  if (!direct) {
     const uint64_t nvec = p.shard_elems / EV;
     const uint64_t shard_byte_off = uint64_t(p.rank) * p.shard_elems * sizeof(T);
     const uint64_t gstride = uint64_t(gridDim.x) * kThreads;
     const float scale = p.scale;
     if (MC) {
       const char* mc = reinterpret_cast<const char*>(p.mc_grad) + shard_byte_off;
-      constexpr int U = 4;
+      constexpr int U = 8;
       for (uint64_t v0 = uint64_t(blockIdx.x) * kThreads + tid; v0 < nvec; v0 += gstride * U) {
         uint4 r[U];
 #pragma unroll
@@ -309,56 +328,65 @@ __global__ void __launch_bounds__(kThreads, 1) rs_kernel(const RSParams p) {
             for (int k = 0; k < EV; ++k) f[k] *= scale;
             float4* o = reinterpret_cast<float4*>(p.out + v * EV);
             o[0] = make_float4(f[0], f[1], f[2], f[3]);
-            if (EV == 8) o[1] = make_float4(f[4], f[5], f[6], f[7]);
+            if (EV == 8) o[1] = make_float4(f[EV - 4], f[EV - 3], f[EV - 2], f[EV - 1]);
+          }
+        }
+      }
+    } else if (W > 0) {
+      constexpr int WW = W > 0 ? W : 1;
+      constexpr int U = (WW >= 8) ? 2 : (WW == 4 ? 4 : 8);     // U*W >= 16 loads in flight per thread
+      for (uint64_t v0 = uint64_t(blockIdx.x) * kThreads + tid; v0 < nvec; v0 += gstride * U) {
+        uint4 r[U][WW];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const uint64_t v = v0 + u * gstride;
+#pragma unroll
+          for (int q = 0; q < WW; ++q) {
+            if (v < nvec) {
+              const char* base = reinterpret_cast<const char*>(p.grad.ptr[q]) + shard_byte_off;
+              r[u][q] = ld_stream(base + (v << 4));
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const uint64_t v = v0 + u * gstride;
+          if (v < nvec) {
+            float acc[EV];
+#pragma unroll
+            for (int k = 0; k < EV; ++k) acc[k] = 0.f;
+#pragma unroll
+            for (int q = 0; q < WW; ++q) {   // fixed order => run-to-run deterministic
+              float f[EV];
+              Tr::unpack(r[u][q], f);
+#pragma unroll
+              for (int k = 0; k < EV; ++k) acc[k] += f[k];
+            }
+            float4* o = reinterpret_cast<float4*>(p.out + v * EV);
+            o[0] = make_float4(acc[0] * scale, acc[1] * scale, acc[2] * scale, acc[3] * scale);
+            if (EV == 8)
+              o[1] = make_float4(acc[EV - 4] * scale, acc[EV - 3] * scale, acc[EV - 2] * scale, acc[EV - 1] * scale);
           }
         }
       }
     } else {
-      constexpr int U = (W > 0 && W <= 4) ? 4 : 2;
+      constexpr int U = 2;
       for (uint64_t v0 = uint64_t(blockIdx.x) * kThreads + tid; v0 < nvec; v0 += gstride * U) {
         float acc[U][EV];
 #pragma unroll
         for (int u = 0; u < U; ++u)
 #pragma unroll
           for (int k = 0; k < EV; ++k) acc[u][k] = 0.f;
-        if (W > 0) {
-          uint4 r[U][W > 0 ? W : 1];
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const uint64_t v = v0 + u * gstride;
-#pragma unroll
-            for (int q = 0; q < (W > 0 ? W : 1); ++q) {
-              if (v < nvec) {
-                const char* base = reinterpret_cast<const char*>(p.grad.ptr[q]) + shard_byte_off;
-                r[u][q] = ld_stream(base + (v << 4));
-              }
-            }
-          }
+        for (int q = 0; q < world; ++q) {
+          const char* base = reinterpret_cast<const char*>(p.grad.ptr[q]) + shard_byte_off;
 #pragma unroll
           for (int u = 0; u < U; ++u) {
             const uint64_t v = v0 + u * gstride;
             if (v < nvec) {
+              float f[EV];
+              Tr::unpack(ld_stream(base + (v << 4)), f);
 #pragma unroll
-              for (int q = 0; q < (W > 0 ? W : 1); ++q) {   // fixed order => deterministic
-                float f[EV];
-                Tr::unpack(r[u][q], f);
-#pragma unroll
-                for (int k = 0; k < EV; ++k) acc[u][k] += f[k];
-              }
-            }
-          }
-        } else {
-          for (int q = 0; q < world; ++q) {
-            const char* base = reinterpret_cast<const char*>(p.grad.ptr[q]) + shard_byte_off;
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-              const uint64_t v = v0 + u * gstride;
-              if (v < nvec) {
-                float f[EV];
-                Tr::unpack(ld_stream(base + (v << 4)), f);
-#pragma unroll
-                for (int k = 0; k < EV; ++k) acc[u][k] += f[k];
-              }
+              for (int k = 0; k < EV; ++k) acc[u][k] += f[k];
             }
           }
         }
@@ -367,11 +395,10 @@ __global__ void __launch_bounds__(kThreads, 1) rs_kernel(const RSParams p) {
           const uint64_t v = v0 + u * gstride;
           if (v < nvec) {
             float4* o = reinterpret_cast<float4*>(p.out + v * EV);
-            o[0] = make_float4(acc[u][0] * scale, acc[u][1] * scale, acc[u][2] * scale,
-                               acc[u][3] * scale);
+            o[0] = make_float4(acc[u][0] * scale, acc[u][1] * scale, acc[u][2] * scale, acc[u][3] * scale);
             if (EV == 8)
-              o[1] = make_float4(acc[u][EV - 4] * scale, acc[u][EV - 3] * scale,
-                                 acc[u][EV - 2] * scale, acc[u][EV - 1] * scale);
+              o[1] = make_float4(acc[u][EV - 4] * scale, acc[u][EV - 3] * scale, acc[u][EV - 2] * scale,
+                                 acc[u][EV - 1] * scale);
           }
         }
       }
@@ -391,10 +418,27 @@ __global__ void __launch_bounds__(kThreads, 1) rs_kernel(const RSParams p) {
 // ----------------------------------------------------------------------------
 // Kernel B — sharded SGD + all-gather push
 // ----------------------------------------------------------------------------
+__device__ __forceinline__ void ld_f32x(const float* base, uint64_t v, int ev, float* out) {
+  const float4* m = reinterpret_cast<const float4*>(base + v * ev);
+  const float4 a = m[0];
+  out[0] = a.x; out[1] = a.y; out[2] = a.z; out[3] = a.w;
+  if (ev == 8) {
+    const float4 b = m[1];
+    out[4] = b.x; out[5] = b.y; out[6] = b.z; out[7] = b.w;
+  }
+}
+__device__ __forceinline__ void st_f32x(float* base, uint64_t v, int ev, const float* in) {
+  float4* m = reinterpret_cast<float4*>(base + v * ev);
+  m[0] = make_float4(in[0], in[1], in[2], in[3]);
+  if (ev == 8) m[1] = make_float4(in[4], in[5], in[6], in[7]);
+}
+
 template <typename T, int W, bool MC>
 __global__ void __launch_bounds__(kThreads, 1) ag_kernel(const AGParams p) {
   using Tr = ElemTraits<T>;
   constexpr int EV = Tr::kPerVec;
+  constexpr int EVA = 8;                        // register array length (>= EV)
+  constexpr int U = (EV == 4) ? 4 : 2;          // vectors in flight per thread
   __shared__ HyperSeg s_hyper[kMaxSmemHyper];
 
   const int tid = threadIdx.x;
@@ -427,63 +471,59 @@ __global__ void __launch_bounds__(kThreads, 1) ag_kernel(const AGParams p) {
     const uint64_t shard_elem_off = uint64_t(p.rank) * p.shard_elems;
     const uint64_t gstride = uint64_t(gridDim.x) * kThreads;
     const char* local_param = reinterpret_cast<const char*>(p.param.ptr[p.rank]);
-    for (uint64_t v = uint64_t(blockIdx.x) * kThreads + tid; v < nvec; v += gstride) {
-      const uint64_t ge = shard_elem_off + v * EV;     // element offset within the bucket
-      float pv[EV];
-      if (p.master_shard != nullptr) {
-        const float4* m = reinterpret_cast<const float4*>(p.master_shard + v * EV);
-        float4 a = m[0];
-        pv[0] = a.x; pv[1] = a.y; pv[2] = a.z; pv[3] = a.w;
-        if (EV == 8) { float4 b = m[1]; pv[EV - 4] = b.x; pv[EV - 3] = b.y; pv[EV - 2] = b.z; pv[EV - 1] = b.w; }
-      } else {
-        Tr::unpack(*reinterpret_cast<const uint4*>(local_param + ge * sizeof(T)), pv);
-      }
-      if (p.do_update) {
-        float gv[EV], mv[EV];
-        {
-          const float4* g = reinterpret_cast<const float4*>(p.grad_shard + v * EV);
-          float4 a = g[0];
-          gv[0] = a.x; gv[1] = a.y; gv[2] = a.z; gv[3] = a.w;
-          if (EV == 8) { float4 b = g[1]; gv[EV - 4] = b.x; gv[EV - 3] = b.y; gv[EV - 2] = b.z; gv[EV - 1] = b.w; }
-        }
-        const bool has_mom = p.mom_shard != nullptr;
-        if (has_mom && !p.first_step) {
-          const float4* m = reinterpret_cast<const float4*>(p.mom_shard + v * EV);
-          float4 a = m[0];
-          mv[0] = a.x; mv[1] = a.y; mv[2] = a.z; mv[3] = a.w;
-          if (EV == 8) { float4 b = m[1]; mv[EV - 4] = b.x; mv[EV - 3] = b.y; mv[EV - 2] = b.z; mv[EV - 1] = b.w; }
-        } else {
+    const bool has_mom = p.mom_shard != nullptr;
+    const bool load_mom = has_mom && !p.first_step && p.do_update;
+    for (uint64_t v0 = uint64_t(blockIdx.x) * kThreads + tid; v0 < nvec; v0 += gstride * U) {
+      float pv[U][EVA], gv[U][EVA], mv[U][EVA];
+      // ---- all loads first (memory-level parallelism) ----
 #pragma unroll
-          for (int k = 0; k < EV; ++k) mv[k] = 0.f;
-        }
-        const HyperSeg h = hyper[p.nhyper == 1 ? 0 : find_hyper(hyper, p.nhyper, ge)];
+      for (int u = 0; u < U; ++u) {
+        const uint64_t v = v0 + u * gstride;
+        if (v < nvec) {
+          if (p.master_shard != nullptr) {
+            ld_f32x(p.master_shard, v, EV, pv[u]);
+          } else {
+            Tr::unpack(*reinterpret_cast<const uint4*>(local_param + (shard_elem_off + v * EV) * sizeof(T)), pv[u]);
+          }
+          if (p.do_update) ld_f32x(p.grad_shard, v, EV, gv[u]);
+          if (load_mom) {
+            ld_f32x(p.mom_shard, v, EV, mv[u]);
+          } else {
 #pragma unroll
-        for (int k = 0; k < EV; ++k) pv[k] = sgd_update(pv[k], gv[k], mv[k], h, p.first_step != 0, has_mom);
-        if (has_mom && h.momentum > 0.f) {
-          float4* m = reinterpret_cast<float4*>(p.mom_shard + v * EV);
-          m[0] = make_float4(mv[0], mv[1], mv[2], mv[3]);
-          if (EV == 8) m[1] = make_float4(mv[EV - 4], mv[EV - 3], mv[EV - 2], mv[EV - 1]);
-        }
-        if (p.master_shard != nullptr) {
-          float4* m = reinterpret_cast<float4*>(p.master_shard + v * EV);
-          m[0] = make_float4(pv[0], pv[1], pv[2], pv[3]);
-          if (EV == 8) m[1] = make_float4(pv[EV - 4], pv[EV - 3], pv[EV - 2], pv[EV - 1]);
+            for (int k = 0; k < EV; ++k) mv[u][k] = 0.f;
+          }
         }
       }
-      const uint4 outv = Tr::pack(pv);
-      const uint64_t boff = ge * sizeof(T);
-      if (MC) {
-        multimem_st(reinterpret_cast<char*>(p.mc_param) + boff, outv);
-      } else if (W > 0) {
+      // ---- update + stores ----
 #pragma unroll
-        for (int k = 0; k < (W > 0 ? W : 1); ++k) {
-          const int q = (p.rank + k) % (W > 0 ? W : 1);   // own copy first, then rotate over peers
-          st_stream(reinterpret_cast<char*>(p.param.ptr[q]) + boff, outv);
-        }
-      } else {
-        for (int k = 0; k < world; ++k) {
-          const int q = (p.rank + k) % world;
-          st_stream(reinterpret_cast<char*>(p.param.ptr[q]) + boff, outv);
+      for (int u = 0; u < U; ++u) {
+        const uint64_t v = v0 + u * gstride;
+        if (v < nvec) {
+          const uint64_t ge = shard_elem_off + v * EV;     // element offset within the bucket
+          if (p.do_update) {
+            const HyperSeg h = hyper[p.nhyper == 1 ? 0 : find_hyper(hyper, p.nhyper, ge)];
+#pragma unroll
+            for (int k = 0; k < EV; ++k)
+              pv[u][k] = sgd_update(pv[u][k], gv[u][k], mv[u][k], h, p.first_step != 0, has_mom);
+            if (has_mom && h.momentum > 0.f) st_f32x(p.mom_shard, v, EV, mv[u]);
+            if (p.master_shard != nullptr) st_f32x(p.master_shard, v, EV, pv[u]);
+          }
+          const uint4 outv = Tr::pack(pv[u]);
+          const uint64_t boff = ge * sizeof(T);
+          if (MC) {
+            multimem_st(reinterpret_cast<char*>(p.mc_param) + boff, outv);
+          } else if (W > 0) {
+#pragma unroll
+            for (int k = 0; k < (W > 0 ? W : 1); ++k) {
+              const int q = (p.rank + k) % (W > 0 ? W : 1);   // own copy first, then rotate over peers
+              st_stream(reinterpret_cast<char*>(p.param.ptr[q]) + boff, outv);
+            }
+          } else {
+            for (int k = 0; k < world; ++k) {
+              const int q = (p.rank + k) % world;
+              st_stream(reinterpret_cast<char*>(p.param.ptr[q]) + boff, outv);
+            }
+          }
         }
       }
     }
@@ -491,8 +531,8 @@ __global__ void __launch_bounds__(kThreads, 1) ag_kernel(const AGParams p) {
     if (p.zero_grad != nullptr) {
       const uint64_t zvec = p.zero_bytes >> 4;
       const uint4 z = make_uint4(0, 0, 0, 0);
-      uint4* zp = reinterpret_cast<uint4*>(p.zero_grad);
-      for (uint64_t v = uint64_t(blockIdx.x) * kThreads + tid; v < zvec; v += gstride) zp[v] = z;
+      char* zp = reinterpret_cast<char*>(p.zero_grad);
+      for (uint64_t v = uint64_t(blockIdx.x) * kThreads + tid; v < zvec; v += gstride) st_stream(zp + (v << 4), z);
     }
   }
 

@@ -1,0 +1,242 @@
+"""WFBP / MG-WFBP baselines: gradient all-reduce overlapped with back-propagation.
+
+Reference: wfbp/dopt.py (on comm_core) and {dear,mgwfbp,wfbp}/hv_distributed_optimizer.py (on
+Horovod).  Behaviour kept:
+  * grouping in REVERSE layer order by number of elements, ``threshold=0`` => per tensor
+    (wfbp/dopt.py:321-355);
+  * MG-WFBP merging from layer-wise backward times and an alpha-beta all-reduce model
+    (wfbp/dopt.py:380-486), ASC variant (hv_distributed_optimizer.py:353-427);
+  * dense path = one all-reduce per group launched from the gradient hook; ``step()`` =
+    synchronise, average, then the wrapped optimizer's own ``step()`` (wfbp/dopt.py:694-701,807-968);
+  * sparse path = compress + all-gather of (values, indices) (wfbp/dopt.py:703-742).
+Deliberate differences: the comm stream waits on the compute stream with an event (the reference
+synchronises the host inside the hook, wfbp/dopt.py:696); collectives are torch.distributed NCCL
+(comm_core / Horovod are not installable here).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from ... import runtime
+from ...utils import perf_model
+from ..compression import NoneCompressor, compressors
+
+
+def threshold_groups(sizes_rev: Sequence[int], threshold: int) -> List[List[int]]:
+    """``sizes_rev`` in backward order; close a group once it holds >= ``threshold`` elements."""
+    groups, cur, acc = [], [], 0
+    for i, n in enumerate(sizes_rev):
+        cur.append(i)
+        acc += n
+        if acc >= threshold:
+            groups.append(cur)
+            cur, acc = [], 0
+    if cur:
+        groups.append(cur)
+    return groups
+
+
+def mgwfbp_groups(sizes: Sequence[int], tb: Sequence[float], alpha: float, beta: float, nbytes: int = 4,
+                  asc: bool = False, small: int = 8192) -> List[List[int]]:
+    """MG-WFBP merged-gradient grouping (Shi et al., INFOCOM 2019).
+
+    ``sizes`` / ``tb``: per-layer element counts and backward times in FORWARD order.  Returns
+    groups of layer indices in backward order (first group = last layers).
+    """
+    L = len(sizes)
+    p = list(sizes)
+    tc = [perf_model.predict_allreduce_time_with_size(alpha, beta, s * nbytes) for s in p]
+    taob = [0.0] * L
+    for l in range(L - 2, -1, -1):
+        taob[l] = taob[l + 1] + tb[l + 1]
+
+    def comm_start():
+        taoc = [0.0] * L
+        taoc[L - 1] = taob[L - 1] + tb[L - 1]
+        for l in range(L - 2, -1, -1):
+            taoc[l] = max(taoc[l + 1] + tc[l + 1], taob[l] + tb[l])
+        return taoc
+
+    def merge(l):
+        tc[l] = 0.0
+        p[l - 1] += p[l]
+        p[l] = 0
+        tc[l - 1] = perf_model.predict_allreduce_time_with_size(alpha, beta, p[l - 1] * nbytes)
+
+    taoc = comm_start()
+    groups, group = [], []
+    for l in range(L - 1, 0, -1):
+        group.append(l)
+        ready_prev = taob[l - 1] + tb[l - 1]          # when layer l-1's gradient is ready
+        merged = False
+        if ready_prev < taoc[l] + tc[l]:              # comm of l would still be running
+            if taoc[l] > ready_prev:                  # ... and has not even started: merging is free
+                merge(l); taoc = comm_start(); merged = True
+            elif not asc and (ready_prev - taoc[l]) < alpha:   # waiting costs less than a start-up
+                merge(l); taoc = comm_start(); merged = True
+        if not merged and not asc and p[l] < small:
+            merge(l); taoc = comm_start(); merged = True
+        if not merged:
+            groups.append(group)
+            group = []
+    group.append(0)
+    groups.append(group)
+    return groups
+
+
+class _DistributedOptimizer(torch.optim.Optimizer):
+    def __init__(self, params, named_parameters, compression=None, is_sparse=False, density=0.001,
+                 seq_layernames=None, layerwise_times=None, norm_clip=None, threshold=0, fp16=False, mgwfbp=False,
+                 asc=False, rdma=False, alpha=None, beta=None, verbose=True):
+        super(self.__class__, self).__init__(params)
+        if not runtime.is_initialized():
+            runtime.init()
+        self._rank, self._world, self._device = runtime.rank(), runtime.size(), runtime.device()
+        self._group = runtime.group()
+        self._compression = compression or NoneCompressor()
+        self._sparse = bool(is_sparse) and not isinstance(self._compression, NoneCompressor)
+        self._density = density
+        self._norm_clip = norm_clip
+        named = list(named_parameters)
+        self._names = {p: n for n, p in named if p.requires_grad}
+        self._params = [p for _, p in named if p.requires_grad]
+        self._fwd_order = [n for n, p in named if p.requires_grad]
+        self._cuda = self._device.type == "cuda"
+        if self._cuda:
+            self._stream = torch.cuda.Stream(device=self._device, priority=-1)
+        self.alpha, self.beta = alpha, beta
+        if mgwfbp or asc:
+            if layerwise_times is None or seq_layernames is None:
+                raise ValueError("MG-WFBP needs seq_layernames and layerwise_times (utils.profiling.benchmark)")
+            if self.alpha is None:
+                table = perf_model.ALPHA_BETA_56GbIB if rdma else perf_model.ALPHA_BETA_10GbE
+                self.alpha, self.beta = table.get(self._world, table[max(table)])
+            by_name = {n: p for n, p in named}
+            sizes = [by_name[n].numel() for n in seq_layernames]
+            gidx = mgwfbp_groups(sizes, layerwise_times, self.alpha, self.beta, 2 if fp16 else 4, asc=asc)
+            self._groups = [[seq_layernames[i] for i in g] for g in gidx]
+        else:
+            rev = self._fwd_order[::-1]
+            by_name = {n: p for n, p in named}
+            gidx = threshold_groups([by_name[n].numel() for n in rev], int(threshold))
+            self._groups = [[rev[i] for i in g] for g in gidx]
+        self._by_name = {n: p for n, p in named}
+        self._group_of = {n: gi for gi, g in enumerate(self._groups) for n in g}
+        self._buffers: Dict[int, torch.Tensor] = {}
+        self._offsets: Dict[str, tuple] = {}
+        for gi, g in enumerate(self._groups):
+            off = 0
+            for n in g:
+                k = self._by_name[n].numel()
+                self._offsets[n] = (off, off + k)
+                off += k
+            self._buffers[gi] = torch.zeros(off, device=self._device, dtype=self._by_name[g[0]].dtype)
+        self._arrived = [0] * len(self._groups)
+        self._launched: Dict[int, object] = {}
+        self._hooks = []
+        if self._world > 1:
+            for p in self._params:
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
+        if verbose and self._rank == 0:
+            print("# of groups: ", len(self._groups), ", # of layers: ", len(self._params))
+
+    # ---- alpha/beta measurement (wfbp/dopt.py:260-285) ----------------------------------------
+    def benchmark_communication(self, num_iters: int = 20):
+        from ...utils.profiling import CommunicationProfiler
+        sync = (lambda: torch.cuda.synchronize()) if self._cuda else (lambda: None)
+        prof = CommunicationProfiler(lambda t: dist.all_reduce(t, group=self._group), sync, device=self._device)
+        sizes, times = prof.benchmark(num_iters)
+        a, b = prof.fit_alpha_beta(sizes, times)
+        ab = runtime.broadcast_object((a, b), src=0)
+        self.alpha, self.beta = ab
+        return ab
+
+    # ---- backward hook ------------------------------------------------------------------------
+    def _on_grad(self, p):
+        n = self._names[p]
+        gi = self._group_of[n]
+        a, b = self._offsets[n]
+        self._buffers[gi][a:b].copy_(p.grad.reshape(-1))
+        self._arrived[gi] += 1
+        if self._arrived[gi] == len(self._groups[gi]):
+            self._launch(gi)
+
+    def _launch(self, gi):
+        buf = self._buffers[gi]
+        ctx = torch.cuda.stream(self._stream) if self._cuda else None
+        if self._cuda:
+            self._stream.wait_stream(torch.cuda.current_stream(self._device))
+            ctx.__enter__()
+        try:
+            if self._sparse:
+                name = "group-%d" % gi
+                _, idx, vals = self._compression.compress(buf, name, ratio=self._density)
+                k = idx.numel()
+                all_vals = torch.empty(k * self._world, dtype=vals.dtype, device=buf.device)
+                all_idx = torch.empty(k * self._world, dtype=idx.dtype, device=buf.device)
+                dist.all_gather_into_tensor(all_vals, vals.contiguous(), group=self._group)
+                dist.all_gather_into_tensor(all_idx, idx.contiguous(), group=self._group)
+                self._launched[gi] = (all_vals, all_idx)
+            else:
+                dist.all_reduce(buf, group=self._group)
+                self._launched[gi] = True
+        finally:
+            if self._cuda:
+                ctx.__exit__(None, None, None)
+
+    def synchronize(self):
+        if self._world == 1:
+            return
+        for gi in range(len(self._groups)):          # groups whose parameters got no gradient
+            if gi not in self._launched:
+                self._launch(gi)
+        if self._cuda:
+            torch.cuda.current_stream(self._device).wait_stream(self._stream)
+        for gi, g in enumerate(self._groups):
+            buf = self._buffers[gi]
+            res = self._launched.pop(gi)
+            if self._sparse:
+                all_vals, all_idx = res
+                buf.zero_()
+                buf.scatter_add_(0, all_idx, all_vals)
+            buf.div_(self._world)
+            for n in g:
+                a, b = self._offsets[n]
+                p = self._by_name[n]
+                if p.grad is not None:
+                    p.grad.copy_(buf[a:b].view_as(p.grad))
+            self._arrived[gi] = 0
+        if self._norm_clip is not None:
+            torch.nn.utils.clip_grad_norm_(self._params, self._norm_clip)
+
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        self.synchronize()
+        super(self.__class__, self).step()
+        return loss
+
+
+def DistributedOptimizer(optimizer, named_parameters=None, model: Optional[nn.Module] = None, compression=None,
+                         is_sparse=False, density=0.001, seq_layernames=None, layerwise_times=None, norm_clip=None,
+                         threshold=0, writer=None, gradient_path=None, fp16=False, mgwfbp=False, asc=False, rdma=False,
+                         multi_job_scheduling=False, alpha=None, beta=None, verbose=True, **ignored):
+    """WFBP (``threshold=0``), threshold fusion, MG-WFBP (``mgwfbp=True``) or ASC (``asc=True``)."""
+    if named_parameters is None:
+        if model is None:
+            raise ValueError("pass named_parameters or model")
+        named_parameters = model.named_parameters()
+    if isinstance(compression, str) or compression is None:
+        compression = compressors[compression]()
+    cls = type(optimizer.__class__.__name__, (optimizer.__class__,), dict(_DistributedOptimizer.__dict__))
+    return cls(optimizer.param_groups, list(named_parameters), compression=compression, is_sparse=is_sparse,
+               density=density, seq_layernames=seq_layernames, layerwise_times=layerwise_times, norm_clip=norm_clip,
+               threshold=threshold, fp16=fp16, mgwfbp=mgwfbp, asc=asc, rdma=rdma, alpha=alpha, beta=beta,
+               verbose=verbose)

@@ -65,6 +65,7 @@ class DearEngine:
         self._mom_initialised = False
         self._hooks = []
         self._closed = False
+        self._wt = None                    # optional wait-time recorder (variants.WaitTimeBucketing)
         self._step_callbacks = []          # called at the re-bucketing safe point
         self._safe_point_actions = []
 
@@ -91,6 +92,9 @@ class DearEngine:
         self._check_plan_consistency()
         self._build(initial=True)
         self._register_hooks()
+        if os.environ.get("DEAR_TIMELINE"):
+            from ..utils import trace
+            trace.attach(self)
 
     # ------------------------------------------------------------------ plan / buffers
     def _apply_policy(self, policy):
@@ -166,6 +170,9 @@ class DearEngine:
         self._nbytes = [[s.numel * s.param.element_size() for s in b.slots] for b in plan.buckets]
         self._hyper_key = [None] * nb
         self._module_bucket = list(plan.module_bucket)
+        if getattr(self, "timeline", None) is not None:
+            from ..utils import trace
+            trace.attach_backend(self)
         if self.verbose:
             print(plan.describe())
 
@@ -220,6 +227,8 @@ class DearEngine:
                 gv.copy_(grad)
                 p.grad = gv
         self._arrived[g][i] = True
+        if self._wt is not None:
+            self._wt.param_in(s)
         self._n_arrived[g] += 1
         if self._n_arrived[g] == self._n_params[g]:
             self._complete[g] = True
@@ -238,6 +247,8 @@ class DearEngine:
                 self.backend.set_pack(g, self._src[g], self._dst_off[g], self._nbytes[g], self._flags[g])
             self.backend.reduce_scatter(g, True)
             self._rs_launched[g] = True
+            if self._wt is not None:
+                self._wt.bucket_out(g)
             self._next_rs -= 1
 
     # ------------------------------------------------------------------ hyper-parameters
@@ -388,6 +399,8 @@ class DearEngine:
             h.remove()
         self._hooks.clear()
         self.synchronize(host=True)
+        if getattr(self, "timeline", None) is not None:
+            self.timeline.close()
 
 
 # =====================================================================================
