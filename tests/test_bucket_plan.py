@@ -1,0 +1,114 @@
+"""Bucket planner: reference grouping rules + layout invariants."""
+import torch
+import torch.nn as nn
+from hypothesis import given, settings, strategies as st
+
+from dear_pytorch_b200.parallel.bucket import BucketPlan, PARAM_ALIGN_BYTES, SHARD_ALIGN_BYTES
+
+
+def mlp(widths):
+    layers = []
+    for a, b in zip(widths[:-1], widths[1:]):
+        layers += [nn.Linear(a, b), nn.ReLU()]
+    return nn.Sequential(*layers)
+
+
+def check_invariants(plan: BucketPlan, world: int):
+    seen = set()
+    for b in plan.buckets:
+        es = torch.tensor([], dtype=b.dtype).element_size()
+        assert b.padded_numel % world == 0
+        assert (b.shard_numel * es) % SHARD_ALIGN_BYTES == 0
+        prev_end = 0
+        for i, s in enumerate(b.slots):
+            assert s.bucket == b.index and s.index_in_bucket == i
+            assert (s.start * es) % PARAM_ALIGN_BYTES == 0
+            assert s.start >= prev_end and s.end <= b.padded_numel
+            prev_end = s.end
+            assert s.param not in seen
+            seen.add(s.param)
+            assert s.param.dtype == b.dtype
+    assert len(seen) == len(plan.slots)
+    assert all(g >= 0 for g in plan.module_bucket)
+
+
+@settings(max_examples=40, deadline=None)
+@given(widths=st.lists(st.integers(1, 70), min_size=2, max_size=9), world=st.sampled_from([1, 2, 3, 4, 8]),
+       thr=st.floats(0.00001, 0.05))
+def test_threshold_policy_invariants(widths, world, thr):
+    model = mlp(widths)
+    plan = BucketPlan(model, world).group_by_threshold(thr)
+    check_invariants(plan, world)
+    # reference rule (dear/dear_dopt.py:125-139): a group is closed when adding the next module would reach the threshold
+    sizes = [plan.module_size_mb(i) for i in range(len(plan.modules))]
+    for b in plan.buckets:
+        tot = sum(sizes[i] for i in b.module_indices)
+        if len(b.module_indices) > 1:
+            assert tot - sizes[b.module_indices[-1]] + sizes[b.module_indices[-1]] < thr or tot < thr + max(sizes)
+    # module order is preserved across buckets
+    flat = [mi for b in plan.buckets for mi in b.module_indices]
+    assert flat == sorted(flat)
+
+
+@settings(max_examples=25, deadline=None)
+@given(n=st.integers(1, 12), k=st.integers(-1, 5).filter(lambda v: v != 0), world=st.sampled_from([1, 2, 4]))
+def test_nearby_layers_policy(n, k, world):
+    model = mlp([4] * (n + 1))
+    plan = BucketPlan(model, world).group_by_nearby_layers(k)
+    check_invariants(plan, world)
+    if k < 0:
+        assert len(plan.buckets) == 1
+    else:
+        assert [len(b.module_indices) for b in plan.buckets] == [k] * (n // k) + ([n % k] if n % k else [])
+
+
+def test_reference_bucket_sizes_resnet50_vgg16():
+    """The 25 MB rule reproduces the bucket sizes the reference prints."""
+    from dear_pytorch_b200.models.registry import create
+    p = BucketPlan(create("resnet50"), 8).group_by_threshold(25)
+    assert len(p.buckets) == 5
+    assert all(abs(b.size_mb - r) < 0.1 for b, r in zip(p.buckets, [24.1, 23.6, 21.0, 21.0, 7.8]))
+    p = BucketPlan(create("vgg16"), 8).group_by_threshold(25)
+    assert [round(b.size_mb) for b in p.buckets] == [20, 18, 18, 392, 64, 16]
+
+
+def test_shared_parameters_belong_to_first_owner():
+    class Tied(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.emb = nn.Embedding(10, 4)
+            self.mid = nn.Linear(4, 4)
+            self.out = nn.Linear(4, 10, bias=False)
+            self.out.weight = self.emb.weight
+
+        def forward(self, x):
+            return self.out(self.mid(self.emb(x)))
+    m = Tied()
+    plan = BucketPlan(m, 2).group_per_module()
+    assert len(plan.modules) == 2                      # `out` owns nothing of its own
+    assert plan.slot_of[m.emb.weight].module_index == 0
+    check_invariants(plan, 2)
+
+
+def test_mixed_dtypes_split_per_group_not_per_layer():
+    m = nn.Sequential(nn.Linear(8, 8), nn.LayerNorm(8), nn.Linear(8, 8), nn.LayerNorm(8)).to(torch.bfloat16)
+    for mod in m:
+        if isinstance(mod, nn.LayerNorm):
+            mod.float()
+    plan = BucketPlan(m, 2).group_by_nearby_layers(-1)
+    assert len(plan.buckets) == 2
+    assert {b.dtype for b in plan.buckets} == {torch.bfloat16, torch.float32}
+    check_invariants(plan, 2)
+
+
+def test_flags_and_hyper_segments():
+    m = mlp([3, 5, 7, 2])
+    plan = BucketPlan(m, 2).group_by_flags([0, 1, 1])
+    assert [len(b.module_indices) for b in plan.buckets] == [2, 1]
+    params = list(m.parameters())
+    group_of = {p: (0 if p.dim() > 1 else 1) for p in params}     # weights vs biases
+    segs = plan.hyper_segments(0, group_of)
+    assert [g for _, g in segs] == [0, 1, 0, 1]
+    assert segs[-1][0] == plan.buckets[0].padded_numel
+    ends = [e for e, _ in segs]
+    assert ends == sorted(ends)

@@ -1,0 +1,121 @@
+"""The native communicator's operation family on the host-emulation backend, and the Comm facade /
+tensor-fusion helpers on both CPU backends (counterpart of common/comm_core/tests/test_comm.py, which
+only prints norms for a human to eyeball)."""
+import pytest
+import torch
+
+from _mp import run_ranks
+
+
+def ops_worker(rank, world):
+    import dear_pytorch_b200 as dear
+    from dear_pytorch_b200.parallel.comm import Comm
+    c = Comm()
+    out = {}
+    t = torch.arange(17.0) * (rank + 1)
+    c.syncStream(c.allReduce(t, 1.0))
+    out["allreduce"] = t.clone()
+    t2 = torch.arange(17.0) * (rank + 1)
+    c.syncStream(c.allReduceRB(t2, 1.0))
+    out["allreduce_rb"] = t2.clone()
+    n = 8 * world
+    t3 = torch.arange(float(n)) + rank
+    c.syncStream(c.allReduceRSAG(t3, 1.0 / world))
+    out["rsag_avg"] = t3.clone()
+    send = torch.arange(float(n)) * (rank + 1)
+    recv = torch.zeros(n // world)
+    c.syncStream(c.reduceScatter(send, recv, 1.0))
+    out["reduce_scatter"] = recv.clone()
+    gathered = torch.zeros(3 * world)
+    c.syncStream(c.allGather(torch.full((3,), float(rank)), gathered))
+    out["allgather"] = gathered.clone()
+    b = torch.arange(5, dtype=torch.int64) * (rank + 2)
+    c.syncStream(c.bcast(b, world - 1))
+    out["bcast_int64"] = b.clone()
+    r = torch.ones(6) * (rank + 1)
+    c.syncStream(c.reduce(r, 0, 1.0))
+    out["reduce_root0"] = r.clone()
+    s, v = torch.full((4,), float(rank)), torch.zeros(4)
+    c.syncStream(c.sendrecv(s, v, (rank + 1) % world))
+    out["sendrecv"] = v.clone()
+    outs = [torch.zeros(2, 2), torch.zeros(600, 600)]
+    c.multiBcast([torch.ones(2, 2), torch.ones(600, 600)], outs, lambda t, o: o.copy_(t * 3))
+    out["multibcast"] = (float(outs[0].sum()), float(outs[1].sum()))
+    out["free_streams"] = c.getNumOfFreeStreams()
+    avg = dear.allreduce(torch.tensor([float(rank)]))
+    out["api_allreduce"] = float(avg)
+    dear.barrier()
+    return out
+
+
+@pytest.mark.parametrize("backend", ["emu", "gloo"])
+def test_collective_family(backend):
+    world = 2
+    outs = run_ranks(ops_worker, world=world, backend=backend)
+    s = sum(range(1, world + 1))
+    for r, o in enumerate(outs):
+        torch.testing.assert_close(o["allreduce"], torch.arange(17.0) * s)
+        torch.testing.assert_close(o["allreduce_rb"], torch.arange(17.0) * s)
+        torch.testing.assert_close(o["rsag_avg"], torch.arange(16.0) + 0.5)
+        per = 16 // world
+        torch.testing.assert_close(o["reduce_scatter"], (torch.arange(16.0) * s)[r * per:(r + 1) * per])
+        torch.testing.assert_close(o["allgather"], torch.arange(world).repeat_interleave(3).float())
+        assert torch.equal(o["bcast_int64"], torch.arange(5) * (world - 1 + 2))
+        if r == 0:
+            torch.testing.assert_close(o["reduce_root0"], torch.ones(6) * s)
+        torch.testing.assert_close(o["sendrecv"], torch.full((4,), float((r + 1) % world)))
+        assert o["multibcast"] == (12.0, 3.0 * 600 * 600)
+        assert o["free_streams"] >= 1
+        assert abs(o["api_allreduce"] - 0.5) < 1e-6
+
+
+def fusion_worker(rank, world):
+    from dear_pytorch_b200.parallel.tensorfusion import (CollectiveOp, CommReduceScatter, MergedCommCollective,
+                                                         MergedCommReduce, TensorGroup)
+    names = ["a", "b", "c", "d", "e"]
+    sizes = {"a": 3, "b": 5, "c": 2, "d": 7, "e": 1}
+    tg = TensorGroup(names, num_nearby_layers=2, sizes=sizes)
+    assert tg.groups == [["a", "b"], ["c", "d"], ["e"]]
+    assert tg.push_tensor("a", torch.ones(3))[1] is None
+    gname, buf = tg.push_tensor("b", torch.full((5,), 2.0))
+    assert gname == "group-0" and buf.tolist() == [1.0] * 3 + [2.0] * 5
+    tg.regroup_by_flags([1, 0, 0, 1, 0])
+    assert tg.groups == [["a", "b", "c"], ["d", "e"]]
+
+    tensors = {n: torch.full((sizes[n],), float(rank + 1)) for n in names}
+    mc = MergedCommCollective(names, merge=True, op=CollectiveOp.ALL_REDUCE, num_nearby_layers=2)
+    mc.init_tensor_group(names, sizes)
+    launched = [mc.collective_async_(n, tensors[n]) for n in names]
+    assert sum(h is not None for h in launched) == 3
+    res = mc.synchronize()
+    total = float(sum(range(1, world + 1)))
+    assert all(torch.equal(res[n], torch.full((sizes[n],), total)) for n in names)
+
+    sym = torch.tensor([[1.0, 2.0], [2.0, 3.0]]) * (rank + 1)
+    ms = MergedCommCollective(merge=False, symmetric=True, op=CollectiveOp.ALL_REDUCE)
+    ms.collective_async_("k", sym)
+    ms.synchronize()
+    assert torch.equal(sym, torch.tensor([[1.0, 2.0], [2.0, 3.0]]) * total)
+
+    red = MergedCommReduce(merge=False, op=CollectiveOp.REDUCE)
+    x = torch.ones(4) * (rank + 1)
+    red.reduce_async_("x", x, 0)
+    red.synchronize()
+    if rank == 0:
+        assert torch.equal(x, torch.full((4,), total))
+
+    rs = CommReduceScatter(op=CollectiveOp.REDUCE_SCATTER)
+    ag = CommReduceScatter(op=CollectiveOp.ALL_GATHER)
+    pad = torch.arange(8.0) * (rank + 1)
+    shard = torch.zeros(8 // world)
+    rs.collective_async_("g", pad, shard)
+    rs.synchronize()
+    ag.collective_async_("g", pad, shard)
+    ag.synchronize()
+    assert torch.equal(pad, torch.arange(8.0) * total)         # RS followed by AG == all-reduce
+    return True
+
+
+@pytest.mark.parametrize("backend", ["emu", "gloo"])
+def test_tensorfusion_helpers(backend):
+    assert all(run_ranks(fusion_worker, world=2, backend=backend))

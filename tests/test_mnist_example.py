@@ -1,0 +1,22 @@
+"""BASELINE.json config #1: the MNIST example with dear.DistributedOptimizer, world_size=2, CPU/gloo."""
+import os
+import sys
+
+from _mp import run_ranks
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def mnist_worker(rank, world):
+    sys.path.insert(0, os.path.join(ROOT, "examples", "mnist"))
+    import pytorch_mnist
+    loss, acc = pytorch_mnist.main(["--no-cuda", "--epochs", "2", "--train-size", "1500", "--test-size", "400",
+                                    "--batch-size", "50", "--log-interval", "1000", "--lr", "0.05"])
+    return loss, acc
+
+
+def test_mnist_two_ranks_gloo_learns():
+    outs = run_ranks(mnist_worker, world=2, backend="gloo", timeout=400)
+    (l0, a0), (l1, a1) = outs
+    assert abs(l0 - l1) < 1e-6 and abs(a0 - a1) < 1e-6       # metric averaging agrees across ranks
+    assert a0 > 0.7, "accuracy %.3f: the model did not learn" % a0
