@@ -1,0 +1,20 @@
+#!/bin/bash
+# Single-node launcher (replaces the reference's mpirun + hostfile scripts, */horovod_mpi_cj.sh).
+# Environment "flags", as in the reference:
+#   dnn (resnet50) bs (64) nworkers (8) method (dear) dtype (fp32) threshold (25) exclude_parts ("")
+#   senlen (64, BERT only)  nstreams (1)  graph (0)
+dnn="${dnn:-resnet50}"; bs="${bs:-64}"; nworkers="${nworkers:-8}"; method="${method:-dear}"
+dtype="${dtype:-fp32}"; threshold="${threshold:-25}"; exclude_parts="${exclude_parts:-}"; senlen="${senlen:-64}"
+nstreams="${nstreams:-1}"; graph="${graph:-0}"
+here="$(cd "$(dirname "$0")/.." && pwd)"
+[ -f "$here/configs/envs.conf" ] && source "$here/configs/envs.conf"
+if [[ "$dnn" == bert* ]]; then
+  driver="$here/benchmarks/bert_benchmark.py"; extra="--sentence-len $senlen"
+else
+  driver="$here/benchmarks/imagenet_benchmark.py"; extra=""
+fi
+port="${MASTER_PORT:-$((20000 + RANDOM % 20000))}"
+exec "${PY:-python}" -m torch.distributed.run --nnodes=1 --nproc-per-node "$nworkers" \
+  --master-addr 127.0.0.1 --master-port "$port" "$driver" --model "$dnn" --batch-size "$bs" \
+  --method "$method" --dtype "$dtype" --threshold "$threshold" --nstreams "$nstreams" --graph "$graph" \
+  ${exclude_parts:+--exclude-parts "$exclude_parts"} $extra "$@"
