@@ -50,27 +50,69 @@ def run(args):
     hvd.init()
     cudnn.benchmark = True
     rank, world = hvd.rank(), hvd.size()
-    if args.model != "resnet50" and not hasattr(models, args.model):
-        return _unavailable("model %s is not in torchvision" % args.model)
-    model = getattr(models, args.model)().cuda()
-    optimizer = optim.SGD(model.parameters(), lr=0.01 * world)
+    is_bert = args.model in ("bert", "bert_large", "bert_base")
+    B = args.batch_size
+    if is_bert:
+        # dear/bert_benchmark.py:72-122, with the installed transformers (5.x returns ModelOutput, so
+        # return_dict=False restores the tuple the reference unpacks)
+        try:
+            from transformers import BertConfig, BertForPreTraining
+        except Exception as exc:
+            return _unavailable("transformers is not importable: %r" % (exc,))
+        cfg_file = "bert_base_config.json" if args.model == "bert_base" else "bert_config.json"
+        config = BertConfig.from_json_file(os.path.join(REF, "dear", cfg_file))
+        if config.vocab_size % 8 != 0:
+            config.vocab_size += 8 - (config.vocab_size % 8)
+        vocab_size = config.vocab_size
+        model = BertForPreTraining(config).cuda()
+        max_len = args.sentence_len
+        input_ids = (torch.rand(B, max_len) * 2000).long().cuda()
+        attention_masks = torch.rand(B, max_len).long().cuda()
+        token_type_ids = torch.rand(B, max_len).long().cuda()
+        next_sentence_label = torch.rand(B, 1).long().cuda()
+        masked_lm_labels = torch.rand(B, max_len).long().cuda()
+        loss_fct = torch.nn.CrossEntropyLoss(ignore_index=-1)
+        optimizer = optim.SGD(model.parameters(), lr=2e-5)
+        size = max_len
+        unit, metric = "samples/s", "samples/sec (BERT-%s pre-training, seq %d, DeAR tensor fusion)" % (
+            "base" if args.model == "bert_base" else "large", max_len)
+    else:
+        if not hasattr(models, args.model):
+            return _unavailable("model %s is not in torchvision" % args.model)
+        model = getattr(models, args.model)().cuda()
+        optimizer = optim.SGD(model.parameters(), lr=0.01 * world)
+        size = 299 if args.model == "inception_v3" else 224
+        data = torch.randn(B, 3, size, size).cuda()
+        target = torch.LongTensor(B).random_() % 1000
+        target = target.cuda()
+        unit, metric = "images/s", "images/sec (ResNet-50 synthetic ImageNet training, DeAR tensor fusion)"
     if world > 1:
         optimizer = hvd.DistributedOptimizer(optimizer, model=model)
         hvd.broadcast_parameters(model.state_dict(), root_rank=0)
-    B = args.batch_size
-    size = 224
-    data = torch.randn(B, 3, size, size).cuda()
-    target = torch.LongTensor(B).random_() % 1000
-    target = target.cuda()
 
-    def benchmark_step(d=data, t=target):
-        optimizer.zero_grad()
-        output = model(d)
-        loss = F.cross_entropy(output, t)
-        loss.backward()
-        optimizer.step()
-        torch.cuda.synchronize()
-        return loss
+    if is_bert:
+        def benchmark_step(ids=None, tgt=None):
+            ids = input_ids if ids is None else ids
+            optimizer.zero_grad()
+            prediction_scores, seq_relationship_score = model(input_ids=ids, token_type_ids=token_type_ids,
+                                                              attention_mask=attention_masks, return_dict=False)
+            loss = loss_fct(prediction_scores.view(-1, vocab_size), masked_lm_labels.view(-1)) + \
+                loss_fct(seq_relationship_score.view(-1, 2), next_sentence_label.view(-1))
+            loss.backward()
+            optimizer.step()
+            torch.cuda.synchronize()
+            return loss
+    else:
+        def benchmark_step(d=None, t=None):
+            d = data if d is None else d
+            t = target if t is None else t
+            optimizer.zero_grad()
+            output = model(d)
+            loss = F.cross_entropy(output, t)
+            loss.backward()
+            optimizer.step()
+            torch.cuda.synchronize()
+            return loss
 
     import torch.distributed as dist
 
@@ -105,8 +147,12 @@ def run(args):
 
     e2e = None
     if not args.no_e2e:
-        hx = [torch.randn(B, 3, size, size).pin_memory() for _ in range(4)]
-        hy = [(torch.LongTensor(B).random_() % 1000).pin_memory() for _ in range(4)]
+        if is_bert:
+            hx = [(torch.rand(B, size) * 2000).long().pin_memory() for _ in range(4)]
+            hy = [torch.zeros(1, dtype=torch.long).pin_memory() for _ in range(4)]
+        else:
+            hx = [torch.randn(B, 3, size, size).pin_memory() for _ in range(4)]
+            hy = [(torch.LongTensor(B).random_() % 1000).pin_memory() for _ in range(4)]
         k = [0]
         losses = []
 
@@ -119,8 +165,8 @@ def run(args):
         for _ in range(min(3, args.warmup)):
             one()
         ms_e = maxr(timed(one, args.steps))
-        e2e = {"value": round(B * world * args.steps / (ms_e / 1e3), 2), "unit": "images/s",
-               "h2d_bytes_per_step": int(hx[0].numel() * 4 + hy[0].numel() * 8), "d2h_bytes_per_step": 4,
+        e2e = {"value": round(B * world * args.steps / (ms_e / 1e3), 2), "unit": unit,
+               "h2d_bytes_per_step": int(hx[0].numel() * hx[0].element_size() + hy[0].numel() * 8), "d2h_bytes_per_step": 4,
                "ms_per_step": round(ms_e / args.steps, 4)}
     clocks = None
     if sampler is not None:
@@ -129,12 +175,12 @@ def run(args):
     if rank == 0:
         value = B * world * args.steps / (ms / 1e3)
         print(json.dumps({
-            "metric": "images/sec (ResNet-50 synthetic ImageNet training, DeAR tensor fusion)", "value": round(value, 2),
-            "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": metric, "value": round(value, 2),
+            "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "fp32 (TF32 convolutions, torch defaults)", "data": "synthetic", "impl": "reference",
-            "config": {"model": args.model, "global_batch": B * world, "batch_per_gpu": B, "image": size,
-                       "parallelism": "dp%d" % world, "optimizer": "SGD lr=0.01*size",
+            "config": {"model": args.model, "global_batch": B * world, "batch_per_gpu": B, ("seq_len" if is_bert else "image"): size,
+                       "parallelism": "dp%d" % world, "optimizer": "SGD",
                        "path": "baseline/_ref/dear/dopt_rsag.py over NCCL (comm_core stand-in: torch.distributed)",
                        "l2": "no explicit flush: working set far larger than L2"},
             "e2e": e2e, "gpu_launches": 0, "clocks": clocks}), flush=True)

@@ -2,12 +2,14 @@
 """Headline benchmark: ResNet-50, batch 64 per GPU, synthetic ImageNet, DeAR with tensor fusion.
 
     python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, 1 rank/GPU)
-    python bench.py --impl reference ...                     (the reference's own code path, NCCL)
+    python bench.py --impl reference ...                     (the reference's own code path over NCCL)
+    python bench.py --model bert --dtype bf16 ...            (BERT-large pre-training, samples/s)
 
 Metric and config follow BASELINE.json ("ResNet-50 images/sec ... bs=64/GPU synthetic ImageNet
-DeAR-TF") and the reference driver dear/imagenet_benchmark.py (SGD lr=0.01*size, synthetic
-224x224x3 batch, cross-entropy).  Timing: W untimed warm-up steps, then exactly K steps between
-CUDA events, bracketed by barrier + synchronize, max over ranks.  Prints ONE JSON line on rank 0.
+DeAR-TF", "BERT-large pretraining bf16 DeAR-TF") and the reference drivers
+dear/imagenet_benchmark.py / dear/bert_benchmark.py (SGD, synthetic batch, cross-entropy).
+Timing: W untimed warm-up steps, then exactly K steps between CUDA events, bracketed by
+barrier + synchronize, max over ranks.  Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
@@ -22,6 +24,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 BASELINE_PUBLISHED = None   # the reference publishes no throughput number
+BERT_MODELS = ("bert", "bert_large", "bert_base")
 
 
 def parse_args(argv=None):
@@ -31,14 +34,23 @@ def parse_args(argv=None):
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", choices=["dear", "reference"], default="dear")
     ap.add_argument("--model", default="resnet50")
-    ap.add_argument("--batch-size", type=int, default=64)
-    ap.add_argument("--dtype", choices=["fp32", "bf16", "amp"], default=os.environ.get("DEAR_BENCH_DTYPE", "fp32"))
+    ap.add_argument("--batch-size", type=int, default=None, help="per GPU (default: 64 images / 32 sentences)")
+    ap.add_argument("--sentence-len", type=int, default=64)
+    ap.add_argument("--dtype", choices=["fp32", "bf16", "amp"], default=os.environ.get("DEAR_BENCH_DTYPE"))
     ap.add_argument("--channels-last", type=int, default=int(os.environ.get("DEAR_BENCH_CL", "1")))
     ap.add_argument("--graph", type=int, default=int(os.environ.get("DEAR_BENCH_GRAPH", "0")))
     ap.add_argument("--threshold", type=float, default=25.0)
+    ap.add_argument("--momentum", type=float, default=0.0)
     ap.add_argument("--backend", default=None)
     ap.add_argument("--no-e2e", action="store_true")
-    return ap.parse_args(argv)
+    args = ap.parse_args(argv)
+    is_bert = args.model in BERT_MODELS
+    if args.batch_size is None:
+        args.batch_size = 32 if is_bert else 64
+    if args.dtype is None:
+        # BERT-large is specified in bf16 (BASELINE.json); ResNet-50 runs at the reference's precision
+        args.dtype = "bf16" if is_bert else "fp32"
+    return args
 
 
 def _free_port():
@@ -64,13 +76,72 @@ def main(argv=None):
     return run_dear(args)
 
 
+class Workload:
+    """Model + synthetic data of one benchmark task."""
+
+    def __init__(self, args, device, rank):
+        import torch
+        import torch.nn.functional as F
+        from dear_pytorch_b200.models.registry import create, input_size
+        self.args = args
+        self.is_bert = args.model in BERT_MODELS
+        cuda = device.type == "cuda"
+        B = args.batch_size
+        if self.is_bert:
+            from dear_pytorch_b200.models import bert as bm
+            model = create(args.model).to(device)
+            if args.dtype == "bf16":
+                model = model.to(torch.bfloat16)
+            crit = bm.BertPretrainingCriterion(model.vocab_size)
+            self.loss_fn = lambda out, tgt: crit(out[0], out[1], tgt[0], tgt[1])
+            self.unit, self.metric = "samples/s", "samples/sec (BERT-%s pre-training, seq %d, DeAR tensor fusion)" % (
+                "base" if args.model == "bert_base" else "large", args.sentence_len)
+
+            def host_batch(seed):
+                ids, mask, types, nsp, mlm = bm.synthetic_batch(B, args.sentence_len, model.vocab_size, "cpu", seed)
+                ts = (ids, types, mask, mlm, nsp)
+                return tuple(t.pin_memory() if cuda else t for t in ts)
+            self.host_batches = [host_batch(100 * rank + i) for i in range(4)]
+            self.to_step_args = lambda b: (b[0], b[1], b[2], (b[3], b[4]))
+            self.image = None
+        else:
+            model = create(args.model).to(device)
+            if args.channels_last:
+                model = model.to(memory_format=torch.channels_last)
+            if args.dtype == "bf16":
+                # bf16 parameters / activations / gradients, fp32 BatchNorm; fp32 master weights and
+                # momentum live (sharded) inside the optimizer
+                model = model.to(torch.bfloat16)
+                for m in model.modules():
+                    if isinstance(m, torch.nn.modules.batchnorm._BatchNorm):
+                        m.float()
+            self.loss_fn = lambda out, y: F.cross_entropy(out.float() if out.dtype != torch.float32 else out, y)
+            self.unit = "images/s"
+            self.metric = "images/sec (ResNet-50 synthetic ImageNet training, DeAR tensor fusion)" \
+                if args.model == "resnet50" else "images/sec (%s synthetic training, DeAR tensor fusion)" % args.model
+            size = input_size(args.model)
+            self.image = size
+            xdt = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+            g = torch.Generator().manual_seed(1000 + rank)
+
+            def host_batch():
+                x = torch.randn(B, 3, size, size, generator=g).to(xdt)
+                if args.channels_last:
+                    x = x.contiguous(memory_format=torch.channels_last)
+                y = torch.randint(0, 1000, (B,), generator=g)
+                return (x.pin_memory(), y.pin_memory()) if cuda else (x, y)
+            self.host_batches = [host_batch() for _ in range(4)]
+            self.to_step_args = lambda b: b
+        model.train()
+        self.model = model
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.host_batches[0])
+
+
 def run_dear(args):
     import torch
-    import torch.nn.functional as F
     import dear_pytorch_b200 as dear
-    from dear_pytorch_b200.models.registry import create, input_size
     from dear_pytorch_b200.utils.clocks import ClockSampler
-    from dear_pytorch_b200.utils.data import PinnedPrefetcher, SyntheticImages
+    from dear_pytorch_b200.utils.data import PinnedPrefetcher
     from dear_pytorch_b200.utils.train import TrainStep
 
     dear.init(backend=args.backend)
@@ -80,51 +151,35 @@ def run_dear(args):
     torch.backends.cudnn.benchmark = True
     torch.manual_seed(1234)
 
-    model = create(args.model).to(device)
-    if args.channels_last:
-        model = model.to(memory_format=torch.channels_last)
-    pdtype = torch.float32
-    if args.dtype == "bf16":
-        # bf16 parameters/activations/gradients, fp32 BatchNorm, fp32 master weights + momentum
-        # (sharded) inside the optimizer
-        model = model.to(torch.bfloat16)
-        for m in model.modules():
-            if isinstance(m, torch.nn.modules.batchnorm._BatchNorm):
-                m.float()
-        pdtype = torch.bfloat16
-    model.train()
-    base = torch.optim.SGD(model.parameters(), lr=0.01 * world, momentum=0.0)
-    opt = dear.DistributedOptimizer(base, model, threshold=args.threshold, verbose=(rank == 0 and bool(os.environ.get("DEAR_VERBOSE"))))
+    wl = Workload(args, device, rank)
+    model = wl.model
+    lr = (2e-5 if wl.is_bert else 0.01 * world)          # dear/bert_benchmark.py:122, dear/imagenet_benchmark.py:94
+    base = torch.optim.SGD(model.parameters(), lr=lr, momentum=args.momentum)
+    opt = dear.DistributedOptimizer(base, model, threshold=args.threshold,
+                                    verbose=(rank == 0 and bool(os.environ.get("DEAR_VERBOSE"))))
     dear.broadcast_parameters(model.state_dict(), 0)
-
-    size = input_size(args.model)
-    B = args.batch_size
-    autocast = args.dtype == "amp"
-
-    def loss_fn(out, y):
-        return F.cross_entropy(out.float() if out.dtype != torch.float32 else out, y)
-
-    step = TrainStep(model, opt, loss_fn, autocast_dtype=torch.bfloat16 if autocast else None,
+    step = TrainStep(model, opt, wl.loss_fn, autocast_dtype=torch.bfloat16 if args.dtype == "amp" else None,
                      use_graph=bool(args.graph) and cuda)
+    B = args.batch_size
 
     # ---- device-resident synthetic batch (the reference's protocol) -------------------------
-    x = torch.randn(B, 3, size, size, device=device).to(pdtype if args.dtype == "bf16" else torch.float32)
-    if args.channels_last:
-        x = x.contiguous(memory_format=torch.channels_last)
-    y = torch.randint(0, 1000, (B,), device=device)
+    dev_batch = wl.to_step_args(tuple(t.to(device) for t in wl.host_batches[0]))
 
     def sync():
         if cuda:
             torch.cuda.synchronize(device)
 
     for _ in range(args.warmup):
-        step(x, y)
+        step(*dev_batch)
     opt.engine.synchronize(host=True)
     comm = dear.communicator()
 
+    def n_launches():
+        return comm.launches() if comm is not None else opt.engine.backend.launches()
+
     def timed(run_one, n):
         dear.barrier(); sync()
-        l0 = comm.launches() if comm is not None else opt.engine.backend.launches()
+        l0 = n_launches()
         if cuda:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -139,28 +194,32 @@ def run_dear(args):
         else:
             ms = (time.perf_counter() - t0) * 1e3
         dear.barrier()
-        l1 = comm.launches() if comm is not None else opt.engine.backend.launches()
-        return ms, l1 - l0
+        return ms, n_launches() - l0
 
     sampler = ClockSampler(device.index if cuda else 0).start() if (cuda and rank == 0) else None
     wall0 = time.time()
-    ms, launches = timed(lambda: step(x, y), args.steps)
+    ms, launches = timed(lambda: step(*dev_batch), args.steps)
     wall1 = time.time()
+    if args.graph and cuda:
+        # a replayed CUDA graph launches the same kernels without going through the host counters
+        launches = 2 * len(opt.engine.plan.buckets) * args.steps
 
     # ---- end to end: pinned host batches -> H2D every step, loss -> host every step ----------
     e2e = None
     if not args.no_e2e:
-        host = SyntheticImages(B, size, channels_last=bool(args.channels_last),
-                               dtype=pdtype if args.dtype == "bf16" else torch.float32, seed=rank)
-        feed = PinnedPrefetcher(host, device)
-        loss_host = torch.zeros(args.steps + args.warmup, dtype=torch.float32)
+        def endless():
+            i = 0
+            while True:
+                yield wl.host_batches[i % len(wl.host_batches)]
+                i += 1
+        feed = PinnedPrefetcher(endless(), device)
+        loss_host = torch.zeros(args.steps + args.warmup + 4, dtype=torch.float32)
         if cuda:
             loss_host = loss_host.pin_memory()
         k = [0]
 
         def one():
-            xb, yb = next(feed)
-            loss = step(xb, yb)
+            loss = step(*wl.to_step_args(next(feed)))
             loss_host[k[0]].copy_(loss.detach().float(), non_blocking=True)   # D2H every step
             k[0] += 1
         for _ in range(min(3, args.warmup)):
@@ -169,32 +228,33 @@ def run_dear(args):
         sync()
         assert torch.isfinite(loss_host[:k[0]]).all(), "non-finite loss in the end-to-end run"
         ms_e2e = _max_over_ranks(ms_e2e, world)
-        e2e = {"value": round(B * world * args.steps / (ms_e2e / 1e3), 2), "unit": "images/s",
-               "h2d_bytes_per_step": int(host.bytes_per_batch), "d2h_bytes_per_step": 4,
+        e2e = {"value": round(B * world * args.steps / (ms_e2e / 1e3), 2), "unit": wl.unit,
+               "h2d_bytes_per_step": int(wl.h2d_bytes), "d2h_bytes_per_step": 4,
                "ms_per_step": round(ms_e2e / args.steps, 4)}
-    clocks = sampler.stop() if sampler is not None else None
+    clocks = None
     if sampler is not None:
+        sampler.stop()
         clocks = sampler.summary(wall0, wall1)
 
     ms = _max_over_ranks(ms, world)
     value = B * world * args.steps / (ms / 1e3)
     if rank == 0:
         n_params = sum(p.numel() for p in model.parameters())
+        cfg = {"model": args.model, "global_batch": B * world, "batch_per_gpu": B, "parallelism": "dp%d" % world,
+               "optimizer": "SGD lr=%g" % lr, "threshold_mb": args.threshold, "buckets": len(opt.engine.plan.buckets),
+               "params": n_params, "backend": dear.backend(), "cuda_graph": bool(args.graph),
+               "l2": "no explicit flush: each step streams activations+weights far larger than the 126 MB L2"}
+        if wl.is_bert:
+            cfg["seq_len"] = args.sentence_len
+        else:
+            cfg.update(image=wl.image, channels_last=bool(args.channels_last))
         out = {
-            "metric": "images/sec (ResNet-50 synthetic ImageNet training, DeAR tensor fusion)" if args.model == "resnet50"
-                      else "images/sec (%s synthetic training, DeAR)" % args.model,
-            "value": round(value, 2), "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak",
+            "metric": wl.metric, "value": round(value, 2), "unit": wl.unit, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None if BASELINE_PUBLISHED is None else round(value / BASELINE_PUBLISHED, 4),
             "dtype": {"fp32": "fp32 (TF32 convolutions, torch defaults, as the reference)", "bf16": "bf16",
                       "amp": "bf16 autocast"}[args.dtype],
-            "data": "synthetic", "impl": "dear",
-            "config": {"model": args.model, "global_batch": B * world, "batch_per_gpu": B, "image": size,
-                       "parallelism": "dp%d" % world, "optimizer": "SGD lr=0.01*size", "threshold_mb": args.threshold,
-                       "buckets": len(opt.engine.plan.buckets), "params": n_params, "backend": dear.backend(),
-                       "channels_last": bool(args.channels_last), "cuda_graph": bool(args.graph),
-                       "l2": "no explicit flush: each step streams activations+weights far larger than the 126 MB L2"},
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "data": "synthetic", "impl": "dear", "config": cfg, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(out), flush=True)
     opt.engine.close()
