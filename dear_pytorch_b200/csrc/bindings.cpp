@@ -22,6 +22,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.attr("SEG_ZERO_FILL") = static_cast<int>(SEG_ZERO_FILL);
   m.def("cuda_usable", &cuda_runtime_usable);
   m.def("status_word", [] { return static_cast<int64_t>(*status_word_host()); });
+  m.def("_set_status_word", [](int64_t v) { *status_word_host() = static_cast<uint32_t>(v); },
+        "fault injection for tests: pretend a kernel flagged a spin-wait timeout");
 
   py::class_<CommOptions>(m, "CommOptions")
       .def(py::init<>())

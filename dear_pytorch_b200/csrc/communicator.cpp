@@ -142,10 +142,11 @@ void Communicator::check_status() {
     __atomic_store_n(st, 0u, __ATOMIC_RELEASE);
     static const char* names[] = {"ok", "reduce-scatter: peers never packed", "reduce-scatter: peers never released the bucket",
                                   "all-gather: peers never arrived", "all-gather: peers never pushed", "general collective"};
-    std::ostringstream oss;
-    oss << "dear: rank " << rank_ << ": cross-GPU wait timed out (" << (v < 6 ? names[v] : "?") << ", code " << v
-        << "); a peer is missing, crashed, or issued collectives in a different order";
-    throw std::runtime_error(oss.str());
+    std::string msg = "dear: rank " + std::to_string(rank_) + ": cross-GPU wait timed out (";
+    msg += (v < 6 ? names[v] : "unknown");
+    msg += ", code " + std::to_string(v) +
+           "); a peer is missing, crashed, or issued collectives in a different order";
+    throw std::runtime_error(msg);
   }
 }
 
@@ -370,7 +371,7 @@ BucketSet::BucketSet(std::shared_ptr<Communicator> comm, std::vector<int64_t> pa
   const int world = comm_->size();
   const size_t es = dtype_size(dtype);
   DEAR_CHECK(static_cast<int>(padded_numels.size()) * kChannelsPerBucket + kGeneralChannels <= kNumChannels,
-             "too many buckets (" << padded_numels.size() << ")");
+             "too many buckets (" << static_cast<long long>(padded_numels.size()) << ")");
   size_t off = 0;
   for (int64_t n : padded_numels) {
     DEAR_CHECK(n > 0 && n % world == 0, "bucket size must be a positive multiple of the world size");

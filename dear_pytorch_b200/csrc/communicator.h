@@ -34,8 +34,8 @@ struct CommOptions {
   int nstreams = 1;
   double spin_timeout_s = 20.0;          // in-kernel bounded spin
   double rendezvous_timeout_s = 120.0;
-  int rs_grid = 48;
-  int ag_grid = 48;
+  int rs_grid = 96;
+  int ag_grid = 96;
   int gen_grid = 8;
 };
 

@@ -132,8 +132,8 @@ def init(backend: Optional[str] = None, device: Optional[torch.device] = None, *
         o.multicast = bool(multicast) and prov == "vmm"
         o.spin_timeout_s = float(os.environ.get("DEAR_SPIN_TIMEOUT_S", "20"))
         o.rendezvous_timeout_s = float(timeout_s)
-        o.rs_grid = _env_int("DEAR_RS_GRID", 48)
-        o.ag_grid = _env_int("DEAR_AG_GRID", 48)
+        o.rs_grid = _env_int("DEAR_RS_GRID", 96)
+        o.ag_grid = _env_int("DEAR_AG_GRID", 96)
         o.gen_grid = _env_int("DEAR_GEN_GRID", 8)
         comm = C.Communicator(rank, world, store, "dear%d" % _env_int("DEAR_JOB_SEQ", 0), o)
         opts = dict(provider=prov, multicast=o.multicast, rs_grid=o.rs_grid, ag_grid=o.ag_grid)

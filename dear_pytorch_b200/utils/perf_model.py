@@ -89,7 +89,10 @@ def rs_roofline_us(bucket_bytes: int, world: int, elem_bytes: int = 4, peaks: di
     """
     pk = peaks or measured_peaks()
     shard = bucket_bytes / world
-    hbm = 2 * bucket_bytes + shard + (shard / elem_bytes) * 4
+    if world == 1 and elem_bytes == 4:
+        hbm = 2 * bucket_bytes          # single GPU: the pack writes the fp32 shard directly
+    else:
+        hbm = 2 * bucket_bytes + shard + (shard / elem_bytes) * 4
     link = bucket_bytes * (world - 1) / world
     t_hbm = hbm / (pk["hbm_gbs"] * 1e3)
     t_link = link / (pk["nvlink_gbs_per_dir"] * 1e3)

@@ -119,3 +119,52 @@ def fusion_worker(rank, world):
 @pytest.mark.parametrize("backend", ["emu", "gloo"])
 def test_tensorfusion_helpers(backend):
     assert all(run_ranks(fusion_worker, world=2, backend=backend))
+
+
+def gtopk_worker(rank, world):
+    from dear_pytorch_b200.parallel.baselines.gtopk import gtopk_sparse_recursive_allreduce
+    from dear_pytorch_b200.parallel.comm import Comm
+    torch.manual_seed(rank)
+    n, k = 64, 6
+    dense = torch.randn(n)
+    idx = torch.topk(dense.abs(), k)[1]
+    vals, gidx = gtopk_sparse_recursive_allreduce(Comm(), dense[idx], idx, n, k)
+    return dense, idx, vals, gidx
+
+
+def test_gtopk_sparse_allreduce_is_rank_consistent():
+    outs = run_ranks(gtopk_worker, world=2, backend="emu")
+    assert torch.equal(outs[0][2], outs[1][2]) and torch.equal(outs[0][3], outs[1][3])
+    # oracle: sum of the two sparsified vectors, then top-k by magnitude
+    full = torch.zeros(64)
+    for dense, idx, _, _ in outs:
+        full[idx] += dense[idx]
+    k = 6
+    top = torch.topk(full.abs(), k)[1]
+    got = torch.zeros(64)
+    got[outs[0][3]] = outs[0][2]
+    want = torch.zeros(64)
+    want[top] = full[top]
+    torch.testing.assert_close(got, want)
+
+
+def timeout_worker(rank, world):
+    """Failure detection: a peer that never joins a collective is reported, not waited for forever."""
+    import dear_pytorch_b200 as dear
+    comm = dear.communicator()
+    if rank == 0:
+        t = torch.ones(4)
+        comm.allReduce(t, 1.0)           # rank 1 never calls it: bounded spin, then the status word is set
+        try:
+            comm.check_status()
+        except RuntimeError as e:
+            return "timeout" if "timed out" in str(e) else str(e)
+        return "no error"
+    import time
+    time.sleep(3.0)
+    return "skipped"
+
+
+def test_missing_peer_is_detected_not_hung():
+    outs = run_ranks(timeout_worker, world=2, backend="emu", extra_env={"DEAR_SPIN_TIMEOUT_S": "1"}, timeout=60)
+    assert outs[0] == "timeout" and outs[1] == "skipped"

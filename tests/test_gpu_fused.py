@@ -56,11 +56,11 @@ def test_single_gpu_fused_sgd_matches_torch(case):
         torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-5)
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_multi_rank_fused_matches_torch(world):
     ngpu = torch.cuda.device_count()
-    if ngpu > 1 and ngpu < world:
-        pytest.skip("needs %d GPUs (or exactly one shared GPU)" % world)
+    if (ngpu > 1 and ngpu < world) or (world == 8 and ngpu < 8):
+        pytest.skip("needs %d GPUs (2 and 4 ranks may also share exactly one GPU)" % world)
     case = CASES[2]
     ref = reference_run(case, 3, world, 2)
     outs = run_ranks(gpu_worker, world=world, backend="b200", args=(case, 3, 2, 0.001, "fp32"), extra_env=_env(),
