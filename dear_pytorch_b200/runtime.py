@@ -130,10 +130,14 @@ def init(backend: Optional[str] = None, device: Optional[torch.device] = None, *
         if multicast is None:
             multicast = os.environ.get("DEAR_MULTICAST", "0") not in ("0", "", "false", "False")
         o.multicast = bool(multicast) and prov == "vmm"
-        o.spin_timeout_s = float(os.environ.get("DEAR_SPIN_TIMEOUT_S", "20"))
+        o.spin_timeout_s = float(os.environ.get("DEAR_SPIN_TIMEOUT_S", "60"))
         o.rendezvous_timeout_s = float(timeout_s)
-        o.rs_grid = _env_int("DEAR_RS_GRID", 96)
-        o.ag_grid = _env_int("DEAR_AG_GRID", 96)
+        # CTAs of the fused kernels.  On one GPU nothing ever spins, so the kernels may take most of the
+        # chip for a few microseconds (HBM-bound).  With peers, CTAs spin on cross-GPU flags while they
+        # wait for the slowest rank: keep the footprint small (32 CTAs saturate NVLink: 770 GB/s x ~2 us
+        # latency = 1.5 MB in flight, each CTA keeps >= 64 KB in flight).
+        o.rs_grid = _env_int("DEAR_RS_GRID", 128 if world == 1 else 32)
+        o.ag_grid = _env_int("DEAR_AG_GRID", 128 if world == 1 else 32)
         o.gen_grid = _env_int("DEAR_GEN_GRID", 8)
         comm = C.Communicator(rank, world, store, "dear%d" % _env_int("DEAR_JOB_SEQ", 0), o)
         opts = dict(provider=prov, multicast=o.multicast, rs_grid=o.rs_grid, ag_grid=o.ag_grid)
