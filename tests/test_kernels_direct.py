@@ -1,0 +1,115 @@
+"""Kernel-level numerics: BucketSet.reduce_scatter / allgather_update against a plain PyTorch fp32
+reference of the same op — odd segment sizes (vector tails), absent gradients (zero fill), in-place
+segments, several hyper-parameter segments, momentum / nesterov / weight decay, fp32 and bf16.
+
+The same test body runs on the host emulation (CPU, always) and on the CUDA kernels (gpu marker)."""
+import pytest
+import torch
+
+from _mp import run_ranks
+
+
+def reference_update(p, g, buf, first, lr, wd, mom, damp, nest):
+    g = g + wd * p if wd else g.clone()
+    if mom > 0:
+        buf = g.clone() if first else mom * buf + (1 - damp) * g
+        g = g + mom * buf if nest else buf
+    return p - lr * g, buf
+
+
+def kernel_worker(rank, world, use_cuda, dtype_name, seed):
+    import dear_pytorch_b200 as dear
+    from dear_pytorch_b200 import ops
+    C = ops.require_native()
+    comm = dear.communicator()
+    dev = dear.device()
+    tdt = torch.float32 if dtype_name == "fp32" else torch.bfloat16
+    es = 4 if dtype_name == "fp32" else 2
+    g = torch.Generator().manual_seed(seed)
+    # parameters of odd sizes; every start is 256-byte aligned like the planner does
+    numels = [37, 1000, 4099, 3, 70001]
+    align = 256 // es
+    starts, off = [], 0
+    for n in numels:
+        off = (off + align - 1) // align * align
+        starts.append(off)
+        off += n
+    quantum = world * (128 // es)
+    padded = (off + quantum - 1) // quantum * quantum
+    shard = padded // world
+    bs = C.BucketSet(comm, [padded], C.DT_F32 if dtype_name == "fp32" else C.DT_BF16, True)
+    pbuf, gbuf = bs.param_buffer(0), bs.grad_buffer(0)
+    full_p = torch.zeros(padded)
+    for s, n in zip(starts, numels):
+        full_p[s:s + n] = torch.randn(n, generator=g)
+    pbuf.copy_(full_p.to(tdt))
+    full_p = pbuf.float().cpu().clone()                          # what the kernel sees after rounding
+    gs = torch.zeros(shard, device=dev)
+    mom = torch.zeros(shard, device=dev)
+    master = pbuf[rank * shard:(rank + 1) * shard].float().clone() if dtype_name != "fp32" else None
+    bs.set_shards(0, gs, mom, master)
+    # hyper segments: params 0-1 group A, 2-3 group B (nesterov), 4 group C (no momentum)
+    hyp = [(starts[2], 0.1, 0.01, 0.9, 0.0, 0), (starts[4], 0.05, 0.0, 0.8, 0.0, 1), (padded, 0.2, 0.001, 0.0, 0.0, 0)]
+    bs.set_hyper(0, [h[0] for h in hyp], [h[1] for h in hyp], [h[2] for h in hyp], [h[3] for h in hyp],
+                 [h[4] for h in hyp], [h[5] for h in hyp])
+    ref_p = full_p.clone()
+    ref_buf = torch.zeros(padded)
+    results = []
+    for step in range(3):
+        # this rank's gradients: param 3 is absent on step 1 (zero fill), param 1 is "in place" on step 2
+        gen = torch.Generator().manual_seed(1000 * step + 7)
+        all_rank_grads = [[torch.randn(n, generator=gen).to(tdt) for n in numels] for _ in range(world)]
+        mine = [t.to(dev) for t in all_rank_grads[rank]]
+        src, flags = [], []
+        for i, t in enumerate(mine):
+            if step == 1 and i == 3:
+                src.append(0); flags.append(C.SEG_ZERO_FILL)
+            elif step == 2 and i == 1:
+                gbuf[starts[i]:starts[i] + numels[i]].copy_(t)
+                src.append(0); flags.append(0)
+            else:
+                src.append(t.data_ptr()); flags.append(0)
+        bs.set_pack(0, src, [s * es for s in starts], [n * es for n in numels], flags)
+        bs.reduce_scatter(0, True)
+        bs.allgather_update(0, True, step == 0, True, False)
+        bs.synchronize()
+        comm.check_status()
+        # reference
+        summed = torch.zeros(padded)
+        for r in range(world):
+            for i, (s, n) in enumerate(zip(starts, numels)):
+                if step == 1 and i == 3:
+                    continue
+                summed[s:s + n] += all_rank_grads[r][i].float()
+        avg = summed / world
+        start = 0
+        for end, lr, wd, m, damp, nest in hyp:
+            sl = slice(start, end)
+            ref_p[sl], ref_buf[sl] = reference_update(ref_p[sl], avg[sl], ref_buf[sl], step == 0, lr, wd, m, damp, bool(nest))
+            start = end
+        got_shard_grad = gs.cpu()
+        torch.testing.assert_close(got_shard_grad, avg[rank * shard:(rank + 1) * shard], rtol=1e-5, atol=1e-6)
+        got = pbuf.float().cpu()
+        if dtype_name == "fp32":
+            torch.testing.assert_close(got, ref_p, rtol=1e-5, atol=1e-6)
+        else:
+            torch.testing.assert_close(master.cpu(), ref_p[rank * shard:(rank + 1) * shard], rtol=1e-5, atol=1e-6)
+            torch.testing.assert_close(got, ref_p.to(torch.bfloat16).float(), rtol=8e-3, atol=1e-6)   # <= 1 bf16 ulp
+        results.append(float(got.abs().sum()))
+    return results
+
+
+@pytest.mark.parametrize("dtype_name", ["fp32", "bf16"])
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_emulated_kernels_match_reference(world, dtype_name):
+    outs = run_ranks(kernel_worker, world=world, backend="emu", args=(False, dtype_name, 5))
+    assert all(o == outs[0] for o in outs)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype_name", ["fp32", "bf16"])
+@pytest.mark.parametrize("world", [1, 2])
+def test_cuda_kernels_match_reference(world, dtype_name):
+    outs = run_ranks(kernel_worker, world=world, backend="b200", args=(True, dtype_name, 5),
+                     extra_env={"DEAR_SPIN_TIMEOUT_S": "15"}, timeout=300)
+    assert all(o == outs[0] for o in outs)
