@@ -15,6 +15,33 @@ from typing import Callable, Optional
 import torch
 
 
+def _tree_map(fn, obj):
+    if torch.is_tensor(obj):
+        return fn(obj)
+    if isinstance(obj, (tuple, list)):
+        return type(obj)(_tree_map(fn, o) for o in obj)
+    return obj
+
+
+def _tree_zip_apply(fn, a, b):
+    if torch.is_tensor(a):
+        fn(a, b)
+    elif isinstance(a, (tuple, list)):
+        for x, y in zip(a, b):
+            _tree_zip_apply(fn, x, y)
+
+
+def _first_tensor(obj):
+    if torch.is_tensor(obj):
+        return obj
+    if isinstance(obj, (tuple, list)):
+        for o in obj:
+            t = _first_tensor(o)
+            if t is not None:
+                return t
+    return None
+
+
 class TrainStep:
     def __init__(self, model: torch.nn.Module, optimizer, loss_fn: Callable, autocast_dtype: Optional[torch.dtype] = None,
                  use_graph: bool = False, graph_warmup: int = 3):
@@ -30,6 +57,7 @@ class TrainStep:
         self._static_loss = None
         self._engine = getattr(optimizer, "_dear", None)
         self._debug = bool(os.environ.get("DEAR_GRAPH_DEBUG"))
+        self._side = None
 
     def _eager(self, *batch):
         *inputs, target = batch
@@ -48,24 +76,31 @@ class TrainStep:
         if self._debug:
             print("[TrainStep] " + msg, flush=True)
 
+    def _eager_on_side_stream(self, batch):
+        """Warm-up iterations of the graph mode run on a side stream (the PyTorch whole-network
+        capture recipe): allocator pools, cuDNN autotuning and autograd streams settle on the stream
+        family the capture will use.  They are ordinary training steps on the caller's batches."""
+        dev = _first_tensor(batch).device
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=dev)
+        cur = torch.cuda.current_stream(dev)
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            loss = self._eager(*batch)
+            if self._engine is not None:
+                self._engine.synchronize(host=False)
+        cur.wait_stream(self._side)
+        _tree_map(lambda t: t.record_stream(self._side), batch)
+        return loss
+
     def _capture(self, batch):
         eng = self._engine
-        dev = batch[0].device
-        self._static_in = tuple(torch.empty_like(t).copy_(t) for t in batch)
-        # warm up on a side stream (the PyTorch whole-network capture recipe): allocator pools,
-        # cuDNN autotuning and autograd streams all settle before the capture
-        side = torch.cuda.Stream(device=dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
-            for _ in range(2):
-                self._eager(*self._static_in)
-            if eng is not None:
-                eng.synchronize(host=False)
-        torch.cuda.current_stream(dev).wait_stream(side)
+        dev = _first_tensor(batch).device
+        self._static_in = _tree_map(lambda t: torch.empty_like(t).copy_(t), batch)
         if eng is not None:
             eng.synchronize(host=True)
         torch.cuda.synchronize(dev)
-        self._log("warm-up on side stream done; capturing")
+        self._log("capturing")
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph, capture_error_mode="thread_local"):
             loss = self._eager(*self._static_in)
@@ -73,7 +108,7 @@ class TrainStep:
                 eng.synchronize(host=False)     # join the communication stream back into the capture
             self._static_loss = loss
         self._log("capture done; first replay")
-        # the capture only records; run the iteration for real
+        # the capture only records: replaying it IS this call's training step
         self._graph.replay()
         return self._static_loss
 
@@ -83,13 +118,14 @@ class TrainStep:
             return self._eager(*batch)
         if self._graph is None:
             if self._calls <= self.graph_warmup:
-                return self._eager(*batch)
+                return self._eager_on_side_stream(batch)
             return self._capture(batch)
         eng = self._engine
         if eng is not None and eng.hyper_changed():
             eng.refresh_hyper_outside_graph()
-        for s, t in zip(self._static_in, batch):
-            if s.data_ptr() != t.data_ptr():
-                s.copy_(t, non_blocking=True)
+        _tree_zip_apply(lambda s, t: s.copy_(t, non_blocking=True) if s.data_ptr() != t.data_ptr() else None,
+                        self._static_in, batch)
         self._graph.replay()
+        if eng is not None:
+            eng.num_steps += 1          # the replay ran the step; Python-side callbacks (tuner) do not run
         return self._static_loss

@@ -125,3 +125,35 @@ def test_general_collectives():
         torch.testing.assert_close(res["allgather"], torch.arange(world).repeat_interleave(5).float())
         torch.testing.assert_close(res["rb"], (torch.arange(1000.) * s / world)[:3] * world)
         torch.testing.assert_close(res["sendrecv"], torch.full((9,), float((r + 1) % world)))
+
+
+def graph_worker(rank, world, use_graph):
+    import dear_pytorch_b200 as dear
+    from dear_pytorch_b200.utils.train import TrainStep
+    dev = dear.device()
+    torch.manual_seed(0)
+    model = nn.Sequential(nn.Linear(64, 256), nn.ReLU(), nn.Linear(256, 256), nn.ReLU(), nn.Linear(256, 10)).to(dev)
+    opt = torch.optim.SGD(model.parameters(), lr=0.05, momentum=0.9, weight_decay=1e-4)
+    opt = dear.DistributedOptimizer(opt, model, threshold=0.05, verbose=False)
+    dear.broadcast_parameters(model.state_dict(), 0)
+    step = TrainStep(model, opt, nn.functional.cross_entropy, use_graph=use_graph, graph_warmup=2)
+    g = torch.Generator().manual_seed(100 + rank)
+    losses = []
+    for t in range(8):
+        x = torch.randn(32, 64, generator=g).to(dev)
+        y = torch.randint(0, 10, (32,), generator=g).to(dev)
+        losses.append(float(step(x, y)))
+    opt.synchronize()
+    dear.communicator().check_status()
+    return losses, [p.detach().float().cpu() for p in model.parameters()], step._graph is not None
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_cuda_graph_replay_matches_eager(world):
+    eager = run_ranks(graph_worker, world=world, backend="b200", args=(False,), extra_env=_env(), timeout=300)
+    graph = run_ranks(graph_worker, world=world, backend="b200", args=(True,), extra_env=_env(), timeout=300)
+    assert graph[0][2] and not eager[0][2]
+    for (le, pe, _), (lg, pg, _) in zip(eager, graph):
+        torch.testing.assert_close(torch.tensor(lg), torch.tensor(le), rtol=1e-4, atol=1e-5)
+        for a, b in zip(pg, pe):
+            torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-5)
