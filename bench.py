@@ -39,6 +39,8 @@ def parse_args(argv=None):
     ap.add_argument("--dtype", choices=["fp32", "bf16", "amp"], default=os.environ.get("DEAR_BENCH_DTYPE"))
     ap.add_argument("--channels-last", type=int, default=int(os.environ.get("DEAR_BENCH_CL", "1")))
     ap.add_argument("--graph", type=int, default=int(os.environ.get("DEAR_BENCH_GRAPH", "0")))
+    ap.add_argument("--fused-bn", type=int, default=int(os.environ.get("DEAR_BENCH_FUSED_BN", "1")),
+                    help="ResNets: fused channels-last BatchNorm(+add)+ReLU kernels (csrc/bn_act.cu)")
     ap.add_argument("--threshold", type=float, default=25.0)
     ap.add_argument("--momentum", type=float, default=0.0)
     ap.add_argument("--backend", default=None)
@@ -105,7 +107,9 @@ class Workload:
             self.to_step_args = lambda b: (b[0], b[1], b[2], (b[3], b[4]))
             self.image = None
         else:
-            model = create(args.model).to(device)
+            kw = {"fused_bn": True} if (args.fused_bn and args.channels_last and args.model.startswith("resnet")) else {}
+            model = create(args.model, **kw).to(device)
+            self.fused_bn = bool(kw)
             if args.channels_last:
                 model = model.to(memory_format=torch.channels_last)
             if args.dtype == "bf16":
@@ -247,7 +251,7 @@ def run_dear(args):
         if wl.is_bert:
             cfg["seq_len"] = args.sentence_len
         else:
-            cfg.update(image=wl.image, channels_last=bool(args.channels_last))
+            cfg.update(image=wl.image, channels_last=bool(args.channels_last), fused_bn_relu=getattr(wl, "fused_bn", False))
         out = {
             "metric": wl.metric, "value": round(value, 2), "unit": wl.unit, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak",

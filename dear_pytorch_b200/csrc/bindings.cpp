@@ -12,6 +12,17 @@
 namespace py = pybind11;
 using namespace dear;
 
+namespace dear { namespace bn {
+bool bn_act_supported(const torch::Tensor& x);
+std::vector<torch::Tensor> bn_act_forward(const torch::Tensor& x, const c10::optional<torch::Tensor>& z,
+                                          const c10::optional<torch::Tensor>& gamma, const c10::optional<torch::Tensor>& beta,
+                                          c10::optional<torch::Tensor> running_mean, c10::optional<torch::Tensor> running_var,
+                                          bool training, double momentum, double eps, bool relu);
+std::vector<torch::Tensor> bn_act_backward(const torch::Tensor& dy, const torch::Tensor& x, const c10::optional<torch::Tensor>& y,
+                                           const torch::Tensor& save_mean, const torch::Tensor& save_invstd,
+                                           const torch::Tensor& scale, const torch::Tensor& shift, bool relu, bool has_residual);
+} }
+
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "B200-native DeAR communication runtime (fused reduce-scatter / SGD+all-gather kernels)";
 
@@ -86,6 +97,13 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def("wait_all", &BucketSet::wait_all)
       .def("synchronize", &BucketSet::synchronize, py::call_guard<py::gil_scoped_release>())
       .def("comm_stream_handle", &BucketSet::comm_stream_handle);
+
+  // fused channels-last BatchNorm (+ residual) (+ ReLU)
+  m.def("bn_act_supported", &dear::bn::bn_act_supported);
+  m.def("bn_act_forward", &dear::bn::bn_act_forward, py::arg("x"), py::arg("residual"), py::arg("weight"), py::arg("bias"),
+        py::arg("running_mean"), py::arg("running_var"), py::arg("training"), py::arg("momentum"), py::arg("eps"),
+        py::arg("relu"));
+  m.def("bn_act_backward", &dear::bn::bn_act_backward);
 
   m.attr("DT_F32") = static_cast<int>(DT_F32);
   m.attr("DT_BF16") = static_cast<int>(DT_BF16);

@@ -9,6 +9,13 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
+from ..ops.fused_bn import FusedBatchNormAct2d
+
+
+def _bn(c, relu, fused):
+    """BatchNorm (+ReLU when ``relu``): the fused channels-last kernel or the stock modules."""
+    return FusedBatchNormAct2d(c, relu=relu) if fused else nn.BatchNorm2d(c)
+
 
 def _conv3x3(cin, cout, stride=1):
     return nn.Conv2d(cin, cout, 3, stride=stride, padding=1, bias=False)
@@ -21,17 +28,21 @@ def _conv1x1(cin, cout, stride=1):
 class BasicBlock(nn.Module):
     expansion = 1
 
-    def __init__(self, cin, width, stride=1, downsample=None):
+    def __init__(self, cin, width, stride=1, downsample=None, fused_bn=False):
         super().__init__()
+        self.fused = fused_bn
         self.conv1 = _conv3x3(cin, width, stride)
-        self.bn1 = nn.BatchNorm2d(width)
+        self.bn1 = _bn(width, True, fused_bn)
         self.conv2 = _conv3x3(width, width)
-        self.bn2 = nn.BatchNorm2d(width)
+        self.bn2 = _bn(width, True, fused_bn)
         self.relu = nn.ReLU(inplace=True)
         self.downsample = downsample
 
     def forward(self, x):
         idt = x if self.downsample is None else self.downsample(x)
+        if self.fused:
+            out = self.bn1(self.conv1(x))                       # BN + ReLU in one kernel
+            return self.bn2(self.conv2(out), residual=idt)      # BN + add + ReLU in one kernel
         out = self.relu(self.bn1(self.conv1(x)))
         out = self.bn2(self.conv2(out))
         return self.relu(out + idt)
@@ -40,19 +51,24 @@ class BasicBlock(nn.Module):
 class Bottleneck(nn.Module):
     expansion = 4
 
-    def __init__(self, cin, width, stride=1, downsample=None):
+    def __init__(self, cin, width, stride=1, downsample=None, fused_bn=False):
         super().__init__()
+        self.fused = fused_bn
         self.conv1 = _conv1x1(cin, width)
-        self.bn1 = nn.BatchNorm2d(width)
+        self.bn1 = _bn(width, True, fused_bn)
         self.conv2 = _conv3x3(width, width, stride)
-        self.bn2 = nn.BatchNorm2d(width)
+        self.bn2 = _bn(width, True, fused_bn)
         self.conv3 = _conv1x1(width, width * 4)
-        self.bn3 = nn.BatchNorm2d(width * 4)
+        self.bn3 = _bn(width * 4, True, fused_bn)
         self.relu = nn.ReLU(inplace=True)
         self.downsample = downsample
 
     def forward(self, x):
         idt = x if self.downsample is None else self.downsample(x)
+        if self.fused:
+            out = self.bn1(self.conv1(x))
+            out = self.bn2(self.conv2(out))
+            return self.bn3(self.conv3(out), residual=idt)
         out = self.relu(self.bn1(self.conv1(x)))
         out = self.relu(self.bn2(self.conv2(out)))
         out = self.bn3(self.conv3(out))
@@ -60,11 +76,12 @@ class Bottleneck(nn.Module):
 
 
 class ResNet(nn.Module):
-    def __init__(self, block, layers, num_classes=1000, zero_init_residual=False):
+    def __init__(self, block, layers, num_classes=1000, zero_init_residual=False, fused_bn=False):
         super().__init__()
         self.inplanes = 64
+        self.fused_bn = fused_bn
         self.conv1 = nn.Conv2d(3, 64, 7, stride=2, padding=3, bias=False)
-        self.bn1 = nn.BatchNorm2d(64)
+        self.bn1 = _bn(64, True, fused_bn)
         self.relu = nn.ReLU(inplace=True)
         self.maxpool = nn.MaxPool2d(3, stride=2, padding=1)
         self.layer1 = self._make_layer(block, 64, layers[0])
@@ -90,15 +107,16 @@ class ResNet(nn.Module):
         downsample = None
         if stride != 1 or self.inplanes != width * block.expansion:
             downsample = nn.Sequential(_conv1x1(self.inplanes, width * block.expansion, stride),
-                                       nn.BatchNorm2d(width * block.expansion))
-        layers = [block(self.inplanes, width, stride, downsample)]
+                                       _bn(width * block.expansion, False, self.fused_bn))
+        layers = [block(self.inplanes, width, stride, downsample, fused_bn=self.fused_bn)]
         self.inplanes = width * block.expansion
         for _ in range(1, blocks):
-            layers.append(block(self.inplanes, width))
+            layers.append(block(self.inplanes, width, fused_bn=self.fused_bn))
         return nn.Sequential(*layers)
 
     def forward(self, x):
-        x = self.maxpool(self.relu(self.bn1(self.conv1(x))))
+        x = self.bn1(self.conv1(x))
+        x = self.maxpool(x if self.fused_bn else self.relu(x))
         x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
         return self.fc(torch.flatten(self.avgpool(x), 1))
 
