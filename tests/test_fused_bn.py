@@ -58,6 +58,11 @@ def _run(dtype, relu, with_res, shape):
     if relu:
         yr = F.relu(yr)
     yr.backward(dy.float())
+    # ReLU is discontinuous: elements whose pre-activation is within rounding distance of zero may
+    # legitimately land on the other side in the fused arithmetic -> exclude them from the comparison
+    with torch.no_grad():
+        pre = F.batch_norm(x.float(), None, None, w, b, True, 0.0, 1e-5) + (z.float() if with_res else 0)
+        safe = (pre.abs() > (1e-4 if dtype == torch.float32 else 5e-2)) if relu else torch.ones_like(pre, dtype=torch.bool)
     # fused
     xf = x.clone().requires_grad_(True)
     zf = z.clone().requires_grad_(True) if with_res else None
@@ -67,15 +72,15 @@ def _run(dtype, relu, with_res, shape):
     assert yf.is_contiguous(memory_format=torch.channels_last) and yf.dtype == dtype
     yf.backward(dy)
     tol = dict(rtol=2e-4, atol=2e-4) if dtype == torch.float32 else dict(rtol=3e-2, atol=3e-2)
-    torch.testing.assert_close(yf.float(), yr, **tol)
+    torch.testing.assert_close(yf.float() * safe, yr * safe, **tol)
     torch.testing.assert_close(rm_f, rm_r, rtol=1e-4, atol=1e-5)
     torch.testing.assert_close(rv_f, rv_r, rtol=1e-4, atol=1e-5)
-    torch.testing.assert_close(xf.grad.float(), xr.grad, **tol)
+    torch.testing.assert_close(xf.grad.float() * safe, xr.grad * safe, **tol)
     gtol = dict(rtol=2e-3, atol=2e-2) if dtype == torch.float32 else dict(rtol=5e-2, atol=0.5)
     torch.testing.assert_close(wf.grad, wr.grad, **gtol)
     torch.testing.assert_close(bf.grad, br.grad, **gtol)
     if with_res:
-        torch.testing.assert_close(zf.grad.float(), zr.grad, **tol)
+        torch.testing.assert_close(zf.grad.float() * safe, zr.grad * safe, **tol)
 
 
 @pytest.mark.gpu
