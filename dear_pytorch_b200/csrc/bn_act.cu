@@ -139,8 +139,8 @@ __global__ void __launch_bounds__(kThreads) bn_stats_kernel(const T* __restrict_
     }
 #pragma unroll
     for (int k = 0; k < V; ++k) {
-      part_mean[int64_t(blockIdx.x) * g.C + c0 + k] = mean[k];
-      part_m2[int64_t(blockIdx.x) * g.C + c0 + k] = m2[k];
+      part_mean[int64_t(c0 + k) * g.row_blocks + blockIdx.x] = mean[k];
+      part_m2[int64_t(c0 + k) * g.row_blocks + blockIdx.x] = m2[k];
     }
     if (tx == 0 && blockIdx.y == 0) part_n[blockIdx.x] = na;
   }
@@ -167,8 +167,8 @@ __global__ void bn_finalize_kernel(const float* __restrict__ part_mean, const fl
       const int b = b0 + 32 * u;
       const bool ok = b < row_blocks;
       nb[u] = ok ? part_n[b] : 0.f;
-      mb[u] = ok ? part_mean[int64_t(b) * C + c] : 0.f;
-      qb[u] = ok ? part_m2[int64_t(b) * C + c] : 0.f;
+      mb[u] = ok ? part_mean[int64_t(c) * row_blocks + b] : 0.f;
+      qb[u] = ok ? part_m2[int64_t(c) * row_blocks + b] : 0.f;
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -311,8 +311,8 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_reduce_kernel(const T* __rest
     }
 #pragma unroll
     for (int k = 0; k < V; ++k) {
-      part_s1[int64_t(blockIdx.x) * g.C + c0 + k] = s1[k];
-      part_s2[int64_t(blockIdx.x) * g.C + c0 + k] = s2[k];
+      part_s1[int64_t(c0 + k) * g.row_blocks + blockIdx.x] = s1[k];
+      part_s2[int64_t(c0 + k) * g.row_blocks + blockIdx.x] = s2[k];
     }
   }
 }
@@ -331,8 +331,8 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ part_s1, const 
     for (int u = 0; u < 4; ++u) {
       const int b = b0 + 32 * u;
       const bool ok = b < row_blocks;
-      a[u] = ok ? part_s1[int64_t(b) * C + c] : 0.f;
-      q[u] = ok ? part_s2[int64_t(b) * C + c] : 0.f;
+      a[u] = ok ? part_s1[int64_t(c) * row_blocks + b] : 0.f;
+      q[u] = ok ? part_s2[int64_t(c) * row_blocks + b] : 0.f;
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) { s1 += a[u]; s2 += q[u]; }

@@ -48,8 +48,8 @@ def _run(dtype, relu, with_res, shape):
     b = torch.randn(C, device=dev)
     dy = torch.randn(N, C, H, W, device=dev).to(dtype).contiguous(memory_format=torch.channels_last)
     # reference in fp32
-    xr = x.float().requires_grad_(True)
-    zr = z.float().requires_grad_(True) if with_res else None
+    xr = x.detach().float().clone().requires_grad_(True)       # (.float() aliases an fp32 tensor: clone)
+    zr = z.detach().float().clone().requires_grad_(True) if with_res else None
     wr, br = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
     rm_r, rv_r = torch.zeros(C, device=dev), torch.ones(C, device=dev)
     yr = F.batch_norm(xr, rm_r, rv_r, wr, br, True, 0.1, 1e-5)
@@ -64,8 +64,8 @@ def _run(dtype, relu, with_res, shape):
         pre = F.batch_norm(x.float(), None, None, w, b, True, 0.0, 1e-5) + (z.float() if with_res else 0)
         safe = (pre.abs() > (1e-4 if dtype == torch.float32 else 5e-2)) if relu else torch.ones_like(pre, dtype=torch.bool)
     # fused
-    xf = x.clone().requires_grad_(True)
-    zf = z.clone().requires_grad_(True) if with_res else None
+    xf = x.detach().clone().requires_grad_(True)
+    zf = z.detach().clone().requires_grad_(True) if with_res else None
     wf, bf = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
     rm_f, rv_f = torch.zeros(C, device=dev), torch.ones(C, device=dev)
     yf = bn_act(xf, wf, bf, rm_f, rv_f, True, 0.1, 1e-5, relu=relu, residual=zf)
