@@ -107,7 +107,7 @@ class Workload:
             self.to_step_args = lambda b: (b[0], b[1], b[2], (b[3], b[4]))
             self.image = None
         else:
-            kw = {"fused_bn": True} if (args.fused_bn and args.channels_last and args.model.startswith("resnet")) else {}
+            kw = {"fused_bn": True} if (args.fused_bn and args.channels_last and args.model.startswith(("resnet", "densenet"))) else {}
             model = create(args.model, **kw).to(device)
             self.fused_bn = bool(kw)
             if args.channels_last:

@@ -395,8 +395,11 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const T* __restr
 static bool make_geo(int64_t M, int64_t C, int vec, Geo* g) {
   if (C % vec != 0) return false;
   const int64_t cv = C / vec;
-  if (cv & (cv - 1)) return false;                       // power of two only (ResNet / VGG-BN widths)
-  const int txv = static_cast<int>(std::min<int64_t>(cv, 64));
+  // channel vectors per CTA: the largest power-of-two divisor of cv (<= 64).  ResNet widths give 16..64;
+  // DenseNet (C = 64 + 32k) gives 8; widths without a divisor >= 4 fall back to the PyTorch composite.
+  int txv = 1;
+  while (txv < 64 && cv % (int64_t(txv) * 2) == 0) txv *= 2;
+  if (txv < 4) return false;
   g->M = M;
   g->C = static_cast<int>(C);
   g->txv = txv;

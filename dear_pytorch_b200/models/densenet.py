@@ -5,25 +5,35 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from ..ops.fused_bn import FusedBatchNormAct2d
+
+
+def _bn_relu(c, fused):
+    """BatchNorm followed by ReLU: one fused channels-last kernel, or the stock module (+ F.relu)."""
+    return FusedBatchNormAct2d(c, relu=True) if fused else nn.BatchNorm2d(c)
+
 
 class _DenseLayer(nn.Module):
-    def __init__(self, cin, growth, bn_size):
+    def __init__(self, cin, growth, bn_size, fused_bn=False):
         super().__init__()
-        self.norm1 = nn.BatchNorm2d(cin)
+        self.fused = fused_bn
+        self.norm1 = _bn_relu(cin, fused_bn)
         self.conv1 = nn.Conv2d(cin, bn_size * growth, 1, bias=False)
-        self.norm2 = nn.BatchNorm2d(bn_size * growth)
+        self.norm2 = _bn_relu(bn_size * growth, fused_bn)
         self.conv2 = nn.Conv2d(bn_size * growth, growth, 3, padding=1, bias=False)
 
     def forward(self, feats):
         x = torch.cat(feats, 1)
+        if self.fused:
+            return self.conv2(self.norm2(self.conv1(self.norm1(x))))
         x = self.conv1(F.relu(self.norm1(x), inplace=True))
         return self.conv2(F.relu(self.norm2(x), inplace=True))
 
 
 class _DenseBlock(nn.Module):
-    def __init__(self, n, cin, growth, bn_size):
+    def __init__(self, n, cin, growth, bn_size, fused_bn=False):
         super().__init__()
-        self.layers = nn.ModuleList(_DenseLayer(cin + i * growth, growth, bn_size) for i in range(n))
+        self.layers = nn.ModuleList(_DenseLayer(cin + i * growth, growth, bn_size, fused_bn) for i in range(n))
 
     def forward(self, x):
         feats = [x]
@@ -33,25 +43,29 @@ class _DenseBlock(nn.Module):
 
 
 class _Transition(nn.Sequential):
-    def __init__(self, cin, cout):
-        super().__init__(nn.BatchNorm2d(cin), nn.ReLU(inplace=True), nn.Conv2d(cin, cout, 1, bias=False),
-                         nn.AvgPool2d(2, 2))
+    def __init__(self, cin, cout, fused_bn=False):
+        head = [FusedBatchNormAct2d(cin, relu=True), nn.Identity()] if fused_bn else \
+            [nn.BatchNorm2d(cin), nn.ReLU(inplace=True)]      # (Identity keeps the state-dict indices)
+        super().__init__(*head, nn.Conv2d(cin, cout, 1, bias=False), nn.AvgPool2d(2, 2))
 
 
 class DenseNet(nn.Module):
-    def __init__(self, growth=32, blocks=(6, 12, 24, 16), init_features=64, bn_size=4, num_classes=1000):
+    def __init__(self, growth=32, blocks=(6, 12, 24, 16), init_features=64, bn_size=4, num_classes=1000, fused_bn=False):
         super().__init__()
-        self.stem = nn.Sequential(nn.Conv2d(3, init_features, 7, stride=2, padding=3, bias=False),
-                                  nn.BatchNorm2d(init_features), nn.ReLU(inplace=True), nn.MaxPool2d(3, 2, 1))
+        self.fused = fused_bn
+        stem_bn = [FusedBatchNormAct2d(init_features, relu=True), nn.Identity()] if fused_bn else \
+            [nn.BatchNorm2d(init_features), nn.ReLU(inplace=True)]
+        self.stem = nn.Sequential(nn.Conv2d(3, init_features, 7, stride=2, padding=3, bias=False), *stem_bn,
+                                  nn.MaxPool2d(3, 2, 1))
         stages, c = [], init_features
         for i, n in enumerate(blocks):
-            stages.append(_DenseBlock(n, c, growth, bn_size))
+            stages.append(_DenseBlock(n, c, growth, bn_size, fused_bn))
             c += n * growth
             if i != len(blocks) - 1:
-                stages.append(_Transition(c, c // 2))
+                stages.append(_Transition(c, c // 2, fused_bn))
                 c //= 2
         self.stages = nn.Sequential(*stages)
-        self.norm = nn.BatchNorm2d(c)
+        self.norm = _bn_relu(c, fused_bn)
         self.classifier = nn.Linear(c, num_classes)
         for m in self.modules():
             if isinstance(m, nn.Conv2d):
@@ -63,7 +77,9 @@ class DenseNet(nn.Module):
                 nn.init.zeros_(m.bias)
 
     def forward(self, x):
-        x = F.relu(self.norm(self.stages(self.stem(x))), inplace=True)
+        x = self.norm(self.stages(self.stem(x)))
+        if not self.fused:
+            x = F.relu(x, inplace=True)
         return self.classifier(torch.flatten(F.adaptive_avg_pool2d(x, 1), 1))
 
 
