@@ -22,13 +22,15 @@ def main(argv=None):
                                  formatter_class=argparse.ArgumentDefaultsHelpFormatter)
     ap.add_argument("--model", type=str, default="resnet50")
     ap.add_argument("--channels-last", type=int, default=1)
+    ap.add_argument("--fused-bn", type=int, default=1, help="fused BatchNorm(+add)+ReLU kernels (resnet*/densenet*)")
     common.add_common_args(ap)
     args = ap.parse_args(argv)
     method, cuda = common.init_runtime(args)
     device = dear.device()
     dtype = args.dtype or ("bf16" if args.fp16 else "fp32")
 
-    model = create(args.model).to(device)
+    kw = {"fused_bn": True} if (args.fused_bn and args.channels_last and args.model.startswith(("resnet", "densenet"))) else {}
+    model = create(args.model, **kw).to(device)
     if args.channels_last and cuda:
         model = model.to(memory_format=torch.channels_last)
     if dtype == "bf16":
