@@ -38,7 +38,8 @@ def parse_args(argv=None):
     ap.add_argument("--sentence-len", type=int, default=64)
     ap.add_argument("--dtype", choices=["fp32", "bf16", "amp"], default=os.environ.get("DEAR_BENCH_DTYPE"))
     ap.add_argument("--channels-last", type=int, default=int(os.environ.get("DEAR_BENCH_CL", "1")))
-    ap.add_argument("--graph", type=int, default=int(os.environ.get("DEAR_BENCH_GRAPH", "0")))
+    ap.add_argument("--graph", type=int, default=int(os.environ.get("DEAR_BENCH_GRAPH", "1")),
+                    help="replay the whole iteration as one CUDA graph (GPU only; validated at 1/2/8 GPUs)")
     ap.add_argument("--fused-bn", type=int, default=int(os.environ.get("DEAR_BENCH_FUSED_BN", "1")),
                     help="ResNets: fused channels-last BatchNorm(+add)+ReLU kernels (csrc/bn_act.cu)")
     ap.add_argument("--threshold", type=float, default=25.0)
@@ -173,13 +174,22 @@ def run_dear(args):
         if cuda:
             torch.cuda.synchronize(device)
 
+    comm = dear.communicator()
+    from dear_pytorch_b200 import ops as _ops
+
+    def n_launches():
+        """kernels of THIS repo launched so far: fused RS / SGD+AG / general collectives + fused BN"""
+        n = comm.launches() if comm is not None else opt.engine.backend.launches()
+        C = _ops.native()
+        return n + (C.bn_act_launches() if C is not None else 0)
+
+    l_warm = n_launches()
     for _ in range(args.warmup):
         step(*dev_batch)
     opt.engine.synchronize(host=True)
-    comm = dear.communicator()
-
-    def n_launches():
-        return comm.launches() if comm is not None else opt.engine.backend.launches()
+    # launches per iteration, counted while the Python step body ran (a replayed CUDA graph launches
+    # the same kernels without passing through the host-side counters)
+    per_step_launches = (n_launches() - l_warm) / max(1, step.eager_calls)
 
     def timed(run_one, n):
         dear.barrier(); sync()
@@ -205,8 +215,7 @@ def run_dear(args):
     ms, launches = timed(lambda: step(*dev_batch), args.steps)
     wall1 = time.time()
     if args.graph and cuda:
-        # a replayed CUDA graph launches the same kernels without going through the host counters
-        launches = 2 * len(opt.engine.plan.buckets) * args.steps
+        launches = int(round(per_step_launches * args.steps))
 
     # ---- end to end: pinned host batches -> H2D every step, loss -> host every step ----------
     e2e = None

@@ -14,6 +14,7 @@ using namespace dear;
 
 namespace dear { namespace bn {
 bool bn_act_supported(const torch::Tensor& x);
+int64_t bn_act_launches();
 std::vector<torch::Tensor> bn_act_forward(const torch::Tensor& x, const c10::optional<torch::Tensor>& z,
                                           const c10::optional<torch::Tensor>& gamma, const c10::optional<torch::Tensor>& beta,
                                           c10::optional<torch::Tensor> running_mean, c10::optional<torch::Tensor> running_var,
@@ -100,6 +101,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
 
   // fused channels-last BatchNorm (+ residual) (+ ReLU)
   m.def("bn_act_supported", &dear::bn::bn_act_supported);
+  m.def("bn_act_launches", &dear::bn::bn_act_launches);
   m.def("bn_act_forward", &dear::bn::bn_act_forward, py::arg("x"), py::arg("residual"), py::arg("weight"), py::arg("bias"),
         py::arg("running_mean"), py::arg("running_var"), py::arg("training"), py::arg("momentum"), py::arg("eps"),
         py::arg("relu"));

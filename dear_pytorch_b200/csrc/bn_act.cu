@@ -16,6 +16,7 @@
 //
 // The reference has no such op (its models are stock torchvision: BatchNorm2d + ReLU as separate
 // cuDNN / ATen kernels, dear/imagenet_benchmark.py:78-82).
+#include <atomic>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <torch/extension.h>
@@ -26,6 +27,8 @@ namespace dear {
 namespace bn {
 
 constexpr int kThreads = 256;
+static std::atomic<int64_t> g_launches{0};      // kernels launched by this file (bench.py reports them)
+int64_t bn_act_launches() { return g_launches.load(); }
 
 template <typename T> struct Vec;
 template <> struct Vec<float> {
@@ -482,6 +485,7 @@ std::vector<torch::Tensor> bn_act_forward(const torch::Tensor& x, const c10::opt
   if (f32) fwd_impl<float>(x, z, scale.data_ptr<float>(), shift.data_ptr<float>(), y, relu, g, s);
   else fwd_impl<__nv_bfloat16>(x, z, scale.data_ptr<float>(), shift.data_ptr<float>(), y, relu, g, s);
   C10_CUDA_KERNEL_LAUNCH_CHECK();
+  g_launches.fetch_add(training ? 3 : 2);
   return {y, save_mean, save_invstd, scale, shift};
 }
 
@@ -543,6 +547,7 @@ std::vector<torch::Tensor> bn_act_backward(const torch::Tensor& dy_in, const tor
                             shift.data_ptr<float>(), ps1, ps2, dgamma.data_ptr<float>(), dbeta.data_ptr<float>(), c1, c2, dx, dz,
                             relu, g, s);
   C10_CUDA_KERNEL_LAUNCH_CHECK();
+  g_launches.fetch_add(3);
   return {dx, dz.has_value() ? *dz : torch::Tensor(), dgamma, dbeta};
 }
 

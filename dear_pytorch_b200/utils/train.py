@@ -58,8 +58,10 @@ class TrainStep:
         self._engine = getattr(optimizer, "_dear", None)
         self._debug = bool(os.environ.get("DEAR_GRAPH_DEBUG"))
         self._side = None
+        self.eager_calls = 0               # how many times the Python step body ran (incl. the capture)
 
     def _eager(self, *batch):
+        self.eager_calls += 1
         *inputs, target = batch
         self.opt.zero_grad()
         if self.autocast_dtype is not None:
