@@ -1,10 +1,16 @@
 """Host->device input pipeline.
 
-``PinnedPrefetcher`` double-buffers batches: while step *t* computes, batch *t+1* is copied from
-pinned host memory on a dedicated copy stream, so the host->device transfer (38.5 MB per step for
-64x3x224x224 fp32) is hidden behind compute.  The reference keeps one fixed batch on the device
-for the whole benchmark (dear/imagenet_benchmark.py:97-103); this pipeline is what the end-to-end
-number of ``bench.py`` goes through.
+``PinnedPrefetcher`` keeps ``depth`` batches in flight: while step *t* computes, batch *t+1* is
+copied from pinned host memory into a **preallocated ring of device buffers** on a dedicated copy
+stream, so the host->device transfer (38.5 MB per step for 64x3x224x224 fp32) is hidden behind
+compute and the steady state performs no device allocation at all (an allocation per step on a side
+stream makes the caching allocator fall back to cudaMalloc while the host runs ahead of the GPU).
+The reference keeps one fixed batch on the device for the whole benchmark
+(dear/imagenet_benchmark.py:97-103); this pipeline is what the end-to-end number of ``bench.py``
+goes through.
+
+Contract: a batch returned by ``next()`` stays valid until the work enqueued before the *next*
+``next()`` call has consumed it (the usual "one batch per training step" loop).
 """
 from __future__ import annotations
 
@@ -39,7 +45,7 @@ class SyntheticImages:
 
 
 class PinnedPrefetcher:
-    """Wrap an iterable of pinned host batches; yields device batches, one copy ahead."""
+    """Wrap an iterable of pinned host batches; yields device batches, ``depth`` copies ahead."""
 
     def __init__(self, host_batches: Iterable[Sequence[torch.Tensor]], device: torch.device, depth: int = 2):
         self.it = iter(host_batches)
@@ -47,10 +53,23 @@ class PinnedPrefetcher:
         self.cuda = self.device.type == "cuda"
         self.depth = max(1, depth)
         self.queue = []
+        self.nslots = self.depth + 1
+        self.ring = [None] * self.nslots          # device buffers, allocated once per slot
+        self.free_ev = [None] * self.nslots       # compute-stream event: slot may be overwritten
+        self._slot = 0
+        self._last = None
         if self.cuda:
             self.stream = torch.cuda.Stream(device=self.device)
         for _ in range(self.depth):
             self._enqueue()
+
+    def _buffers_for(self, slot, host):
+        bufs = self.ring[slot]
+        if bufs is None or len(bufs) != len(host) or any(b.shape != h.shape or b.dtype != h.dtype or b.stride() != h.stride()
+                                                         for b, h in zip(bufs, host)):
+            bufs = tuple(torch.empty_strided(h.shape, h.stride(), dtype=h.dtype, device=self.device) for h in host)
+            self.ring[slot] = bufs
+        return bufs
 
     def _enqueue(self):
         try:
@@ -58,13 +77,19 @@ class PinnedPrefetcher:
         except StopIteration:
             return
         if not self.cuda:
-            self.queue.append((tuple(host), None))
+            self.queue.append((tuple(host), None, -1))
             return
+        slot = self._slot
+        self._slot = (slot + 1) % self.nslots
+        bufs = self._buffers_for(slot, host)
         with torch.cuda.stream(self.stream):
-            dev = tuple(t.to(self.device, non_blocking=True) for t in host)
+            if self.free_ev[slot] is not None:
+                self.stream.wait_event(self.free_ev[slot])      # the consumer is done with this slot
+            for b, h in zip(bufs, host):
+                b.copy_(h, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self.stream)
-        self.queue.append((dev, ev))
+        self.queue.append((bufs, ev, slot))
 
     def __iter__(self):
         return self
@@ -72,11 +97,14 @@ class PinnedPrefetcher:
     def __next__(self):
         if not self.queue:
             raise StopIteration
-        dev, ev = self.queue.pop(0)
+        if self.cuda and self._last is not None:
+            # everything enqueued so far has consumed the previous batch: its slot is free after that
+            done = torch.cuda.Event()
+            done.record(torch.cuda.current_stream(self.device))
+            self.free_ev[self._last] = done
+        dev, ev, slot = self.queue.pop(0)
         if ev is not None:
-            cur = torch.cuda.current_stream(self.device)
-            cur.wait_event(ev)
-            for t in dev:
-                t.record_stream(cur)      # allocated on the copy stream, consumed on the compute stream
+            torch.cuda.current_stream(self.device).wait_event(ev)
+        self._last = slot if slot >= 0 else None
         self._enqueue()
         return dev
