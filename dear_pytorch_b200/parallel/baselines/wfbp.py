@@ -89,10 +89,61 @@ def mgwfbp_groups(sizes: Sequence[int], tb: Sequence[float], alpha: float, beta:
     return groups
 
 
+def mgs_groups(sizes: Sequence[int], tb: Sequence[float], world: int, density: float) -> List[List[int]]:
+    """MGS-SGD merged *sparsified*-gradient grouping (Shi et al., INFOCOM 2020; reference
+    wfbp/dopt.py:488-569): merge layer l into l-1 when the extra waiting (longer backward + top-k of
+    the merged tensor) is smaller than the all-gather start-up time it saves.  Uses the reference's
+    cost models (``perf_model.topk_perf_model`` / ``allgather_perf_model``).  Layers in FORWARD order;
+    returns groups of layer indices in backward order."""
+    L = len(sizes)
+    p = list(sizes)
+    tb = list(tb)
+    Pm = world if world in perf_model.GbE_multi_p_ab_small else max(k for k in perf_model.GbE_multi_p_ab_small if k <= max(world, 2))
+    topk = perf_model.topk_perf_model
+    ag = lambda n: perf_model.allgather_perf_model(n, Pm, density)
+
+    def schedule():
+        ts = [topk(n) for n in p]
+        tc = [ag(n) for n in p]
+        taob, taos, taoc = [0.0] * L, [0.0] * L, [0.0] * L
+        taos[L - 1] = taob[L - 1] + tb[L - 1]
+        for l in range(L - 2, -1, -1):
+            taob[l] = taos[l + 1] + ts[l + 1]
+            taos[l] = taob[l] + tb[l]
+        taoc[L - 1] = taos[L - 1] + ts[L - 1]
+        for l in range(L - 2, -1, -1):
+            taoc[l] = max(taoc[l + 1] + tc[l + 1], taos[l] + ts[l])
+        return ts, taos, taoc
+
+    ts, taos, taoc = schedule()
+    groups, group = [], [L - 1] if L > 1 else []
+    for l in range(L - 2, 0, -1):
+        group.append(l)
+        t_wait = tb[l - 1] + topk(p[l] + p[l - 1]) - topk(p[l]) - topk(p[l - 1]) - (taoc[l] - (taos[l] + ts[l]))
+        t_save = ag(p[l]) + ag(p[l - 1]) - ag(p[l] + p[l - 1])
+        if t_wait < t_save:
+            tb[l - 1] += tb[l]; tb[l] = 0.0
+            p[l - 1] += p[l]; p[l] = 0
+            ts, taos, taoc = schedule()
+        else:
+            groups.append(group)
+            group = []
+    group.append(0)
+    groups.append(group)
+    # the walk above only closes groups between l and l-1 for l >= 2; de-duplicate and keep order
+    seen, out = set(), []
+    for g in groups:
+        g2 = [i for i in g if i not in seen]
+        seen.update(g2)
+        if g2:
+            out.append(g2)
+    return out
+
+
 class _DistributedOptimizer(torch.optim.Optimizer):
     def __init__(self, params, named_parameters, compression=None, is_sparse=False, density=0.001,
                  seq_layernames=None, layerwise_times=None, norm_clip=None, threshold=0, fp16=False, mgwfbp=False,
-                 asc=False, rdma=False, alpha=None, beta=None, verbose=True):
+                 asc=False, mgs=False, rdma=False, alpha=None, beta=None, verbose=True):
         super(self.__class__, self).__init__(params)
         if not runtime.is_initialized():
             runtime.init()
@@ -110,7 +161,12 @@ class _DistributedOptimizer(torch.optim.Optimizer):
         if self._cuda:
             self._stream = torch.cuda.Stream(device=self._device, priority=-1)
         self.alpha, self.beta = alpha, beta
-        if mgwfbp or asc:
+        if mgs and self._sparse and layerwise_times is not None and seq_layernames is not None:
+            by_name = {n: p for n, p in named}
+            sizes = [by_name[n].numel() for n in seq_layernames]
+            gidx = mgs_groups(sizes, layerwise_times, self._world, density)
+            self._groups = [[seq_layernames[i] for i in g] for g in gidx]
+        elif mgwfbp or asc:
             if layerwise_times is None or seq_layernames is None:
                 raise ValueError("MG-WFBP needs seq_layernames and layerwise_times (utils.profiling.benchmark)")
             if self.alpha is None:
@@ -226,8 +282,8 @@ class _DistributedOptimizer(torch.optim.Optimizer):
 
 def DistributedOptimizer(optimizer, named_parameters=None, model: Optional[nn.Module] = None, compression=None,
                          is_sparse=False, density=0.001, seq_layernames=None, layerwise_times=None, norm_clip=None,
-                         threshold=0, writer=None, gradient_path=None, fp16=False, mgwfbp=False, asc=False, rdma=False,
-                         multi_job_scheduling=False, alpha=None, beta=None, verbose=True, **ignored):
+                         threshold=0, writer=None, gradient_path=None, fp16=False, mgwfbp=False, asc=False, mgs=False,
+                         rdma=False, multi_job_scheduling=False, alpha=None, beta=None, verbose=True, **ignored):
     """WFBP (``threshold=0``), threshold fusion, MG-WFBP (``mgwfbp=True``) or ASC (``asc=True``)."""
     if named_parameters is None:
         if model is None:
@@ -238,5 +294,5 @@ def DistributedOptimizer(optimizer, named_parameters=None, model: Optional[nn.Mo
     cls = type(optimizer.__class__.__name__, (optimizer.__class__,), dict(_DistributedOptimizer.__dict__))
     return cls(optimizer.param_groups, list(named_parameters), compression=compression, is_sparse=is_sparse,
                density=density, seq_layernames=seq_layernames, layerwise_times=layerwise_times, norm_clip=norm_clip,
-               threshold=threshold, fp16=fp16, mgwfbp=mgwfbp, asc=asc, rdma=rdma, alpha=alpha, beta=beta,
+               threshold=threshold, fp16=fp16, mgwfbp=mgwfbp, asc=asc, mgs=mgs, rdma=rdma, alpha=alpha, beta=beta,
                verbose=verbose)
