@@ -157,3 +157,41 @@ def test_cuda_graph_replay_matches_eager(world):
         torch.testing.assert_close(torch.tensor(lg), torch.tensor(le), rtol=1e-4, atol=1e-5)
         for a, b in zip(pg, pe):
             torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-5)
+
+
+def gpu_rebucket_worker(rank, world, steps, per_rank):
+    import dear_pytorch_b200 as dear
+    dev = dear.device()
+    case = dict(momentum=0.9, weight_decay=1e-3)
+    model = make_model().to(dev)
+    model.eval()
+    opt = torch.optim.SGD(model.parameters(), lr=0.05, **case)
+    opt = dear.DistributedOptimizer(opt, model, threshold=0.001, verbose=False)
+    dear.broadcast_parameters(model.state_dict(), 0)
+    layouts = []
+    for t in range(steps):
+        if t == 2:
+            opt.engine.request_rebucket(("threshold", 0.004))
+        if t == 4:
+            opt.engine.request_rebucket(("nearby", -1))
+        x, y = data(t, world * per_rank)
+        x, y = x[rank * per_rank:(rank + 1) * per_rank].to(dev), y[rank * per_rank:(rank + 1) * per_rank].to(dev)
+        opt.zero_grad()
+        nn.functional.cross_entropy(model(x), y).backward()
+        opt.step()
+        layouts.append(len(opt.engine.plan.buckets))
+    opt.synchronize()
+    dear.communicator().check_status()
+    return [p.detach().float().cpu() for p in model.parameters()], layouts
+
+
+def test_rebucketing_on_gpu_migrates_sharded_state():
+    """dopt_rsag_bo's re-bucketing at the safe point, on the fused path: new symmetric arenas are
+    rendezvoused, parameters and the sharded momentum move, training stays equivalent to SGD."""
+    case = dict(momentum=0.9, weight_decay=1e-3)
+    ref = reference_run(case, 7, 2, 4)
+    outs = run_ranks(gpu_rebucket_worker, world=2, backend="b200", args=(7, 4), extra_env=_env(), timeout=300)
+    for params, layouts in outs:
+        assert len(set(layouts)) == 3 and layouts[-1] == 1
+        for a, b in zip(params, ref):
+            torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-5)
