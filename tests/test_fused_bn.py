@@ -86,7 +86,7 @@ def _run(dtype, relu, with_res, shape):
 @pytest.mark.gpu
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("relu,with_res", [(True, False), (True, True), (False, False), (False, True)])
-@pytest.mark.parametrize("shape", [(8, 64, 14, 14), (3, 256, 7, 5), (2, 2048, 3, 3), (5, 16, 9, 9)])
+@pytest.mark.parametrize("shape", [(8, 64, 14, 14), (3, 256, 7, 5), (2, 2048, 3, 3), (5, 16, 9, 9), (2, 96, 6, 6), (3, 160, 5, 5)])
 def test_fused_kernels_match_pytorch(dtype, relu, with_res, shape):
     from dear_pytorch_b200 import ops
     C = ops.require_native()
