@@ -22,16 +22,22 @@ def main(argv=None):
     ap.add_argument("--model", type=str, default="bert", choices=["bert", "bert_large", "bert_base"])
     ap.add_argument("--sentence-len", type=int, default=128)
     ap.add_argument("--lr", type=float, default=2e-5)
+    ap.add_argument("--config", type=str, default=None, help="optional JSON file with BertConfig fields")
     common.add_common_args(ap)
     args = ap.parse_args(argv)
     method, cuda = common.init_runtime(args)
     device = dear.device()
     dtype = args.dtype or ("bf16" if args.fp16 else "fp32")
 
-    cfg_path = os.path.join(common.ROOT, "configs", "bert_base_config.json" if args.model == "bert_base" else "bert_config.json")
-    import json
-    with open(cfg_path) as f:
-        cfg = bert_models.BertConfig(**{k: v for k, v in json.load(f).items() if k in bert_models.BertConfig.__dataclass_fields__})
+    # architecture hyper-parameters: models/bert.py (BERT_LARGE = 24 layers / 1024 hidden / 16 heads / 4096 FFN,
+    # BERT_BASE = 12 / 768 / 12 / 3072; vocabulary 30522) or a user-supplied JSON file
+    if args.config:
+        import json
+        with open(args.config) as f:
+            cfg = bert_models.BertConfig(**{k: v for k, v in json.load(f).items()
+                                            if k in bert_models.BertConfig.__dataclass_fields__})
+    else:
+        cfg = bert_models.BERT_BASE if args.model == "bert_base" else bert_models.BERT_LARGE
     model = bert_models.BertForPreTraining(cfg).to(device)      # vocabulary padded to a multiple of 8
     if dtype == "bf16":
         model = model.to(torch.bfloat16)
