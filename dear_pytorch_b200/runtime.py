@@ -211,5 +211,9 @@ def broadcast_object(obj, src: int = 0):
     if st.world == 1:
         return obj
     box = [obj]
-    dist.broadcast_object_list(box, src=src, group=st.group, device=torch.device("cpu"))
+    try:
+        dist.broadcast_object_list(box, src=src, group=st.group, device=torch.device("cpu"))
+    except (RuntimeError, ValueError):
+        # a user-created NCCL-only process group has no CPU backend: stage through the GPU
+        dist.broadcast_object_list(box, src=src, group=st.group, device=st.device)
     return box[0]
