@@ -44,6 +44,8 @@ def parse_args(argv=None):
                     help="ResNets: fused channels-last BatchNorm(+add)+ReLU kernels (csrc/bn_act.cu)")
     ap.add_argument("--threshold", type=float, default=25.0)
     ap.add_argument("--momentum", type=float, default=0.0)
+    ap.add_argument("--optimizer", choices=["sgd", "adam", "adamw"], default="sgd",
+                    help="sgd = the reference's benchmark optimizer; adam/adamw use the sharded Adam epilogue of Kernel B")
     ap.add_argument("--backend", default=None)
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args(argv)
@@ -159,7 +161,11 @@ def run_dear(args):
     wl = Workload(args, device, rank)
     model = wl.model
     lr = (2e-5 if wl.is_bert else 0.01 * world)          # dear/bert_benchmark.py:122, dear/imagenet_benchmark.py:94
-    base = torch.optim.SGD(model.parameters(), lr=lr, momentum=args.momentum)
+    if args.optimizer == "sgd":
+        base = torch.optim.SGD(model.parameters(), lr=lr, momentum=args.momentum)
+    else:
+        lr *= 0.1
+        base = (torch.optim.AdamW if args.optimizer == "adamw" else torch.optim.Adam)(model.parameters(), lr=lr)
     opt = dear.DistributedOptimizer(base, model, threshold=args.threshold,
                                     verbose=(rank == 0 and bool(os.environ.get("DEAR_VERBOSE"))))
     dear.broadcast_parameters(model.state_dict(), 0)
@@ -257,7 +263,7 @@ def run_dear(args):
     if rank == 0:
         n_params = sum(p.numel() for p in model.parameters())
         cfg = {"model": args.model, "global_batch": B * world, "batch_per_gpu": B, "parallelism": "dp%d" % world,
-               "optimizer": "SGD lr=%g" % lr, "threshold_mb": args.threshold, "buckets": len(opt.engine.plan.buckets),
+               "optimizer": "%s lr=%g" % (args.optimizer.upper(), lr), "threshold_mb": args.threshold, "buckets": len(opt.engine.plan.buckets),
                "params": n_params, "backend": dear.backend(), "cuda_graph": bool(args.graph),
                "l2": "no explicit flush: each step streams activations+weights far larger than the 126 MB L2"}
         if wl.is_bert:

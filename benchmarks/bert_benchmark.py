@@ -44,7 +44,7 @@ def main(argv=None):
     criterion = bert_models.BertPretrainingCriterion(model.vocab_size)
     ids, mask, types, nsp, mlm = bert_models.synthetic_batch(args.batch_size, args.sentence_len, model.vocab_size, device)
 
-    optimizer = torch.optim.SGD(model.parameters(), lr=args.lr, momentum=args.momentum)
+    optimizer = common.make_base_optimizer(args, model.parameters(), args.lr)
 
     def profile():
         from dear_pytorch_b200.utils.profiling import benchmark

@@ -44,6 +44,8 @@ def add_common_args(ap):
     ap.add_argument("--density", type=float, default=1.0)
     ap.add_argument("--exclude-parts", type=str, default="", help="reducescatter, allgather (time breakdown)")
     ap.add_argument("--momentum", type=float, default=0.0)
+    ap.add_argument("--optimizer", choices=["sgd", "adam", "adamw"], default="sgd",
+                    help="adam/adamw: sharded Adam fused into the all-gather kernel (dear methods only)")
     ap.add_argument("--graph", type=int, default=0, help="capture the whole iteration in a CUDA graph")
     ap.add_argument("--json", type=str, default=None, help="also write the result as JSON to this file")
     return ap
@@ -172,3 +174,13 @@ def finish(args, result, extra):
         import json
         with open(args.json, "w") as f:
             json.dump(dict(result, **extra), f, indent=1)
+
+
+def make_base_optimizer(args, params, lr):
+    """The reference benchmarks always use SGD (dear/imagenet_benchmark.py:94, dear/bert_benchmark.py:122)."""
+    import torch
+    if getattr(args, "optimizer", "sgd") == "adamw":
+        return torch.optim.AdamW(params, lr=lr)
+    if getattr(args, "optimizer", "sgd") == "adam":
+        return torch.optim.Adam(params, lr=lr)
+    return torch.optim.SGD(params, lr=lr, momentum=args.momentum)

@@ -46,7 +46,7 @@ def main(argv=None):
         data = data.contiguous(memory_format=torch.channels_last)
     target = torch.randint(0, 1000, (args.batch_size,), device=device)
 
-    optimizer = torch.optim.SGD(model.parameters(), lr=0.01 * dear.size(), momentum=args.momentum)
+    optimizer = common.make_base_optimizer(args, model.parameters(), 0.01 * dear.size())
 
     def profile():
         from dear_pytorch_b200.utils.profiling import benchmark

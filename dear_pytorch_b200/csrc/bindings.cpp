@@ -86,9 +86,12 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def("param_buffer", &BucketSet::param_buffer)
       .def("grad_buffer", &BucketSet::grad_buffer)
       .def("set_shards", &BucketSet::set_shards, py::arg("bucket"), py::arg("grad_shard"),
-           py::arg("momentum") = py::none(), py::arg("master") = py::none())
+           py::arg("momentum") = py::none(), py::arg("master") = py::none(), py::arg("var") = py::none())
+      .def("set_step", &BucketSet::set_step)
       .def("set_pack", &BucketSet::set_pack)
-      .def("set_hyper", &BucketSet::set_hyper)
+      .def("set_hyper", &BucketSet::set_hyper, py::arg("bucket"), py::arg("ends"), py::arg("lr"), py::arg("weight_decay"),
+           py::arg("momentum"), py::arg("dampening"), py::arg("nesterov"), py::arg("opt") = std::vector<int64_t>{},
+           py::arg("beta2") = std::vector<double>{}, py::arg("eps") = std::vector<double>{})
       .def("reduce_scatter", &BucketSet::reduce_scatter, py::arg("bucket"), py::arg("pack") = true)
       .def("allgather_update", &BucketSet::allgather_update, py::arg("bucket"), py::arg("do_update") = true,
            py::arg("first_step") = false, py::arg("entry_barrier") = true, py::arg("zero_grad") = false)
@@ -107,6 +110,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("relu"));
   m.def("bn_act_backward", &dear::bn::bn_act_backward);
 
+  m.attr("OPT_SGD") = static_cast<int>(OPT_SGD);
+  m.attr("OPT_ADAM") = static_cast<int>(OPT_ADAM);
+  m.attr("OPT_ADAMW") = static_cast<int>(OPT_ADAMW);
   m.attr("DT_F32") = static_cast<int>(DT_F32);
   m.attr("DT_BF16") = static_cast<int>(DT_BF16);
   m.attr("DT_F16") = static_cast<int>(DT_F16);

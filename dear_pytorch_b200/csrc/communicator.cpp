@@ -436,8 +436,20 @@ torch::Tensor BucketSet::grad_buffer(int g) {
   return wrap(arena_->local_data() + b.grad_off, b.padded, dtype_, comm_->is_cuda(), comm_->options().device, arena_);
 }
 
+void BucketSet::set_step(int g, int64_t t) {
+  buckets_.at(g);
+  const uint32_t v = static_cast<uint32_t>(t);
+  uint32_t* dst = arena_->ctrl() + 2 * kNumChannels + g;
+  if (comm_->is_cuda()) {
+    DEAR_CUDA(cudaStreamSynchronize(S(stream_)));
+    DEAR_CUDA(cudaMemcpy(dst, &v, sizeof(v), cudaMemcpyHostToDevice));
+  } else {
+    *dst = v;
+  }
+}
+
 void BucketSet::set_shards(int g, torch::Tensor grad_shard, std::optional<torch::Tensor> mom,
-                           std::optional<torch::Tensor> master) {
+                           std::optional<torch::Tensor> master, std::optional<torch::Tensor> var) {
   auto& b = buckets_.at(g);
   auto chk = [&](const torch::Tensor& t, const char* what) {
     DEAR_CHECK(t.scalar_type() == torch::kFloat && t.is_contiguous() && t.numel() == b.shard,
@@ -450,6 +462,8 @@ void BucketSet::set_shards(int g, torch::Tensor grad_shard, std::optional<torch:
   b.master = torch::Tensor();
   if (mom.has_value() && mom->defined()) { chk(*mom, "momentum shard"); b.mom = *mom; }
   if (master.has_value() && master->defined()) { chk(*master, "master shard"); b.master = *master; }
+  b.var = torch::Tensor();
+  if (var.has_value() && var->defined()) { chk(*var, "second-moment shard"); b.var = *var; }
   // (low-precision buckets must have a master shard by the time allgather_update() runs)
 }
 
@@ -523,7 +537,8 @@ bool BucketSet::set_pack(int g, const std::vector<int64_t>& src_ptrs, const std:
 
 bool BucketSet::set_hyper(int g, const std::vector<int64_t>& ends, const std::vector<double>& lr,
                           const std::vector<double>& wd, const std::vector<double>& mom,
-                          const std::vector<double>& damp, const std::vector<int64_t>& nesterov) {
+                          const std::vector<double>& damp, const std::vector<int64_t>& nesterov,
+                          const std::vector<int64_t>& opt, const std::vector<double>& beta2, const std::vector<double>& eps) {
   auto& b = buckets_.at(g);
   const size_t n = ends.size();
   DEAR_CHECK(n >= 1 && lr.size() == n && wd.size() == n && mom.size() == n && damp.size() == n && nesterov.size() == n,
@@ -536,12 +551,18 @@ bool BucketSet::set_hyper(int g, const std::vector<int64_t>& ends, const std::ve
     segs[i].momentum = static_cast<float>(mom[i]);
     segs[i].dampening = static_cast<float>(damp[i]);
     segs[i].nesterov = nesterov[i] ? 1u : 0u;
-    segs[i].reserved = 0;
+    segs[i].opt = i < opt.size() ? static_cast<uint32_t>(opt[i]) : OPT_SGD;
+    segs[i].beta2 = i < beta2.size() ? static_cast<float>(beta2[i]) : 0.f;
+    segs[i].eps = i < eps.size() ? static_cast<float>(eps[i]) : 0.f;
     DEAR_CHECK(i == 0 || segs[i].end > segs[i - 1].end, "set_hyper: segment ends must increase");
   }
   DEAR_CHECK(segs.back().end >= static_cast<uint64_t>(b.padded), "set_hyper: segments must cover the bucket");
   const bool same = segs.size() == b.hyper_host.size() &&
                     std::memcmp(segs.data(), b.hyper_host.data(), segs.size() * sizeof(HyperSeg)) == 0;
+  bool any_adam = false, all_adam = true;
+  for (const auto& sg : segs) { any_adam |= sg.opt != OPT_SGD; all_adam &= sg.opt != OPT_SGD; }
+  DEAR_CHECK(!any_adam || all_adam, "a bucket cannot mix SGD and Adam parameter groups");
+  b.adam = all_adam;
   if (same) return false;
   b.hyper_host = std::move(segs);
   if (comm_->is_cuda())
@@ -612,6 +633,12 @@ void BucketSet::allgather_update(int g, bool do_update, bool first_step, bool en
     DEAR_CHECK(!b.hyper_host.empty(), "set_hyper() must be called before allgather_update()");
     p.grad_shard = b.grad_shard.data_ptr<float>();
     p.mom_shard = b.mom.defined() ? b.mom.data_ptr<float>() : nullptr;
+    p.adam = b.adam ? 1u : 0u;
+    if (b.adam) {
+      DEAR_CHECK(b.mom.defined() && b.var.defined(), "Adam needs exp_avg and exp_avg_sq shards (set_shards)");
+      p.var_shard = b.var.data_ptr<float>();
+    }
+    p.step_ctr = arena_->ctrl() + 2 * kNumChannels + g;
     p.hyper = cuda ? b.hyper_dev : b.hyper_host.data();
     p.nhyper = static_cast<uint32_t>(b.hyper_host.size());
   }

@@ -116,13 +116,16 @@ class BucketSet {
   bool has_multicast() const { return arena_->has_multicast(); }
 
   void set_shards(int g, torch::Tensor grad_shard, std::optional<torch::Tensor> mom,
-                  std::optional<torch::Tensor> master);
+                  std::optional<torch::Tensor> master, std::optional<torch::Tensor> var);
+  // number of updates already applied to bucket g (Adam bias correction); device-resident afterwards
+  void set_step(int g, int64_t t);
   // Gradient sources for the fused pack.  Returns true if the device table was re-uploaded.
   bool set_pack(int g, const std::vector<int64_t>& src_ptrs, const std::vector<int64_t>& dst_off_bytes,
                 const std::vector<int64_t>& nbytes, const std::vector<int64_t>& flags);
   bool set_hyper(int g, const std::vector<int64_t>& ends, const std::vector<double>& lr,
                  const std::vector<double>& wd, const std::vector<double>& mom,
-                 const std::vector<double>& damp, const std::vector<int64_t>& nesterov);
+                 const std::vector<double>& damp, const std::vector<int64_t>& nesterov,
+                 const std::vector<int64_t>& opt, const std::vector<double>& beta2, const std::vector<double>& eps);
 
   void reduce_scatter(int g, bool pack);
   void allgather_update(int g, bool do_update, bool first_step, bool entry_barrier, bool zero_grad);
@@ -138,7 +141,8 @@ class BucketSet {
     int64_t padded = 0;
     int64_t shard = 0;
     size_t param_off = 0, grad_off = 0;
-    torch::Tensor grad_shard, mom, master;
+    torch::Tensor grad_shard, mom, master, var;
+    bool adam = false;
     std::vector<PackSeg> pack_host;
     std::vector<HyperSeg> hyper_host;
     uint32_t ntiles = 0;

@@ -15,6 +15,7 @@
 #pragma once
 #include <cstdint>
 #include <cstddef>
+#include <cmath>
 
 #if defined(__CUDACC__)
 #define DEAR_HD __host__ __device__ __forceinline__
@@ -81,15 +82,18 @@ struct PackSeg {
 };
 constexpr uint32_t SEG_ZERO_FILL = 1u;
 
-// Contiguous element range of a bucket sharing one set of SGD hyper-parameters.
+// Contiguous element range of a bucket sharing one set of optimizer hyper-parameters.
+enum OptKind : uint32_t { OPT_SGD = 0, OPT_ADAM = 1 /* L2 in the gradient */, OPT_ADAMW = 2 /* decoupled decay */ };
 struct HyperSeg {
   uint64_t end;           // exclusive end (element offset within the bucket)
   float lr;
   float weight_decay;
-  float momentum;
+  float momentum;         // SGD momentum, or Adam beta1
   float dampening;
   uint32_t nesterov;
-  uint32_t reserved;
+  uint32_t opt;           // OptKind
+  float beta2;            // Adam only
+  float eps;              // Adam only
 };
 
 // ---- per-element math shared by the CUDA kernels and the host emulation ----
@@ -107,6 +111,22 @@ DEAR_HD float sgd_update(float p, float g, float& mom, const HyperSeg& h, bool f
     g = h.nesterov ? (g + h.momentum * buf) : buf;
   }
   return p - h.lr * g;
+}
+
+// torch.optim.Adam / AdamW semantics (non-amsgrad): exp_avg `m`, exp_avg_sq `v`, bias corrections
+// bc1 = 1 - beta1^t, bc2 = 1 - beta2^t.  This extends the reference, whose DeAR path is SGD-only
+// (dear/dear_dopt.py:310-336; its BERT driver had to drop AdamW, dear/bert_benchmark.py:118-122).
+DEAR_HD float adam_update(float p, float g, float& m, float& v, const HyperSeg& h, float bc1, float sqrt_bc2) {
+  if (h.opt == OPT_ADAM && h.weight_decay != 0.f) g = g + h.weight_decay * p;
+  m = h.momentum * m + (1.f - h.momentum) * g;
+  v = h.beta2 * v + (1.f - h.beta2) * g * g;
+#if defined(__CUDA_ARCH__)
+  const float denom = sqrtf(v) / sqrt_bc2 + h.eps;
+#else
+  const float denom = std::sqrt(v) / sqrt_bc2 + h.eps;
+#endif
+  if (h.opt == OPT_ADAMW) p = p * (1.f - h.lr * h.weight_decay);
+  return p - (h.lr / bc1) * (m / denom);
 }
 
 // Index of the hyper segment containing element `e` (segments sorted by end).
@@ -159,7 +179,10 @@ struct AGParams {
   PeerTable param;         // every rank's parameter bucket base
   void* mc_param;          // NVLS multicast alias (or nullptr)
   const float* grad_shard; // local fp32 averaged gradient shard
-  float* mom_shard;        // local fp32 momentum shard (nullptr if no momentum)
+  float* mom_shard;        // local fp32 momentum / Adam exp_avg shard (nullptr if unused)
+  float* var_shard;        // local fp32 Adam exp_avg_sq shard (nullptr for SGD)
+  uint32_t* step_ctr;      // device-resident count of applied updates (Adam bias correction; graph-safe)
+  uint32_t adam;           // 1 => every hyper segment is Adam/AdamW
   float* master_shard;     // local fp32 master shard (nullptr => param bucket is fp32 master)
   void* zero_grad;         // local gradient bucket to zero after use (nullptr => skip)
   uint64_t zero_bytes;

@@ -10,6 +10,7 @@
 #include <c10/util/Half.h>
 
 #include <chrono>
+#include <cmath>
 #include <cstring>
 #include <thread>
 
@@ -103,13 +104,21 @@ void ag_impl(const AGParams& p) {
   }
   const uint64_t off = uint64_t(p.rank) * p.shard_elems;
   const bool has_mom = p.mom_shard != nullptr;
+  const bool adam = p.adam && p.do_update;
+  const uint32_t t_step = (adam && p.step_ctr) ? *p.step_ctr + 1 : 1;
   for (uint64_t i = 0; i < p.shard_elems; ++i) {
     float pv = p.master_shard ? p.master_shard[i] : ld<T>(p.param.ptr[p.rank], off + i);
     if (p.do_update) {
       const HyperSeg& h = p.hyper[p.nhyper == 1 ? 0 : find_hyper(p.hyper, p.nhyper, off + i)];
-      float mv = (has_mom && !p.first_step) ? p.mom_shard[i] : 0.f;
-      pv = sgd_update(pv, p.grad_shard[i], mv, h, p.first_step != 0, has_mom);
-      if (has_mom && h.momentum > 0.f) p.mom_shard[i] = mv;
+      if (adam) {
+        const float bc1 = 1.f - std::pow(h.momentum, float(t_step));
+        const float sqrt_bc2 = std::sqrt(1.f - std::pow(h.beta2, float(t_step)));
+        pv = adam_update(pv, p.grad_shard[i], p.mom_shard[i], p.var_shard[i], h, bc1, sqrt_bc2);
+      } else {
+        float mv = (has_mom && !p.first_step) ? p.mom_shard[i] : 0.f;
+        pv = sgd_update(pv, p.grad_shard[i], mv, h, p.first_step != 0, has_mom);
+        if (has_mom && h.momentum > 0.f) p.mom_shard[i] = mv;
+      }
       if (p.master_shard) p.master_shard[i] = pv;
     }
     for (int k = 0; k < p.world; ++k) st<T>(p.param.ptr[(p.rank + k) % p.world], off + i, pv);
@@ -118,6 +127,7 @@ void ag_impl(const AGParams& p) {
   signal_all(p.sig, ch_pushed, p.rank, p.world, e);
   wait_all(sig_local, ch_pushed, e, p.world, p.timeout_ns, p.status, ST_TIMEOUT_AG_PUSHED);
   *epoch_p = e;
+  if (p.do_update && p.step_ctr) *p.step_ctr = *p.step_ctr + 1;
 }
 
 template <typename T>

@@ -433,12 +433,12 @@ __device__ __forceinline__ void st_f32x(float* base, uint64_t v, int ev, const f
   if (ev == 8) m[1] = make_float4(in[4], in[5], in[6], in[7]);
 }
 
-template <typename T, int W, bool MC>
+template <typename T, int W, bool MC, bool ADAM>
 __global__ void __launch_bounds__(kThreads, 1) ag_kernel(const AGParams p) {
   using Tr = ElemTraits<T>;
   constexpr int EV = Tr::kPerVec;
   constexpr int EVA = 8;                        // register array length (>= EV)
-  constexpr int U = (EV == 4) ? 4 : 2;          // vectors in flight per thread
+  constexpr int U = ADAM ? ((EV == 4) ? 2 : 1) : ((EV == 4) ? 4 : 2);   // vectors in flight per thread
   __shared__ HyperSeg s_hyper[kMaxSmemHyper];
 
   const int tid = threadIdx.x;
@@ -472,9 +472,12 @@ __global__ void __launch_bounds__(kThreads, 1) ag_kernel(const AGParams p) {
     const uint64_t gstride = uint64_t(gridDim.x) * kThreads;
     const char* local_param = reinterpret_cast<const char*>(p.param.ptr[p.rank]);
     const bool has_mom = p.mom_shard != nullptr;
-    const bool load_mom = has_mom && !p.first_step && p.do_update;
+    const bool load_mom = has_mom && (ADAM || !p.first_step) && p.do_update;
+    // Adam bias corrections come from a device-resident update counter (graph replay safe)
+    const uint32_t t_step = (ADAM && p.step_ctr != nullptr) ? *reinterpret_cast<volatile uint32_t*>(p.step_ctr) + 1 : 1;
     for (uint64_t v0 = uint64_t(blockIdx.x) * kThreads + tid; v0 < nvec; v0 += gstride * U) {
       float pv[U][EVA], gv[U][EVA], mv[U][EVA];
+      float vv[ADAM ? U : 1][EVA];
       // ---- all loads first (memory-level parallelism) ----
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -492,6 +495,7 @@ __global__ void __launch_bounds__(kThreads, 1) ag_kernel(const AGParams p) {
 #pragma unroll
             for (int k = 0; k < EV; ++k) mv[u][k] = 0.f;
           }
+          if (ADAM && p.do_update) ld_f32x(p.var_shard, v, EV, vv[ADAM ? u : 0]);
         }
       }
       // ---- update + stores ----
@@ -502,10 +506,20 @@ __global__ void __launch_bounds__(kThreads, 1) ag_kernel(const AGParams p) {
           const uint64_t ge = shard_elem_off + v * EV;     // element offset within the bucket
           if (p.do_update) {
             const HyperSeg h = hyper[p.nhyper == 1 ? 0 : find_hyper(hyper, p.nhyper, ge)];
+            if (ADAM) {
+              const float bc1 = 1.f - powf(h.momentum, float(t_step));
+              const float sqrt_bc2 = sqrtf(1.f - powf(h.beta2, float(t_step)));
 #pragma unroll
-            for (int k = 0; k < EV; ++k)
-              pv[u][k] = sgd_update(pv[u][k], gv[u][k], mv[u][k], h, p.first_step != 0, has_mom);
-            if (has_mom && h.momentum > 0.f) st_f32x(p.mom_shard, v, EV, mv[u]);
+              for (int k = 0; k < EV; ++k)
+                pv[u][k] = adam_update(pv[u][k], gv[u][k], mv[u][k], vv[ADAM ? u : 0][k], h, bc1, sqrt_bc2);
+              st_f32x(p.mom_shard, v, EV, mv[u]);
+              st_f32x(p.var_shard, v, EV, vv[ADAM ? u : 0]);
+            } else {
+#pragma unroll
+              for (int k = 0; k < EV; ++k)
+                pv[u][k] = sgd_update(pv[u][k], gv[u][k], mv[u][k], h, p.first_step != 0, has_mom);
+              if (has_mom && h.momentum > 0.f) st_f32x(p.mom_shard, v, EV, mv[u]);
+            }
             if (p.master_shard != nullptr) st_f32x(p.master_shard, v, EV, pv[u]);
           }
           const uint4 outv = Tr::pack(pv[u]);
@@ -545,6 +559,7 @@ __global__ void __launch_bounds__(kThreads, 1) ag_kernel(const AGParams p) {
     if (tid == 0) {
       *cnt_exit = 0;
       *epoch_p = e;
+      if (p.do_update && p.step_ctr != nullptr) *p.step_ctr = *p.step_ctr + 1;
     }
   }
 }
@@ -728,15 +743,21 @@ void launch_rs(const RSParams& p, int grid, cudaStream_t s) {
   check_launch("rs_kernel");
 }
 
+template <typename T, bool MC, bool ADAM>
+static void launch_ag_wa(const AGParams& p, int grid, cudaStream_t s) {
+  switch (p.world) {
+    case 1: ag_kernel<T, 1, MC, ADAM><<<grid, kThreads, 0, s>>>(p); break;
+    case 2: ag_kernel<T, 2, MC, ADAM><<<grid, kThreads, 0, s>>>(p); break;
+    case 4: ag_kernel<T, 4, MC, ADAM><<<grid, kThreads, 0, s>>>(p); break;
+    case 8: ag_kernel<T, 8, MC, ADAM><<<grid, kThreads, 0, s>>>(p); break;
+    default: ag_kernel<T, 0, MC, ADAM><<<grid, kThreads, 0, s>>>(p); break;
+  }
+}
+
 template <typename T, bool MC>
 static void launch_ag_w(const AGParams& p, int grid, cudaStream_t s) {
-  switch (p.world) {
-    case 1: ag_kernel<T, 1, MC><<<grid, kThreads, 0, s>>>(p); break;
-    case 2: ag_kernel<T, 2, MC><<<grid, kThreads, 0, s>>>(p); break;
-    case 4: ag_kernel<T, 4, MC><<<grid, kThreads, 0, s>>>(p); break;
-    case 8: ag_kernel<T, 8, MC><<<grid, kThreads, 0, s>>>(p); break;
-    default: ag_kernel<T, 0, MC><<<grid, kThreads, 0, s>>>(p); break;
-  }
+  if (p.adam && p.do_update) launch_ag_wa<T, MC, true>(p, grid, s);
+  else launch_ag_wa<T, MC, false>(p, grid, s);
 }
 
 void launch_ag(const AGParams& p, int grid, cudaStream_t s) {

@@ -286,7 +286,7 @@ PeerTable SymmArena::sig_table() const {
 }
 
 void SymmArena::alloc_ctrl() {
-  const size_t n = sizeof(uint32_t) * 2 * kNumChannels;
+  const size_t n = sizeof(uint32_t) * 3 * kNumChannels;   // epochs | arrival counters | per-bucket update counts
   if (is_cuda()) {
     void* p = nullptr;
     DEAR_CUDA(cudaMalloc(&p, n));

@@ -28,20 +28,28 @@ from .bucket import BucketPlan
 _DT_CODE = {torch.float32: "DT_F32", torch.bfloat16: "DT_BF16", torch.float16: "DT_F16"}
 
 
+OPT_SGD, OPT_ADAM, OPT_ADAMW = 0, 1, 2
+
+
 class HyperSpec:
-    """Per-bucket SGD hyper-parameter segments: [(end_elem, lr, wd, momentum, dampening, nesterov)]."""
+    """Per-bucket hyper-parameter segments:
+    ``[(end_elem, lr, wd, momentum|beta1, dampening, nesterov, opt, beta2, eps)]`` (opt: 0 SGD, 1 Adam, 2 AdamW)."""
 
     __slots__ = ("segs",)
 
     def __init__(self, segs):
-        self.segs = tuple(segs)
+        self.segs = tuple(tuple(s) + (OPT_SGD, 0.0, 0.0)[len(s) - 6:] if len(s) < 9 else tuple(s) for s in segs)
 
     def __eq__(self, other):
         return isinstance(other, HyperSpec) and self.segs == other.segs
 
     @property
+    def is_adam(self):
+        return any(s[6] != OPT_SGD for s in self.segs)
+
+    @property
     def uses_momentum(self):
-        return any(s[3] > 0 for s in self.segs)
+        return self.is_adam or any(s[3] > 0 for s in self.segs)
 
 
 class _BackendBase:
@@ -56,6 +64,7 @@ class _BackendBase:
         self.grad_shard: List[torch.Tensor] = [None] * nb
         self.mom_shard: List[Optional[torch.Tensor]] = [None] * nb
         self.master_shard: List[Optional[torch.Tensor]] = [None] * nb
+        self.var_shard: List[Optional[torch.Tensor]] = [None] * nb       # Adam exp_avg_sq
         self.hyper: List[Optional[HyperSpec]] = [None] * nb
 
     # -- shard state ------------------------------------------------------------------
@@ -76,7 +85,16 @@ class _BackendBase:
             self.mom_shard[g] = torch.zeros(self.plan.buckets[g].shard_numel, dtype=torch.float32, device=self.device)
             self._shards_changed(g)
 
+    def ensure_var(self, g: int):
+        if self.var_shard[g] is None:
+            self.var_shard[g] = torch.zeros(self.plan.buckets[g].shard_numel, dtype=torch.float32, device=self.device)
+            self._shards_changed(g)
+
     def _shards_changed(self, g: Optional[int] = None):
+        pass
+
+    def set_step(self, t: int) -> None:
+        """Number of updates already applied (Adam bias correction); called after (re)building buckets."""
         pass
 
     def set_hyper(self, g: int, spec: HyperSpec) -> None:
@@ -131,7 +149,7 @@ class NativeBackend(_BackendBase):
         for i in (range(len(self.where)) if g is None else (g,)):
             bs, li = self.where[i]
             if self.grad_shard[i] is not None:
-                bs.set_shards(li, self.grad_shard[i], self.mom_shard[i], self.master_shard[i])
+                bs.set_shards(li, self.grad_shard[i], self.mom_shard[i], self.master_shard[i], self.var_shard[i])
 
     def set_hyper(self, g, spec: HyperSpec):
         if self.hyper[g] == spec:
@@ -139,9 +157,16 @@ class NativeBackend(_BackendBase):
         self.hyper[g] = spec
         if spec.uses_momentum:
             self.ensure_momentum(g)
+        if spec.is_adam:
+            self.ensure_var(g)
         bs, li = self.where[g]
         bs.set_hyper(li, [s[0] for s in spec.segs], [s[1] for s in spec.segs], [s[2] for s in spec.segs],
-                     [s[3] for s in spec.segs], [s[4] for s in spec.segs], [int(s[5]) for s in spec.segs])
+                     [s[3] for s in spec.segs], [s[4] for s in spec.segs], [int(s[5]) for s in spec.segs],
+                     [int(s[6]) for s in spec.segs], [s[7] for s in spec.segs], [s[8] for s in spec.segs])
+
+    def set_step(self, t: int):
+        for i, (bs, li) in enumerate(self.where):
+            bs.set_step(li, int(t))
 
     def set_pack(self, g, src_ptrs, dst_off, nbytes, flags):
         bs, li = self.where[g]
@@ -192,6 +217,7 @@ class TorchBackend(_BackendBase):
         self._rs_out = [torch.zeros(b.shard_numel, dtype=b.dtype, device=device) for b in plan.buckets]
         self._alloc_shards()
         self._n_launch = 0
+        self._t = 0                      # updates applied so far (Adam bias correction)
         if self.cuda:
             self.stream = torch.cuda.Stream(device=device, priority=-1)
             self.ag_done = [torch.cuda.Event() for _ in plan.buckets]
@@ -207,6 +233,11 @@ class TorchBackend(_BackendBase):
         self.hyper[g] = spec
         if spec.uses_momentum:
             self.ensure_momentum(g)
+        if spec.is_adam:
+            self.ensure_var(g)
+
+    def set_step(self, t: int):
+        self._t = int(t)
 
     def set_pack(self, g, src_ptrs, dst_off, nbytes, flags):
         pass    # gradients are accumulated straight into the bucket views
@@ -235,7 +266,7 @@ class TorchBackend(_BackendBase):
         lo, hi = self.rank * b.shard_numel, (self.rank + 1) * b.shard_numel
         master = self.master_shard[g]
         start = 0
-        for (end, lr, wd, mom, damp, nesterov) in self.hyper[g].segs:
+        for (end, lr, wd, mom, damp, nesterov, opt, beta2, eps) in self.hyper[g].segs:
             a, z = max(start, lo), min(end, hi)
             start = end
             if a >= z:
@@ -243,6 +274,19 @@ class TorchBackend(_BackendBase):
             sl = slice(a - lo, z - lo)
             p = master[sl] if master is not None else self._pbuf[g][a:z]
             d = self.grad_shard[g][sl]
+            if opt != OPT_SGD:
+                t = self._t + 1
+                m, v = self.mom_shard[g][sl], self.var_shard[g][sl]
+                if opt == OPT_ADAM and wd != 0:
+                    d = d.add(p, alpha=wd)
+                m.mul_(mom).add_(d, alpha=1 - mom)
+                v.mul_(beta2).addcmul_(d, d, value=1 - beta2)
+                bc1, bc2 = 1 - mom ** t, 1 - beta2 ** t
+                if opt == OPT_ADAMW:
+                    p.mul_(1 - lr * wd)
+                p.addcdiv_(m, v.sqrt().div_(bc2 ** 0.5).add_(eps), value=-lr / bc1)
+                self._n_launch += 6
+                continue
             if wd != 0:
                 d = d.add(p, alpha=wd)
             if mom > 0:
@@ -269,6 +313,8 @@ class TorchBackend(_BackendBase):
                 dist.all_gather_into_tensor(self._pbuf[g], src, group=self.group)
             else:
                 self._pbuf[g][lo:lo + b.shard_numel].copy_(src)
+            if do_update and g == len(self.plan.buckets) - 1:
+                self._t += 1
             if self.cuda:
                 self.ag_done[g].record(self.stream)
                 self._pending[g] = True

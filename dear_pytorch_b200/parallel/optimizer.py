@@ -31,7 +31,7 @@ import torch
 import torch.nn as nn
 
 from .. import runtime
-from .backends import HyperSpec, NativeBackend, TorchBackend
+from .backends import OPT_ADAM, OPT_ADAMW, OPT_SGD, HyperSpec, NativeBackend, TorchBackend
 from .bucket import BucketPlan
 
 THRESHOLD = 25            # MB, reference default (dear/dear_dopt.py:43)
@@ -63,6 +63,13 @@ class DearEngine:
         self.threshold = threshold
         self.num_nearby_layers = num_nearby_layers
         self._mom_initialised = False
+        self.num_updates = 0               # parameter updates applied so far (Adam bias correction)
+        if isinstance(optimizer, torch.optim.AdamW):
+            self.opt_kind = OPT_ADAMW
+        elif isinstance(optimizer, torch.optim.Adam):
+            self.opt_kind = OPT_ADAM
+        else:
+            self.opt_kind = OPT_SGD
         self._hooks = []
         self._closed = False
         self._wt = None                    # optional wait-time recorder (variants.WaitTimeBucketing)
@@ -154,6 +161,7 @@ class DearEngine:
         be.init_master_shards()
         if carry is not None:
             self._restore_state(carry)
+        be.set_step(self.num_updates)
         nb = len(plan.buckets)
         self._n_params = [len(b.slots) for b in plan.buckets]
         self._arrived = [[False] * n for n in self._n_params]
@@ -253,22 +261,28 @@ class DearEngine:
 
     # ------------------------------------------------------------------ hyper-parameters
     def _refresh_hyper(self):
-        groups = self.opt.param_groups
-        key_all = tuple((g["lr"], g.get("weight_decay", 0.0), g.get("momentum", 0.0), g.get("dampening", 0.0),
-                         bool(g.get("nesterov", False))) for g in groups)
+        key_all = self._hyper_key_now()
         for b in self.plan.buckets:
             if self._hyper_key[b.index] == key_all:
                 continue
             segs = []
             for end, gi in self.plan.hyper_segments(b.index, self.group_of):
-                lr, wd, mom, damp, nest = key_all[gi]
-                segs.append((int(end), float(lr), float(wd), float(mom), float(damp), bool(nest)))
+                segs.append((int(end),) + key_all[gi])
             self.backend.set_hyper(b.index, HyperSpec(segs))
             self._hyper_key[b.index] = key_all
 
     def _hyper_key_now(self):
-        return tuple((g["lr"], g.get("weight_decay", 0.0), g.get("momentum", 0.0), g.get("dampening", 0.0),
-                      bool(g.get("nesterov", False))) for g in self.opt.param_groups)
+        """Per param group: (lr, wd, momentum|beta1, dampening, nesterov, opt, beta2, eps)."""
+        keys = []
+        for g in self.opt.param_groups:
+            if self.opt_kind == OPT_SGD:
+                keys.append((float(g["lr"]), float(g.get("weight_decay", 0.0)), float(g.get("momentum", 0.0)),
+                             float(g.get("dampening", 0.0)), bool(g.get("nesterov", False)), OPT_SGD, 0.0, 0.0))
+            else:
+                b1, b2 = g["betas"]
+                keys.append((float(g["lr"]), float(g.get("weight_decay", 0.0)), float(b1), 0.0, False, self.opt_kind,
+                             float(b2), float(g["eps"])))
+        return tuple(keys)
 
     def hyper_changed(self) -> bool:
         key = self._hyper_key_now()
@@ -295,6 +309,7 @@ class DearEngine:
                 self._pending[g] = True
             self._any_pending = True
             self._mom_initialised = True
+            self.num_updates += 1
         else:
             # time-breakdown mode (no all-gather): peers may still be pulling from this rank's
             # gradient buckets, so rendezvous on the device before the next backward reuses them
@@ -345,10 +360,11 @@ class DearEngine:
     def _gather_state(self) -> dict:
         """Full (un-sharded) optimizer state per parameter name: momentum and fp32 master."""
         from ..utils.checkpoint import gather_sharded
-        out = {"momentum": {}, "master": {}, "mom_init": self._mom_initialised}
+        out = {"momentum": {}, "master": {}, "var": {}, "mom_init": self._mom_initialised, "num_updates": self.num_updates}
         for b in self.plan.buckets:
             g = b.index
-            for kind, shard in (("momentum", self.backend.mom_shard[g]), ("master", self.backend.master_shard[g])):
+            for kind, shard in (("momentum", self.backend.mom_shard[g]), ("master", self.backend.master_shard[g]),
+                                ("var", self.backend.var_shard[g])):
                 if shard is None:
                     continue
                 full = gather_sharded(shard, self.world)
@@ -360,16 +376,20 @@ class DearEngine:
     def _restore_state(self, carry: dict):
         be = self.backend
         self._mom_initialised = bool(carry.get("mom_init", False))
+        self.num_updates = int(carry.get("num_updates", self.num_updates))
         for b in self.plan.buckets:
             g = b.index
             lo, hi = self.rank * b.shard_numel, (self.rank + 1) * b.shard_numel
-            for kind in ("momentum", "master"):
+            for kind in ("momentum", "master", "var"):
                 vals = carry.get(kind, {})
                 if not any(s.name in vals for s in b.slots):
                     continue
                 if kind == "momentum":
                     be.ensure_momentum(g)
                     shard = be.mom_shard[g]
+                elif kind == "var":
+                    be.ensure_var(g)
+                    shard = be.var_shard[g]
                 else:
                     shard = be.master_shard[g]
                     if shard is None:
@@ -413,12 +433,14 @@ class _DistributedOptimizer(torch.optim.Optimizer):
     def __init__(self, params, model, threshold=THRESHOLD, num_nearby_layers=NUM_NEARBY_LAYERS,
                  exclude_parts="", policy=None, verbose=True):
         super(self.__class__, self).__init__(params)
-        if not isinstance(self, torch.optim.SGD):
+        if not isinstance(self, (torch.optim.SGD, torch.optim.Adam, torch.optim.AdamW)):
             raise TypeError(
-                "the decoupled all-reduce fuses the SGD update (momentum / dampening / nesterov / "
-                "weight decay) into the all-gather; got %s. Use torch.optim.SGD (as the reference does, "
-                "dear/dear_dopt.py:310-336) or parallel.baselines for other optimizers."
-                % type(self).__mro__[1].__name__)
+                "the decoupled all-reduce fuses the parameter update into the all-gather kernel; supported: "
+                "torch.optim.SGD (the reference's only DeAR optimizer, dear/dear_dopt.py:310-336), Adam and AdamW; "
+                "got %s. Use parallel.baselines for other optimizers." % type(self).__mro__[1].__name__)
+        for g in self.param_groups:
+            if g.get("amsgrad", False) or g.get("capturable", False) or g.get("differentiable", False):
+                raise ValueError("amsgrad / capturable / differentiable Adam variants are not supported")
         for g in self.param_groups:
             if g.get("maximize", False):
                 raise ValueError("maximize=True is not supported")

@@ -53,7 +53,12 @@ def optimizer_state_dict(optimizer) -> dict:
     state = {}
     for s in eng.plan.slots:
         ent = {}
-        if s.name in carry["momentum"] and carry["mom_init"]:
+        if eng.opt_kind != 0:              # Adam / AdamW: torch.optim.Adam state layout
+            if s.name in carry["momentum"]:
+                ent["step"] = torch.tensor(float(carry["num_updates"]))
+                ent["exp_avg"] = carry["momentum"][s.name].reshape(s.param.shape).clone()
+                ent["exp_avg_sq"] = carry["var"][s.name].reshape(s.param.shape).clone()
+        elif s.name in carry["momentum"] and carry["mom_init"]:
             ent["momentum_buffer"] = carry["momentum"][s.name].reshape(s.param.shape).clone()
         if s.name in carry["master"]:
             ent["master_param"] = carry["master"][s.name].reshape(s.param.shape).clone()
@@ -65,7 +70,8 @@ def optimizer_state_dict(optimizer) -> dict:
         d["params"] = [index[p] for p in g["params"]]
         groups.append(d)
     return {"state": state, "param_groups": groups,
-            "dear": {"num_steps": eng.num_steps, "policy": eng.plan.policy, "world": eng.world}}
+            "dear": {"num_steps": eng.num_steps, "num_updates": eng.num_updates, "policy": eng.plan.policy,
+                     "world": eng.world}}
 
 
 @torch.no_grad()
@@ -78,7 +84,9 @@ def load_optimizer_state_dict(optimizer, sd: dict) -> None:
             if k != "params":
                 g[k] = v
     index = _param_index(optimizer)
-    carry = {"momentum": {}, "master": {}, "mom_init": False}
+    meta = sd.get("dear") or {}
+    carry = {"momentum": {}, "master": {}, "var": {}, "mom_init": False,
+             "num_updates": int(meta.get("num_updates", eng.num_updates))}
     for s in eng.plan.slots:
         ent = sd["state"].get(index[s.param])
         if ent is None:
@@ -89,12 +97,16 @@ def load_optimizer_state_dict(optimizer, sd: dict) -> None:
         if mb is not None:
             carry["momentum"][s.name] = mb.to(eng.device, torch.float32).reshape(-1)
             carry["mom_init"] = True
+        if ent.get("exp_avg") is not None:
+            carry["momentum"][s.name] = ent["exp_avg"].to(eng.device, torch.float32).reshape(-1)
+            carry["var"][s.name] = ent["exp_avg_sq"].to(eng.device, torch.float32).reshape(-1)
+            carry["num_updates"] = int(float(ent.get("step", carry["num_updates"])))
         mp = ent.get("master_param")
         if mp is not None:
             carry["master"][s.name] = mp.to(eng.device, torch.float32).reshape(-1)
     eng._restore_state(carry)
+    eng.backend.set_step(eng.num_updates)
     eng._hyper_key = [None] * len(eng._hyper_key)
-    meta = sd.get("dear") or {}
     eng.num_steps = int(meta.get("num_steps", eng.num_steps))
 
 

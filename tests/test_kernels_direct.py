@@ -113,3 +113,84 @@ def test_cuda_kernels_match_reference(world, dtype_name):
     outs = run_ranks(kernel_worker, world=world, backend="b200", args=(True, dtype_name, 5),
                      extra_env={"DEAR_SPIN_TIMEOUT_S": "15"}, timeout=300)
     assert all(o == outs[0] for o in outs)
+
+
+def adam_worker(rank, world, use_cuda, dtype_name, seed):
+    """Kernel B with the Adam / AdamW epilogue against torch.optim.Adam(W) on the averaged gradient."""
+    import dear_pytorch_b200 as dear
+    from dear_pytorch_b200 import ops
+    C = ops.require_native()
+    comm = dear.communicator()
+    dev = dear.device()
+    tdt = torch.float32 if dtype_name == "fp32" else torch.bfloat16
+    es = 4 if dtype_name == "fp32" else 2
+    numels = [513, 4099, 70001]
+    align = 256 // es
+    starts, off = [], 0
+    for n in numels:
+        off = (off + align - 1) // align * align
+        starts.append(off)
+        off += n
+    quantum = world * (128 // es)
+    padded = (off + quantum - 1) // quantum * quantum
+    shard = padded // world
+    bs = C.BucketSet(comm, [padded], C.DT_F32 if dtype_name == "fp32" else C.DT_BF16, True)
+    pbuf = bs.param_buffer(0)
+    g = torch.Generator().manual_seed(seed)
+    full_p = torch.zeros(padded)
+    for s, n in zip(starts, numels):
+        full_p[s:s + n] = torch.randn(n, generator=g)
+    pbuf.copy_(full_p.to(tdt))
+    full_p = pbuf.float().cpu().clone()
+    gs = torch.zeros(shard, device=dev)
+    m = torch.zeros(shard, device=dev)
+    v = torch.zeros(shard, device=dev)
+    master = pbuf[rank * shard:(rank + 1) * shard].float().clone() if dtype_name != "fp32" else None
+    bs.set_shards(0, gs, m, master, v)
+    bs.set_step(0, 0)
+    # params 0-1: Adam with L2 weight decay; param 2: AdamW
+    hyp = [(starts[2], 1e-2, 1e-2, 0.9, 0.999, 1e-8, C.OPT_ADAM), (padded, 5e-3, 5e-2, 0.8, 0.95, 1e-6, C.OPT_ADAMW)]
+    bs.set_hyper(0, [h[0] for h in hyp], [h[1] for h in hyp], [h[2] for h in hyp], [h[3] for h in hyp],
+                 [0.0] * len(hyp), [0] * len(hyp), opt=[h[6] for h in hyp], beta2=[h[4] for h in hyp], eps=[h[5] for h in hyp])
+    ref_params = [torch.nn.Parameter(full_p[s:s + n].clone()) for s, n in zip(starts, numels)]
+    ref_opts = [torch.optim.Adam(ref_params[:2], lr=1e-2, weight_decay=1e-2, betas=(0.9, 0.999), eps=1e-8),
+                torch.optim.AdamW(ref_params[2:], lr=5e-3, weight_decay=5e-2, betas=(0.8, 0.95), eps=1e-6)]
+    out = []
+    for step in range(4):
+        gen = torch.Generator().manual_seed(1000 * step + 11)
+        all_rank_grads = [[torch.randn(n, generator=gen).to(tdt) for n in numels] for _ in range(world)]
+        mine = [t.to(dev) for t in all_rank_grads[rank]]
+        bs.set_pack(0, [t.data_ptr() for t in mine], [s * es for s in starts], [n * es for n in numels], [0] * len(numels))
+        bs.reduce_scatter(0, True)
+        bs.allgather_update(0, True, step == 0, True, False)
+        bs.synchronize()
+        comm.check_status()
+        for i, p in enumerate(ref_params):
+            p.grad = sum(all_rank_grads[r][i].float() for r in range(world)) / world
+        for o in ref_opts:
+            o.step()
+        got = pbuf.float().cpu()
+        for i, (s, n) in enumerate(zip(starts, numels)):
+            want = ref_params[i].detach()
+            if dtype_name == "fp32":
+                torch.testing.assert_close(got[s:s + n], want, rtol=2e-5, atol=2e-6)
+            else:
+                torch.testing.assert_close(got[s:s + n], want.to(torch.bfloat16).float(), rtol=8e-3, atol=1e-5)
+        out.append(float(got.abs().sum()))
+    return out
+
+
+@pytest.mark.parametrize("dtype_name", ["fp32", "bf16"])
+@pytest.mark.parametrize("world", [1, 3])
+def test_emulated_adam_kernel(world, dtype_name):
+    outs = run_ranks(adam_worker, world=world, backend="emu", args=(False, dtype_name, 9))
+    assert all(o == outs[0] for o in outs)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype_name", ["fp32", "bf16"])
+@pytest.mark.parametrize("world", [1, 2])
+def test_cuda_adam_kernel(world, dtype_name):
+    outs = run_ranks(adam_worker, world=world, backend="b200", args=(True, dtype_name, 9),
+                     extra_env={"DEAR_SPIN_TIMEOUT_S": "15"}, timeout=300)
+    assert all(o == outs[0] for o in outs)
