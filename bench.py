@@ -42,6 +42,10 @@ def parse_args(argv=None):
                     help="replay the whole iteration as one CUDA graph (GPU only; validated at 1/2/8 GPUs)")
     ap.add_argument("--fused-bn", type=int, default=int(os.environ.get("DEAR_BENCH_FUSED_BN", "1")),
                     help="ResNets: fused channels-last BatchNorm(+add)+ReLU kernels (csrc/bn_act.cu)")
+    ap.add_argument("--fused-ln", type=int, default=int(os.environ.get("DEAR_BENCH_FUSED_LN", "1")),
+                    help="BERT: dropout + add + LayerNorm in one kernel (csrc/ln_fused.cu)")
+    ap.add_argument("--tc-ffn", type=int, default=int(os.environ.get("DEAR_BENCH_TC_FFN", "1")),
+                    help="BERT bf16: feed-forward block on the tcgen05 GEMMs with fused GELU epilogues (csrc/tc_gemm*.cu)")
     ap.add_argument("--threshold", type=float, default=25.0)
     ap.add_argument("--momentum", type=float, default=0.0)
     ap.add_argument("--optimizer", choices=["sgd", "adam", "adamw"], default="sgd",
@@ -94,7 +98,9 @@ class Workload:
         B = args.batch_size
         if self.is_bert:
             from dear_pytorch_b200.models import bert as bm
-            model = create(args.model).to(device)
+            self.fused_ln = bool(args.fused_ln) and cuda
+            self.tc_ffn = bool(args.tc_ffn) and cuda and args.dtype == "bf16"
+            model = create(args.model, fused_ln=self.fused_ln, tc_ffn=self.tc_ffn).to(device)
             if args.dtype == "bf16":
                 model = model.to(torch.bfloat16)
             crit = bm.BertPretrainingCriterion(model.vocab_size)
@@ -187,7 +193,10 @@ def run_dear(args):
         """kernels of THIS repo launched so far: fused RS / SGD+AG / general collectives + fused BN"""
         n = comm.launches() if comm is not None else opt.engine.backend.launches()
         C = _ops.native()
-        return n + (C.bn_act_launches() if C is not None else 0)
+        if C is not None:
+            n += C.bn_act_launches() + C.ln_launches()
+        from dear_pytorch_b200.ops.tc_gemm import tc_launches
+        return n + tc_launches()
 
     l_warm = n_launches()
     # W untimed warm-up steps.  In graph mode the capture (3 eager iterations + 1 capturing call) must
@@ -267,7 +276,7 @@ def run_dear(args):
                "params": n_params, "backend": dear.backend(), "cuda_graph": bool(args.graph),
                "l2": "no explicit flush: each step streams activations+weights far larger than the 126 MB L2"}
         if wl.is_bert:
-            cfg["seq_len"] = args.sentence_len
+            cfg.update(seq_len=args.sentence_len, fused_dropout_add_ln=wl.fused_ln, tcgen05_ffn=wl.tc_ffn)
         else:
             cfg.update(image=wl.image, channels_last=bool(args.channels_last), fused_bn_relu=getattr(wl, "fused_bn", False))
         out = {

@@ -24,6 +24,15 @@ std::vector<torch::Tensor> bn_act_backward(const torch::Tensor& dy, const torch:
                                            const torch::Tensor& scale, const torch::Tensor& shift, bool relu, bool has_residual);
 } }
 
+namespace dear { namespace ln {
+bool ln_supported(const torch::Tensor& x);
+int64_t ln_launches();
+std::vector<torch::Tensor> ln_forward(const torch::Tensor& a, const torch::Tensor& residual, const torch::Tensor& gamma,
+                                      const torch::Tensor& beta, double p, bool training, double eps);
+std::vector<torch::Tensor> ln_backward(const torch::Tensor& dy, const torch::Tensor& s, const torch::Tensor& mean,
+                                       const torch::Tensor& rstd, const torch::Tensor& gamma, const torch::Tensor& mask, double p);
+} }
+
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "B200-native DeAR communication runtime (fused reduce-scatter / SGD+all-gather kernels)";
 
@@ -109,6 +118,13 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("running_mean"), py::arg("running_var"), py::arg("training"), py::arg("momentum"), py::arg("eps"),
         py::arg("relu"));
   m.def("bn_act_backward", &dear::bn::bn_act_backward);
+
+  // fused dropout + residual add + LayerNorm
+  m.def("ln_supported", &dear::ln::ln_supported);
+  m.def("ln_launches", &dear::ln::ln_launches);
+  m.def("ln_forward", &dear::ln::ln_forward, py::arg("a"), py::arg("residual"), py::arg("weight"), py::arg("bias"),
+        py::arg("p"), py::arg("training"), py::arg("eps"));
+  m.def("ln_backward", &dear::ln::ln_backward);
 
   m.attr("OPT_SGD") = static_cast<int>(OPT_SGD);
   m.attr("OPT_ADAM") = static_cast<int>(OPT_ADAM);

@@ -16,6 +16,9 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from ..ops.fused_ln import FusedDropoutAddLayerNorm
+from ..ops.tc_gemm import fused_ffn
+
 
 @dataclass
 class BertConfig:
@@ -77,28 +80,44 @@ class BertSelfAttention(nn.Module):
 
 
 class BertLayer(nn.Module):
-    def __init__(self, c: BertConfig):
+    """Post-LN transformer layer.  ``fused_ln``: dropout + add + LayerNorm in one kernel
+    (ops/fused_ln.py); ``tc_ffn``: feed-forward block on the tcgen05 GEMMs with GELU / GELU' in the
+    epilogues (ops/tc_gemm.py).  Parameters and state-dict keys are identical in every mode."""
+
+    def __init__(self, c: BertConfig, fused_ln: bool = False, tc_ffn: bool = False):
         super().__init__()
         self.attention = BertSelfAttention(c)
         self.attn_out = nn.Linear(c.hidden_size, c.hidden_size)
-        self.attn_norm = nn.LayerNorm(c.hidden_size, eps=c.layer_norm_eps)
         self.intermediate = nn.Linear(c.hidden_size, c.intermediate_size)
         self.output = nn.Linear(c.intermediate_size, c.hidden_size)
-        self.out_norm = nn.LayerNorm(c.hidden_size, eps=c.layer_norm_eps)
-        self.dropout = nn.Dropout(c.hidden_dropout_prob)
+        self.fused_ln, self.tc_ffn = fused_ln, tc_ffn
+        if fused_ln:
+            self.attn_norm = FusedDropoutAddLayerNorm(c.hidden_size, eps=c.layer_norm_eps, p=c.hidden_dropout_prob)
+            self.out_norm = FusedDropoutAddLayerNorm(c.hidden_size, eps=c.layer_norm_eps, p=c.hidden_dropout_prob)
+        else:
+            self.attn_norm = nn.LayerNorm(c.hidden_size, eps=c.layer_norm_eps)
+            self.out_norm = nn.LayerNorm(c.hidden_size, eps=c.layer_norm_eps)
+            self.dropout = nn.Dropout(c.hidden_dropout_prob)
+
+    def ffn(self, x):
+        if self.tc_ffn:
+            return fused_ffn(x, self.intermediate.weight, self.intermediate.bias, self.output.weight, self.output.bias)
+        return self.output(F.gelu(self.intermediate(x)))
 
     def forward(self, x, attn_bias):
-        a = self.dropout(self.attn_out(self.attention(x, attn_bias)))
-        x = self.attn_norm(x + a)
-        h = self.dropout(self.output(F.gelu(self.intermediate(x))))
-        return self.out_norm(x + h)
+        a = self.attn_out(self.attention(x, attn_bias))
+        if self.fused_ln:
+            x = self.attn_norm(a, x)
+            return self.out_norm(self.ffn(x), x)
+        x = self.attn_norm(x + self.dropout(a))
+        return self.out_norm(x + self.dropout(self.ffn(x)))
 
 
 class BertModel(nn.Module):
-    def __init__(self, c: BertConfig, vocab: int):
+    def __init__(self, c: BertConfig, vocab: int, fused_ln: bool = False, tc_ffn: bool = False):
         super().__init__()
         self.embeddings = BertEmbeddings(c, vocab)
-        self.layers = nn.ModuleList(BertLayer(c) for _ in range(c.num_hidden_layers))
+        self.layers = nn.ModuleList(BertLayer(c, fused_ln, tc_ffn) for _ in range(c.num_hidden_layers))
         self.pooler = nn.Linear(c.hidden_size, c.hidden_size)
 
     def forward(self, input_ids, token_type_ids=None, attention_mask=None, position_ids=None):
@@ -129,11 +148,12 @@ class BertPreTrainingHeads(nn.Module):
 
 
 class BertForPreTraining(nn.Module):
-    def __init__(self, config: BertConfig = BERT_LARGE, pad_vocab_to: int = 8):
+    def __init__(self, config: BertConfig = BERT_LARGE, pad_vocab_to: int = 8, fused_ln: bool = False,
+                 tc_ffn: bool = False):
         super().__init__()
         self.config = config
         self.vocab_size = config.padded_vocab(pad_vocab_to)
-        self.bert = BertModel(config, self.vocab_size)
+        self.bert = BertModel(config, self.vocab_size, fused_ln, tc_ffn)
         self.cls = BertPreTrainingHeads(config, self.vocab_size)
         self.apply(self._init)
 

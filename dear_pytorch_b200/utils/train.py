@@ -130,4 +130,5 @@ class TrainStep:
         self._graph.replay()
         if eng is not None:
             eng.num_steps += 1          # the replay ran the step; Python-side callbacks (tuner) do not run
+            eng.num_updates += 1        # mirrors the device-resident Adam step counter (checkpointing)
         return self._static_loss

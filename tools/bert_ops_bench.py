@@ -1,0 +1,138 @@
+#!/usr/bin/env python
+"""Micro-benchmark of the BERT-layer hot ops of this repo against their PyTorch-eager equivalents
+(cuBLASLt GEMMs + ATen elementwise kernels) at the benchmark's shapes (BERT-large, batch 32 x seq 64
+= 2048 tokens, hidden 1024, intermediate 4096, bf16).
+
+Every candidate is captured (x REPS) in a CUDA graph and replayed, so the numbers are device time
+per call without CPU launch overhead; timing is CUDA events around the replays after a warm-up.
+
+    python tools/bert_ops_bench.py [--tokens 2048] [--hidden 1024] [--inter 4096] [--json out.json]
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+import torch.nn.functional as F
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from dear_pytorch_b200.ops.fused_ln import dropout_add_layer_norm       # noqa: E402
+from dear_pytorch_b200.ops.tc_gemm import fused_ffn, require_tc         # noqa: E402
+
+REPS = 10
+
+
+def graph_time(fn, iters=20):
+    """us per call of fn() replayed from a CUDA graph."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            fn()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(REPS):
+            fn()
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e3 / (iters * REPS)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--tokens", type=int, default=2048)
+    ap.add_argument("--hidden", type=int, default=1024)
+    ap.add_argument("--inter", type=int, default=4096)
+    ap.add_argument("--json", default=None)
+    a = ap.parse_args()
+    dev = torch.device("cuda:0")
+    tc = require_tc()
+    M, H, I = a.tokens, a.hidden, a.inter
+    bf = torch.bfloat16
+    torch.manual_seed(0)
+    x = torch.randn(M, H, device=dev).to(bf)
+    w1 = (torch.randn(I, H, device=dev) * H ** -0.5).to(bf)
+    b1 = torch.randn(I, device=dev).to(bf)
+    w2 = (torch.randn(H, I, device=dev) * I ** -0.5).to(bf)
+    b2 = torch.randn(H, device=dev).to(bf)
+    z = torch.randn(M, I, device=dev).to(bf)
+    h = F.gelu(z)
+    dy = torch.randn(M, H, device=dev).to(bf)
+    gamma = torch.ones(H, device=dev, dtype=bf)
+    beta = torch.zeros(H, device=dev, dtype=bf)
+    flops_up = 2.0 * M * H * I
+    out = {"shape": {"tokens": M, "hidden": H, "inter": I}, "us": {}}
+    r = out["us"]
+
+    # 1. up projection + GELU (forward)
+    r["up_gelu_eager"] = graph_time(lambda: F.gelu(F.linear(x, w1, b1)))
+    r["up_gelu_tcgen05"] = graph_time(lambda: tc.ffn_up(x, w1, b1))
+    r["up_gemm_only_cublas"] = graph_time(lambda: F.linear(x, w1, b1))
+    # 2. down projection (forward)
+    r["down_eager"] = graph_time(lambda: F.linear(h, w2, b2))
+    r["down_tcgen05"] = graph_time(lambda: tc.linear_bias(h, w2, b2))
+    # 3. dgrad of the down projection + GELU backward
+    def eager_dgelu():
+        dh = dy.mm(w2)
+        return torch.ops.aten.gelu_backward(dh, z)
+    r["dgrad_dgelu_eager"] = graph_time(eager_dgelu)
+    r["dgrad_dgelu_tcgen05"] = graph_time(lambda: tc.ffn_dgelu(dy, w2, z))
+    r["dgrad_gemm_only_cublas"] = graph_time(lambda: dy.mm(w2))
+
+    # 4. whole feed-forward block, forward + backward
+    xs = x.clone().requires_grad_(True)
+    ps = [t.clone().requires_grad_(True) for t in (w1, b1, w2, b2)]
+
+    def ffn_eager():
+        y = F.linear(F.gelu(F.linear(xs, ps[0], ps[1])), ps[2], ps[3])
+        return torch.autograd.grad(y, [xs] + ps, dy)
+
+    def ffn_fused(down):
+        y = fused_ffn(xs, ps[0], ps[1], ps[2], ps[3], tc_down=down)
+        return torch.autograd.grad(y, [xs] + ps, dy)
+    r["ffn_fwd_bwd_eager"] = graph_time(ffn_eager)
+    r["ffn_fwd_bwd_tcgen05"] = graph_time(lambda: ffn_fused(True))
+    r["ffn_fwd_bwd_tcgen05_cublas_down"] = graph_time(lambda: ffn_fused(False))
+
+    # 5. dropout + add + LayerNorm, forward + backward
+    av = x.clone().requires_grad_(True)
+    rv = dy.clone().requires_grad_(True)
+    gv, bv = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+
+    def ln_eager():
+        y = F.layer_norm(rv + F.dropout(av, 0.1, True), (H,), gv, bv, 1e-12)
+        return torch.autograd.grad(y, [av, rv, gv, bv], dy)
+
+    def ln_fused():
+        y = dropout_add_layer_norm(av, rv, gv, bv, 0.1, True, 1e-12)
+        return torch.autograd.grad(y, [av, rv, gv, bv], dy)
+    r["drop_add_ln_fwd_bwd_eager"] = graph_time(ln_eager)
+    r["drop_add_ln_fwd_bwd_fused"] = graph_time(ln_fused)
+    r["drop_add_ln_fwd_eager"] = graph_time(lambda: F.layer_norm(rv.detach() + F.dropout(av.detach(), 0.1, True), (H,), gamma, beta, 1e-12))
+    r["drop_add_ln_fwd_fused"] = graph_time(lambda: dropout_add_layer_norm(av.detach(), rv.detach(), gamma, beta, 0.1, True, 1e-12))
+
+    for k in list(r):
+        r[k] = round(r[k], 2)
+    out["tflops"] = {"up_gelu_tcgen05": round(flops_up / r["up_gelu_tcgen05"] / 1e6, 1),
+                     "up_gemm_only_cublas": round(flops_up / r["up_gemm_only_cublas"] / 1e6, 1),
+                     "dgrad_dgelu_tcgen05": round(flops_up / r["dgrad_dgelu_tcgen05"] / 1e6, 1),
+                     "dgrad_gemm_only_cublas": round(flops_up / r["dgrad_gemm_only_cublas"] / 1e6, 1)}
+    print(json.dumps(out, indent=1))
+    if a.json:
+        with open(a.json, "w") as f:
+            json.dump(out, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
