@@ -23,6 +23,8 @@ def main(argv=None):
     ap.add_argument("--sentence-len", type=int, default=128)
     ap.add_argument("--lr", type=float, default=2e-5)
     ap.add_argument("--config", type=str, default=None, help="optional JSON file with BertConfig fields")
+    ap.add_argument("--fused-ln", type=int, default=1, help="dropout + add + LayerNorm in one kernel (CUDA)")
+    ap.add_argument("--tc-ffn", type=int, default=1, help="feed-forward block on the tcgen05 GEMMs (CUDA, bf16)")
     common.add_common_args(ap)
     args = ap.parse_args(argv)
     method, cuda = common.init_runtime(args)
@@ -38,7 +40,9 @@ def main(argv=None):
                                             if k in bert_models.BertConfig.__dataclass_fields__})
     else:
         cfg = bert_models.BERT_BASE if args.model == "bert_base" else bert_models.BERT_LARGE
-    model = bert_models.BertForPreTraining(cfg).to(device)      # vocabulary padded to a multiple of 8
+    model = bert_models.BertForPreTraining(cfg, fused_ln=bool(args.fused_ln) and cuda,
+                                           tc_ffn=bool(args.tc_ffn) and cuda and dtype == "bf16").to(device)
+    # (vocabulary padded to a multiple of 8)
     if dtype == "bf16":
         model = model.to(torch.bfloat16)
     criterion = bert_models.BertPretrainingCriterion(model.vocab_size)

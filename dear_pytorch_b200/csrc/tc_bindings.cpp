@@ -5,6 +5,8 @@
 #include <map>
 #include <mutex>
 
+namespace py = pybind11;
+
 namespace dear_tc {
 
 static std::atomic<long> g_launches{0};
@@ -26,16 +28,80 @@ void* workspace(size_t bytes, int device) {
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 long launches() { return g_launches.load(); }
 
-std::vector<at::Tensor> ffn_up(const at::Tensor& x, const at::Tensor& w, const at::Tensor& bias);
-at::Tensor linear_bias(const at::Tensor& x, const at::Tensor& w, const at::Tensor& bias);
-at::Tensor ffn_dgelu(const at::Tensor& dy, const at::Tensor& w, const at::Tensor& z);
+std::vector<at::Tensor> ffn_up_v0(const at::Tensor& x, const at::Tensor& w, const at::Tensor& bias);
+std::vector<at::Tensor> ffn_up_v1(const at::Tensor& x, const at::Tensor& w, const at::Tensor& bias);
+std::vector<at::Tensor> ffn_up_v2(const at::Tensor& x, const at::Tensor& w, const at::Tensor& bias);
+std::vector<at::Tensor> ffn_up_v3(const at::Tensor& x, const at::Tensor& w, const at::Tensor& bias);
+std::vector<at::Tensor> ffn_up_v4(const at::Tensor& x, const at::Tensor& w, const at::Tensor& bias);
+at::Tensor ffn_dgelu_v0(const at::Tensor& dy, const at::Tensor& w, const at::Tensor& z);
+at::Tensor ffn_dgelu_v1(const at::Tensor& dy, const at::Tensor& w, const at::Tensor& z);
+at::Tensor ffn_dgelu_v2(const at::Tensor& dy, const at::Tensor& w, const at::Tensor& z);
+at::Tensor linear_bias_v0(const at::Tensor& x, const at::Tensor& w, const at::Tensor& bias);
+at::Tensor linear_bias_v1(const at::Tensor& x, const at::Tensor& w, const at::Tensor& bias);
+at::Tensor linear_bias_v2(const at::Tensor& x, const at::Tensor& w, const at::Tensor& bias);
+at::Tensor linear_bias_v3(const at::Tensor& x, const at::Tensor& w, const at::Tensor& bias);
 
 }  // namespace dear_tc
 
+namespace {
+
+template <class Fn>
+struct Variant {
+  Fn fn;
+  const char* config;
+};
+
+using Fn3V = std::vector<at::Tensor> (*)(const at::Tensor&, const at::Tensor&, const at::Tensor&);
+using Fn3T = at::Tensor (*)(const at::Tensor&, const at::Tensor&, const at::Tensor&);
+
+const Variant<Fn3V> k_ffn_up[] = {
+    {&dear_tc::ffn_up_v0, "tile/cluster/2sm=(256, 128, 2, 1, true) scheduler=default"},
+    {&dear_tc::ffn_up_v1, "tile/cluster/2sm=(256, 256, 2, 1, true) scheduler=default"},
+    {&dear_tc::ffn_up_v2, "tile/cluster/2sm=(128, 256, 1, 1, false) scheduler=default"},
+    {&dear_tc::ffn_up_v3, "tile/cluster/2sm=(256, 256, 2, 1, true) scheduler=StreamKScheduler"},
+    {&dear_tc::ffn_up_v4, "tile/cluster/2sm=(256, 128, 2, 2, true) scheduler=default"},
+};
+const Variant<Fn3T> k_ffn_dgelu[] = {
+    {&dear_tc::ffn_dgelu_v0, "tile/cluster/2sm=(256, 128, 2, 1, true) scheduler=default"},
+    {&dear_tc::ffn_dgelu_v1, "tile/cluster/2sm=(256, 256, 2, 1, true) scheduler=default"},
+    {&dear_tc::ffn_dgelu_v2, "tile/cluster/2sm=(128, 256, 1, 1, false) scheduler=default"},
+};
+const Variant<Fn3T> k_linear_bias[] = {
+    {&dear_tc::linear_bias_v0, "tile/cluster/2sm=(256, 128, 2, 1, true) scheduler=default"},
+    {&dear_tc::linear_bias_v1, "tile/cluster/2sm=(256, 256, 2, 1, true) scheduler=default"},
+    {&dear_tc::linear_bias_v2, "tile/cluster/2sm=(128, 128, 1, 1, false) scheduler=default"},
+    {&dear_tc::linear_bias_v3, "tile/cluster/2sm=(256, 128, 2, 1, true) scheduler=StreamKScheduler"},
+};
+
+template <class V, size_t N>
+const V& pick(const V (&table)[N], int variant, const char* op) {
+  TORCH_CHECK(variant >= 0 && variant < static_cast<int>(N), op, ": variant ", variant, " out of range [0, ", N, ")");
+  return table[variant];
+}
+
+template <class V, size_t N>
+std::vector<std::string> configs(const V (&table)[N]) {
+  std::vector<std::string> out;
+  for (const auto& v : table) out.emplace_back(v.config);
+  return out;
+}
+
+}  // namespace
+
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "tcgen05/TMEM/TMA GEMMs with fused bias / GELU / dGELU epilogues (sm_100a)";
-  m.def("ffn_up", &dear_tc::ffn_up, "H, Z = gelu(X W^T + b), X W^T + b");
-  m.def("linear_bias", &dear_tc::linear_bias, "Y = X W^T + b");
-  m.def("ffn_dgelu", &dear_tc::ffn_dgelu, "dZ = (dY W) * gelu'(Z)");
+  m.def("ffn_up", [](const at::Tensor& x, const at::Tensor& w, const at::Tensor& b, int variant) {
+    return pick(k_ffn_up, variant, "ffn_up").fn(x, w, b); }, py::arg("x"), py::arg("w"), py::arg("bias"), py::arg("variant") = 0,
+    "H, Z = gelu(X W^T + b), X W^T + b");
+  m.def("linear_bias", [](const at::Tensor& x, const at::Tensor& w, const at::Tensor& b, int variant) {
+    return pick(k_linear_bias, variant, "linear_bias").fn(x, w, b); }, py::arg("x"), py::arg("w"), py::arg("bias"), py::arg("variant") = 0,
+    "Y = X W^T + b");
+  m.def("ffn_dgelu", [](const at::Tensor& dy, const at::Tensor& w, const at::Tensor& z, int variant) {
+    return pick(k_ffn_dgelu, variant, "ffn_dgelu").fn(dy, w, z); }, py::arg("dy"), py::arg("w"), py::arg("z"), py::arg("variant") = 0,
+    "dZ = (dY W) * gelu'(Z)");
+  m.def("variants", []() {
+    return std::map<std::string, std::vector<std::string>>{
+        {"ffn_up", configs(k_ffn_up)}, {"linear_bias", configs(k_linear_bias)}, {"ffn_dgelu", configs(k_ffn_dgelu)}}; },
+    "kernel configurations compiled for each op (index = `variant`)");
   m.def("launches", &dear_tc::launches);
 }

@@ -38,12 +38,40 @@ namespace dear_tc {
 using namespace cute;
 
 // ---- activation functors (erf GELU, as torch.nn.functional.gelu default) -------------------------
+// The epilogue runs on 4 warps per CTA while one thread feeds the tensor core, so a 128x128 tile must
+// cost fewer epilogue instructions than its mainloop takes cycles (~4096 for K=1024) or the epilogue,
+// not the MMA, bounds the kernel: libm's erff() (~40 instructions + a branch) does not fit, the
+// Abramowitz-Stegun 7.1.26 form below (2 MUFU + ~12 FMA, |error| <= 1.5e-7, far below bf16
+// resolution) does.  Phi(-|x|) = 0.5 * erfc(|x|/sqrt2) is evaluated directly, so the negative tail
+// has no cancellation.
+struct NormalTail {
+  float q;      // Phi(-|x|)
+  float e;      // exp(-x^2 / 2)
+};
+CUTLASS_HOST_DEVICE NormalTail normal_tail(float x) {
+  const float ax = fabsf(x);
+#if defined(__CUDA_ARCH__)
+  const float e = __expf(-0.5f * x * x);
+  const float t = __fdividef(1.0f, fmaf(0.3275911f * 0.70710678118654752440f, ax, 1.0f));
+#else
+  const float e = expf(-0.5f * x * x);
+  const float t = 1.0f / (1.0f + 0.3275911f * 0.70710678118654752440f * ax);
+#endif
+  float p = 1.061405429f;
+  p = fmaf(p, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  return {0.5f * p * t * e, e};
+}
+
 template <class T>
 struct GeluErf {
   static const bool kIsHeavy = true;
   CUTLASS_HOST_DEVICE T operator()(T const& v) const {
-    float x = static_cast<float>(v);
-    return T(0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)));
+    const float x = static_cast<float>(v);
+    const float q = normal_tail(x).q;
+    return T(x * (x < 0.f ? q : 1.0f - q));
   }
 };
 template <class T, int N>
@@ -58,15 +86,15 @@ struct GeluErf<cutlass::Array<T, N>> {
   }
 };
 
-// d/dz [ z * Phi(z) ] = Phi(z) + z * phi(z); called as f(dY, Z)
+// d/dz [ z * Phi(z) ] = Phi(z) + z * phi(z); called as f(dY, Z).  phi(z) shares exp(-z^2/2) with the tail.
 template <class T>
 struct DGeluErf {
   static const bool kIsHeavy = true;
   CUTLASS_HOST_DEVICE T operator()(T const& d, T const& zz) const {
-    float z = static_cast<float>(zz);
-    float cdf = 0.5f * (1.0f + erff(z * 0.70710678118654752440f));
-    float pdf = 0.39894228040143267794f * expf(-0.5f * z * z);
-    return T(static_cast<float>(d) * (cdf + z * pdf));
+    const float z = static_cast<float>(zz);
+    const NormalTail nt = normal_tail(z);
+    const float cdf = z < 0.f ? nt.q : 1.0f - nt.q;
+    return T(static_cast<float>(d) * fmaf(z, 0.39894228040143267794f * nt.e, cdf));
   }
 };
 template <class T, int N>
@@ -91,24 +119,28 @@ using bf16 = cutlass::bfloat16_t;
 using RowMajor = cutlass::layout::RowMajor;
 using ColMajor = cutlass::layout::ColumnMajor;
 
-// One GEMM flavour = (layout of B, epilogue fusion).  A is always row-major [M,K] bf16, D row-major
-// [M,N] bf16, fp32 accumulation in TMEM.  256x128x64 MMA tile on a CTA pair (cluster 2x1).
-template <class LayoutB, class FusionOp>
+// One GEMM flavour = (layout of B, epilogue fusion, MMA tile, cluster, 1- or 2-SM MMA, tile scheduler).
+// A is always row-major [M,K] bf16, D row-major [M,N] bf16, fp32 accumulation in TMEM, K tile 64
+// (one 128-byte swizzle row of bf16).  2-SM: a CTA pair shares one TM x TN tile (tcgen05.mma.cta_group::2).
+template <class LayoutB, class FusionOp, int TM = 256, int TN = 128, int CM = 2, int CN = 1, bool TwoSm = true,
+          class Scheduler = void>
 struct TcGemm {
-  using MmaTile = Shape<_256, _128, _64>;
-  using Cluster = Shape<_2, _1, _1>;
+  using MmaTile = Shape<Int<TM>, Int<TN>, _64>;
+  using Cluster = Shape<Int<CM>, Int<CN>, _1>;
   static constexpr int kAlign = 8;      // 16 bytes of bf16
+  using EpiSchedule = cute::conditional_t<TwoSm, cutlass::epilogue::TmaWarpSpecialized2Sm, cutlass::epilogue::TmaWarpSpecialized1Sm>;
+  using MainSchedule = cute::conditional_t<TwoSm, cutlass::gemm::KernelTmaWarpSpecialized2SmSm100,
+                                           cutlass::gemm::KernelTmaWarpSpecialized1SmSm100>;
   using Epilogue = typename cutlass::epilogue::collective::CollectiveBuilder<
       cutlass::arch::Sm100, cutlass::arch::OpClassTensorOp, MmaTile, Cluster,
       cutlass::epilogue::collective::EpilogueTileAuto, float, float,
-      bf16, RowMajor, kAlign, bf16, RowMajor, kAlign,
-      cutlass::epilogue::TmaWarpSpecialized2Sm, FusionOp>::CollectiveOp;
+      bf16, RowMajor, kAlign, bf16, RowMajor, kAlign, EpiSchedule, FusionOp>::CollectiveOp;
   using Mainloop = typename cutlass::gemm::collective::CollectiveBuilder<
       cutlass::arch::Sm100, cutlass::arch::OpClassTensorOp,
       bf16, RowMajor, kAlign, bf16, LayoutB, kAlign, float, MmaTile, Cluster,
       cutlass::gemm::collective::StageCountAutoCarveout<static_cast<int>(sizeof(typename Epilogue::SharedStorage))>,
-      cutlass::gemm::KernelTmaWarpSpecialized2SmSm100>::CollectiveOp;
-  using Kernel = cutlass::gemm::kernel::GemmUniversal<Shape<int, int, int, int>, Mainloop, Epilogue, void>;
+      MainSchedule>::CollectiveOp;
+  using Kernel = cutlass::gemm::kernel::GemmUniversal<Shape<int, int, int, int>, Mainloop, Epilogue, Scheduler>;
   using Gemm = cutlass::gemm::device::GemmUniversalAdapter<Kernel>;
   using StrideA = typename Kernel::StrideA;
   using StrideB = typename Kernel::StrideB;
@@ -116,6 +148,10 @@ struct TcGemm {
   using StrideD = typename Kernel::StrideD;
   using FusionArgs = decltype(std::declval<typename Epilogue::Arguments>().thread);
 };
+
+using FusionUp = cutlass::epilogue::fusion::LinCombPerColBiasEltActAux<RowMajor, GeluErf, bf16, float, bf16, bf16>;
+using FusionBias = cutlass::epilogue::fusion::LinCombPerColBiasEltAct<Ident, bf16, float, bf16>;
+using FusionDGelu = cutlass::epilogue::fusion::LinCombDeEltAct<RowMajor, DGeluErf, bf16, float, bf16>;
 
 // shared state (defined in tc_bindings.cpp)
 void* workspace(size_t bytes, int device);
@@ -158,8 +194,58 @@ inline void run(int M, int N, int K, const bf16* A, const bf16* B, bf16* D, Fusi
   count_launch();
 }
 
-std::vector<at::Tensor> ffn_up(const at::Tensor& x, const at::Tensor& w, const at::Tensor& bias);
-at::Tensor linear_bias(const at::Tensor& x, const at::Tensor& w, const at::Tensor& bias);
-at::Tensor ffn_dgelu(const at::Tensor& dy, const at::Tensor& w, const at::Tensor& z);
+// ---- the three operations, generic over the GEMM configuration ------------------------------------
+// H = gelu(Z), Z = X W^T + b.   x [M,K], w [N,K], bias [N]  ->  (H [M,N], Z [M,N])
+template <class G>
+std::vector<at::Tensor> ffn_up_impl(const at::Tensor& x, const at::Tensor& w, const at::Tensor& bias) {
+  check_operand(x, "x"); check_operand(w, "w"); check_operand(bias, "bias");
+  TORCH_CHECK(x.dim() == 2 && w.dim() == 2 && x.size(1) == w.size(1) && bias.numel() == w.size(0), "ffn_up: shape mismatch");
+  c10::cuda::CUDAGuard guard(x.device());
+  int M = x.size(0), K = x.size(1), N = w.size(0);
+  auto h = at::empty({M, N}, x.options());
+  auto z = at::empty({M, N}, x.options());
+  typename G::FusionArgs f{};
+  f.alpha = 1.0f; f.beta = 0.0f;
+  f.bias_ptr = reinterpret_cast<const bf16*>(bias.data_ptr());
+  f.aux_ptr = reinterpret_cast<bf16*>(z.data_ptr());
+  f.dAux = cutlass::make_cute_packed_stride(typename G::StrideD{}, cute::make_shape(M, N, 1));
+  run<G>(M, N, K, reinterpret_cast<const bf16*>(x.data_ptr()), reinterpret_cast<const bf16*>(w.data_ptr()),
+         reinterpret_cast<bf16*>(h.data_ptr()), f, x.get_device());
+  return {h, z};
+}
+
+// Y = X W^T + b
+template <class G>
+at::Tensor linear_bias_impl(const at::Tensor& x, const at::Tensor& w, const at::Tensor& bias) {
+  check_operand(x, "x"); check_operand(w, "w"); check_operand(bias, "bias");
+  TORCH_CHECK(x.dim() == 2 && w.dim() == 2 && x.size(1) == w.size(1) && bias.numel() == w.size(0), "linear_bias: shape mismatch");
+  c10::cuda::CUDAGuard guard(x.device());
+  int M = x.size(0), K = x.size(1), N = w.size(0);
+  auto y = at::empty({M, N}, x.options());
+  typename G::FusionArgs f{};
+  f.alpha = 1.0f; f.beta = 0.0f;
+  f.bias_ptr = reinterpret_cast<const bf16*>(bias.data_ptr());
+  run<G>(M, N, K, reinterpret_cast<const bf16*>(x.data_ptr()), reinterpret_cast<const bf16*>(w.data_ptr()),
+         reinterpret_cast<bf16*>(y.data_ptr()), f, x.get_device());
+  return y;
+}
+
+// dZ = (dY W) * gelu'(Z).   dy [M,K], w [K,N] (the down projection's weight as stored: [out=K, in=N]), z [M,N]
+template <class G>
+at::Tensor ffn_dgelu_impl(const at::Tensor& dy, const at::Tensor& w, const at::Tensor& z) {
+  check_operand(dy, "dy"); check_operand(w, "w"); check_operand(z, "z");
+  TORCH_CHECK(dy.dim() == 2 && w.dim() == 2 && z.dim() == 2 && dy.size(1) == w.size(0) && z.size(0) == dy.size(0) &&
+              z.size(1) == w.size(1), "ffn_dgelu: shape mismatch");
+  c10::cuda::CUDAGuard guard(dy.device());
+  int M = dy.size(0), K = dy.size(1), N = w.size(1);
+  auto dz = at::empty({M, N}, dy.options());
+  typename G::FusionArgs f{};
+  f.alpha = 1.0f; f.beta = 0.0f;
+  f.aux_ptr = reinterpret_cast<const bf16*>(z.data_ptr());
+  f.dAux = cutlass::make_cute_packed_stride(typename G::StrideD{}, cute::make_shape(M, N, 1));
+  run<G>(M, N, K, reinterpret_cast<const bf16*>(dy.data_ptr()), reinterpret_cast<const bf16*>(w.data_ptr()),
+         reinterpret_cast<bf16*>(dz.data_ptr()), f, dy.get_device());
+  return dz;
+}
 
 }  // namespace dear_tc

@@ -1,0 +1,12 @@
+// ffn_dgelu variant 0: MMA tile / cluster / 2-SM = (256, 128, 2, 1, true), scheduler = void
+// (one translation unit per instantiation so they compile in parallel)
+#include "tc_gemm.h"
+
+namespace dear_tc {
+
+at::Tensor ffn_dgelu_v0(const at::Tensor& dy, const at::Tensor& w, const at::Tensor& z) {
+  using G = TcGemm<RowMajor, FusionDGelu, 256, 128, 2, 1, true, void>;
+  return ffn_dgelu_impl<G>(dy, w, z);
+}
+
+}  // namespace dear_tc

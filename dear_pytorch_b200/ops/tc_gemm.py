@@ -49,6 +49,12 @@ def tc_launches() -> int:
     return int(mod.launches()) if mod is not None else 0
 
 
+# kernel configuration per op (index into ``_tc.variants()[op]``); chosen from tools/bert_ops_bench.py on a B200
+VARIANT = {"ffn_up": int(os.environ.get("DEAR_TC_UP_VARIANT", "0")),
+           "linear_bias": int(os.environ.get("DEAR_TC_DOWN_VARIANT", "0")),
+           "ffn_dgelu": int(os.environ.get("DEAR_TC_DGELU_VARIANT", "0"))}
+
+
 def _eligible(x: torch.Tensor, *ws: torch.Tensor) -> bool:
     if not (x.is_cuda and x.dtype == torch.bfloat16):
         return False
@@ -62,8 +68,8 @@ class _FusedFFN(torch.autograd.Function):
         x2 = x.reshape(-1, x.shape[-1])
         if not x2.is_contiguous():
             x2 = x2.contiguous()
-        h, z = tc.ffn_up(x2, w1, b1)
-        y = tc.linear_bias(h, w2, b2) if tc_down else torch.addmm(b2, h, w2.t())
+        h, z = tc.ffn_up(x2, w1, b1, VARIANT["ffn_up"])
+        y = tc.linear_bias(h, w2, b2, VARIANT["linear_bias"]) if tc_down else torch.addmm(b2, h, w2.t())
         ctx.save_for_backward(x2, w1, w2, h, z)
         ctx.x_shape = x.shape
         return y.view(*x.shape[:-1], w2.shape[0])
@@ -75,7 +81,7 @@ class _FusedFFN(torch.autograd.Function):
         dy2 = dy.reshape(-1, dy.shape[-1])
         if not dy2.is_contiguous():
             dy2 = dy2.contiguous()
-        dz = tc.ffn_dgelu(dy2, w2, z)                      # (dy W2) * gelu'(z), one kernel
+        dz = tc.ffn_dgelu(dy2, w2, z, VARIANT["ffn_dgelu"])                     # (dy W2) * gelu'(z), one kernel
         dw2 = dy2.t().mm(h) if ctx.needs_input_grad[3] else None
         db2 = dy2.sum(0) if ctx.needs_input_grad[4] else None
         dw1 = dz.t().mm(x2) if ctx.needs_input_grad[1] else None
@@ -97,5 +103,5 @@ def linear_bias(x, w, b):
     """``F.linear(x, w, b)`` on the tcgen05 mainloop (forward only; used by benchmarks/tests)."""
     if _eligible(x, w):
         x2 = x.reshape(-1, x.shape[-1]).contiguous()
-        return require_tc().linear_bias(x2, w, b).view(*x.shape[:-1], w.shape[0])
+        return require_tc().linear_bias(x2, w, b, VARIANT["linear_bias"]).view(*x.shape[:-1], w.shape[0])
     return F.linear(x, w, b)

@@ -5,6 +5,7 @@ Produces dear_pytorch_b200/_C.*.so (runtime, collectives, fused BN) and dear_pyt
 The reference's counterpart is common/comm_core/setup.py:16-44 (NCCL+MPI); this
 extension links neither.
 """
+import glob
 import os
 
 from setuptools import setup
@@ -49,7 +50,9 @@ def cutlass_root():
 CUTLASS = cutlass_root()
 tc_ext = CUDAExtension(
     name="dear_pytorch_b200._tc",
-    sources=[os.path.join(CSRC, f) for f in ("tc_bindings.cpp", "tc_gemm_up.cu", "tc_gemm_bias.cu", "tc_gemm_dgelu.cu")],
+    # one translation unit per (operation, tile configuration): they compile in parallel
+    sources=[os.path.join(CSRC, "tc_bindings.cpp")] + sorted(
+        os.path.relpath(f, ROOT) for f in glob.glob(os.path.join(ROOT, CSRC, "tc_gemm_*.cu"))),
     include_dirs=[os.path.join(ROOT, CSRC), os.path.join(CUTLASS, "include"), os.path.join(CUTLASS, "tools", "util", "include")],
     extra_compile_args={"cxx": CXX_FLAGS, "nvcc": NVCC_FLAGS + ["--expt-extended-lambda", "-diag-suppress", "20012"]},
 )

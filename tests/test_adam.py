@@ -82,24 +82,26 @@ def test_adam_checkpoint_resume(backend):
         assert float(next(iter(stock.state.values()))["step"]) == 3.0
 
 
+def gpu_worker(rank, world, kind, kw, steps, per_rank):
+    import dear_pytorch_b200 as dear
+    dev = dear.device()
+    model = make_model().to(dev); model.eval()
+    opt = dear.DistributedOptimizer(make_opt(kind, model.parameters(), kw), model, threshold=0.002, verbose=False)
+    dear.broadcast_parameters(model.state_dict(), 0)
+    for t in range(steps):
+        x, y = data(t, world * per_rank)
+        x, y = x[rank * per_rank:(rank + 1) * per_rank].to(dev), y[rank * per_rank:(rank + 1) * per_rank].to(dev)
+        opt.zero_grad()
+        nn.functional.cross_entropy(model(x), y).backward()
+        opt.step()
+    opt.synchronize()
+    dear.communicator().check_status()
+    return [p.detach().cpu() for p in model.parameters()]
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("world", [1, 2])
 def test_adam_on_gpu(world):
-    def gpu_worker(rank, world, kind, kw, steps, per_rank):
-        import dear_pytorch_b200 as dear
-        dev = dear.device()
-        model = make_model().to(dev); model.eval()
-        opt = dear.DistributedOptimizer(make_opt(kind, model.parameters(), kw), model, threshold=0.002, verbose=False)
-        dear.broadcast_parameters(model.state_dict(), 0)
-        for t in range(steps):
-            x, y = data(t, world * per_rank)
-            x, y = x[rank * per_rank:(rank + 1) * per_rank].to(dev), y[rank * per_rank:(rank + 1) * per_rank].to(dev)
-            opt.zero_grad()
-            nn.functional.cross_entropy(model(x), y).backward()
-            opt.step()
-        opt.synchronize()
-        dear.communicator().check_status()
-        return [p.detach().cpu() for p in model.parameters()]
     kind, kw = CASES[2]
     ref = reference(kind, kw, 5, world, 4)
     for params in run_ranks(gpu_worker, world=world, backend="b200", args=(kind, kw, 5, 4),

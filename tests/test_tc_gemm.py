@@ -14,6 +14,23 @@ def test_cpu_fallback_is_the_plain_formula():
     torch.testing.assert_close(linear_bias(x, w1, b1), F.linear(x, w1, b1))
 
 
+def test_fast_gelu_math_matches_erf():
+    """The epilogue's Abramowitz-Stegun normal tail (csrc/tc_gemm.h: normal_tail) against erf, in fp32 on the host."""
+    import math
+    x = torch.linspace(-9.0, 9.0, 20001, dtype=torch.float64)
+    ax = x.abs()
+    t = 1.0 / (1.0 + 0.3275911 * 0.7071067811865476 * ax)
+    poly = ((((1.061405429 * t - 1.453152027) * t + 1.421413741) * t - 0.284496736) * t + 0.254829592) * t
+    e = torch.exp(-0.5 * x * x)
+    q = 0.5 * poly * e
+    cdf = torch.where(x < 0, q, 1.0 - q)
+    ref = 0.5 * (1.0 + torch.erf(x / math.sqrt(2.0)))
+    assert (cdf - ref).abs().max().item() < 1e-7
+    assert (x * cdf - x * ref).abs().max().item() < 5e-7
+    dref = ref + x * torch.exp(-0.5 * x * x) / math.sqrt(2 * math.pi)
+    assert ((cdf + x * 0.3989422804014327 * e) - dref).abs().max().item() < 2e-7
+
+
 def _rand(shape, dev, scale=1.0):
     return (scale * torch.randn(shape, device=dev)).to(torch.bfloat16)
 
@@ -25,14 +42,16 @@ def test_ffn_up_and_linear_bias(M, K, N):
     dev = torch.device("cuda:0")
     torch.manual_seed(1)
     x, w, b = _rand((M, K), dev), _rand((N, K), dev, K ** -0.5), _rand((N,), dev)
-    n0 = tc_launches()
-    h, z = tc.ffn_up(x, w, b)
-    y = tc.linear_bias(x, w, b)
-    assert tc_launches() == n0 + 2
     z_ref = x.float() @ w.float().t() + b.float()
-    torch.testing.assert_close(z.float(), z_ref, rtol=1e-2, atol=1e-2)
-    torch.testing.assert_close(y.float(), z_ref, rtol=1e-2, atol=1e-2)
-    torch.testing.assert_close(h.float(), F.gelu(z_ref), rtol=1e-2, atol=1e-2)
+    n0 = tc_launches()
+    for v in range(len(tc.variants()["ffn_up"])):          # every compiled tile configuration
+        h, z = tc.ffn_up(x, w, b, v)
+        torch.testing.assert_close(z.float(), z_ref, rtol=1e-2, atol=1e-2, msg=lambda s: "ffn_up variant %d: %s" % (v, s))
+        torch.testing.assert_close(h.float(), F.gelu(z_ref), rtol=1e-2, atol=1e-2, msg=lambda s: "gelu variant %d: %s" % (v, s))
+    for v in range(len(tc.variants()["linear_bias"])):
+        y = tc.linear_bias(x, w, b, v)
+        torch.testing.assert_close(y.float(), z_ref, rtol=1e-2, atol=1e-2, msg=lambda s: "linear_bias variant %d: %s" % (v, s))
+    assert tc_launches() == n0 + len(tc.variants()["ffn_up"]) + len(tc.variants()["linear_bias"])
 
 
 @pytest.mark.gpu
@@ -42,10 +61,11 @@ def test_ffn_dgelu(M, K, N):
     dev = torch.device("cuda:0")
     torch.manual_seed(2)
     dy, w, z = _rand((M, K), dev), _rand((K, N), dev, K ** -0.5), _rand((M, N), dev)
-    dz = tc.ffn_dgelu(dy, w, z)
     z32 = z.float().requires_grad_(True)
     F.gelu(z32).backward(dy.float() @ w.float())
-    torch.testing.assert_close(dz.float(), z32.grad, rtol=1.5e-2, atol=1.5e-2)
+    for v in range(len(tc.variants()["ffn_dgelu"])):
+        dz = tc.ffn_dgelu(dy, w, z, v)
+        torch.testing.assert_close(dz.float(), z32.grad, rtol=1.5e-2, atol=1.5e-2, msg=lambda s: "variant %d: %s" % (v, s))
 
 
 @pytest.mark.gpu

@@ -25,7 +25,15 @@ REPS = 10
 
 
 def graph_time(fn, iters=20):
-    """us per call of fn() replayed from a CUDA graph."""
+    """us per call of fn() replayed from a CUDA graph (inf and a message if the candidate raises)."""
+    try:
+        return _graph_time(fn, iters)
+    except Exception as exc:          # a kernel configuration that cannot run this shape: report, keep going
+        print("candidate failed: %s" % str(exc).splitlines()[0][:200], flush=True)
+        return float("inf")
+
+
+def _graph_time(fn, iters):
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
@@ -72,22 +80,30 @@ def main():
     gamma = torch.ones(H, device=dev, dtype=bf)
     beta = torch.zeros(H, device=dev, dtype=bf)
     flops_up = 2.0 * M * H * I
-    out = {"shape": {"tokens": M, "hidden": H, "inter": I}, "us": {}}
+    out = {"shape": {"tokens": M, "hidden": H, "inter": I}, "variants": tc.variants(), "us": {}}
     r = out["us"]
 
     # 1. up projection + GELU (forward)
     r["up_gelu_eager"] = graph_time(lambda: F.gelu(F.linear(x, w1, b1)))
-    r["up_gelu_tcgen05"] = graph_time(lambda: tc.ffn_up(x, w1, b1))
+    for v, cfg in enumerate(tc.variants()["ffn_up"]):
+        r["up_gelu_tcgen05_v%d" % v] = graph_time(lambda: tc.ffn_up(x, w1, b1, v))
+    r["up_gelu_tcgen05"] = min(r["up_gelu_tcgen05_v%d" % v] for v in range(len(tc.variants()["ffn_up"])))
+    for v, cfg in enumerate(tc.variants()["linear_bias"]):
+        r["up_bias_only_tcgen05_v%d" % v] = graph_time(lambda: tc.linear_bias(x, w1, b1, v))
     r["up_gemm_only_cublas"] = graph_time(lambda: F.linear(x, w1, b1))
     # 2. down projection (forward)
     r["down_eager"] = graph_time(lambda: F.linear(h, w2, b2))
-    r["down_tcgen05"] = graph_time(lambda: tc.linear_bias(h, w2, b2))
+    for v, cfg in enumerate(tc.variants()["linear_bias"]):
+        r["down_tcgen05_v%d" % v] = graph_time(lambda: tc.linear_bias(h, w2, b2, v))
+    r["down_tcgen05"] = min(r["down_tcgen05_v%d" % v] for v in range(len(tc.variants()["linear_bias"])))
     # 3. dgrad of the down projection + GELU backward
     def eager_dgelu():
         dh = dy.mm(w2)
         return torch.ops.aten.gelu_backward(dh, z)
     r["dgrad_dgelu_eager"] = graph_time(eager_dgelu)
-    r["dgrad_dgelu_tcgen05"] = graph_time(lambda: tc.ffn_dgelu(dy, w2, z))
+    for v, cfg in enumerate(tc.variants()["ffn_dgelu"]):
+        r["dgrad_dgelu_tcgen05_v%d" % v] = graph_time(lambda: tc.ffn_dgelu(dy, w2, z, v))
+    r["dgrad_dgelu_tcgen05"] = min(r["dgrad_dgelu_tcgen05_v%d" % v] for v in range(len(tc.variants()["ffn_dgelu"])))
     r["dgrad_gemm_only_cublas"] = graph_time(lambda: dy.mm(w2))
 
     # 4. whole feed-forward block, forward + backward

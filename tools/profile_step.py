@@ -69,11 +69,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--batch-size", type=int, default=None)
     ap.add_argument("--threshold", type=float, default=25.0)
+    ap.add_argument("--top", type=int, default=30, help="rows of the per-kernel table")
+    ap.add_argument("--extra", default="", help="extra bench.py flags, e.g. '--fused-ln 0 --tc-ffn 0'")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "step_profile"))
     a = ap.parse_args()
     args = bench.parse_args(["--model", a.model] + (["--dtype", a.dtype] if a.dtype else []) +
                             (["--batch-size", str(a.batch_size)] if a.batch_size else []) +
-                            ["--threshold", str(a.threshold)])
+                            ["--threshold", str(a.threshold)] + a.extra.split())
     dear.init()
     rank, world, device = dear.rank(), dear.size(), dear.device()
     torch.backends.cudnn.benchmark = True
@@ -126,6 +128,20 @@ def main():
             rep[tag] = {"n_per_step": len(ds) / a.steps, "mean_us": sum(ds) / len(ds), "max_us": max(ds),
                         "total_ms_per_step": sum(ds) / 1e3 / a.steps,
                         "overlapped_with_compute_frac": overlap_with(iv, comp_iv) / max(sum(ds), 1e-9)}
+    # per-kernel aggregate: where the GPU time of a step goes (durations are valid under CUPTI, gaps are not)
+    agg = {}
+    for e in kern:
+        name = e["name"]
+        name = name[:name.index("<")] if "<" in name and not name.startswith("void") else name
+        name = name.replace("void ", "")[:100]
+        c = agg.setdefault(name, [0, 0.0])
+        c[0] += 1
+        c[1] += e["dur"]
+    total = sum(c[1] for c in agg.values())
+    rep["kernel_us_per_step"] = round(total / a.steps, 1)
+    rep["top_kernels"] = [{"name": n, "per_step": round(c[0] / a.steps, 1), "us_per_step": round(c[1] / a.steps, 1),
+                           "pct": round(100.0 * c[1] / total, 1)}
+                          for n, c in sorted(agg.items(), key=lambda kv: -kv[1][1])[:a.top]]
     with open("%s.rank%d.report.json" % (a.out, rank), "w") as f:
         json.dump(rep, f, indent=1)
     if rank == 0:
