@@ -44,7 +44,7 @@ def parse_args(argv=None):
                     help="ResNets: fused channels-last BatchNorm(+add)+ReLU kernels (csrc/bn_act.cu)")
     ap.add_argument("--fused-ln", type=int, default=int(os.environ.get("DEAR_BENCH_FUSED_LN", "1")),
                     help="BERT: dropout + add + LayerNorm in one kernel (csrc/ln_fused.cu)")
-    ap.add_argument("--tc-ffn", type=int, default=int(os.environ.get("DEAR_BENCH_TC_FFN", "1")),
+    ap.add_argument("--tc-ffn", type=int, default=int(os.environ.get("DEAR_BENCH_TC_FFN", "0")),
                     help="BERT bf16: feed-forward block on the tcgen05 GEMMs with fused GELU epilogues (csrc/tc_gemm*.cu)")
     ap.add_argument("--threshold", type=float, default=25.0)
     ap.add_argument("--momentum", type=float, default=0.0)

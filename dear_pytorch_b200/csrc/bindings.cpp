@@ -28,9 +28,14 @@ namespace dear { namespace ln {
 bool ln_supported(const torch::Tensor& x);
 int64_t ln_launches();
 std::vector<torch::Tensor> ln_forward(const torch::Tensor& a, const torch::Tensor& residual, const torch::Tensor& gamma,
-                                      const torch::Tensor& beta, double p, bool training, double eps);
+                                      const torch::Tensor& beta, double p, bool training, double eps,
+                                      const c10::optional<torch::Tensor>& a_bias);
 std::vector<torch::Tensor> ln_backward(const torch::Tensor& dy, const torch::Tensor& s, const torch::Tensor& mean,
-                                       const torch::Tensor& rstd, const torch::Tensor& gamma, const torch::Tensor& mask, double p);
+                                       const torch::Tensor& rstd, const torch::Tensor& gamma, const torch::Tensor& mask, double p,
+                                       bool want_dbias);
+bool bias_gelu_supported(const torch::Tensor& z);
+torch::Tensor bias_gelu_forward(const torch::Tensor& z, const torch::Tensor& bias);
+std::vector<torch::Tensor> bias_gelu_backward(const torch::Tensor& dh, const torch::Tensor& z, const torch::Tensor& bias);
 } }
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
@@ -123,8 +128,13 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("ln_supported", &dear::ln::ln_supported);
   m.def("ln_launches", &dear::ln::ln_launches);
   m.def("ln_forward", &dear::ln::ln_forward, py::arg("a"), py::arg("residual"), py::arg("weight"), py::arg("bias"),
-        py::arg("p"), py::arg("training"), py::arg("eps"));
-  m.def("ln_backward", &dear::ln::ln_backward);
+        py::arg("p"), py::arg("training"), py::arg("eps"), py::arg("a_bias") = py::none());
+  m.def("ln_backward", &dear::ln::ln_backward, py::arg("dy"), py::arg("s"), py::arg("mean"), py::arg("rstd"), py::arg("weight"),
+        py::arg("mask"), py::arg("p"), py::arg("want_dbias") = false);
+  // fused bias + GELU (forward) and GELU backward + bias gradient (backward)
+  m.def("bias_gelu_supported", &dear::ln::bias_gelu_supported);
+  m.def("bias_gelu_forward", &dear::ln::bias_gelu_forward);
+  m.def("bias_gelu_backward", &dear::ln::bias_gelu_backward);
 
   m.attr("OPT_SGD") = static_cast<int>(OPT_SGD);
   m.attr("OPT_ADAM") = static_cast<int>(OPT_ADAM);

@@ -94,7 +94,7 @@ __device__ __forceinline__ void draw_keep(uint64_t seed, uint64_t offset, uint64
 // ------------------------------------------------------------------------------------------ forward
 template <typename T, bool DROP>
 __global__ void __launch_bounds__(kThreads)
-ln_fwd_kernel(const T* __restrict__ a, const T* __restrict__ res, const T* __restrict__ gamma,
+ln_fwd_kernel(const T* __restrict__ a, const T* __restrict__ a_bias, const T* __restrict__ res, const T* __restrict__ gamma,
               const T* __restrict__ beta, T* __restrict__ y, T* __restrict__ s_out, float* __restrict__ mean_out,
               float* __restrict__ rstd_out, uint8_t* __restrict__ mask, int rows, int H, float eps, float p,
               at::PhiloxCudaState rng) {
@@ -122,6 +122,12 @@ ln_fwd_kernel(const T* __restrict__ a, const T* __restrict__ res, const T* __res
         float fa[VEC], fr[VEC];
         Vec<T>::load(a + base + c, fa);
         Vec<T>::load(res + base + c, fr);
+        if (a_bias != nullptr) {                     // bias of the linear layer that produced a (its GEMM ran bias-free)
+          float fb[VEC];
+          Vec<T>::load(a_bias + c, fb);
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) fa[i] = Vec<T>::round(fa[i] + fb[i]);
+        }
         if (DROP) {
           bool keep[VEC];
           draw_keep<VEC>(seed, offset, base + c, p, keep);
@@ -180,8 +186,8 @@ ln_fwd_kernel(const T* __restrict__ a, const T* __restrict__ res, const T* __res
 }
 
 // ----------------------------------------------------------------------------------------- backward
-// ds, da per row; per-block partial dgamma / dbeta to part[2][gridDim.x][H]
-template <typename T, bool DROP>
+// ds, da per row; per-block partial dgamma / dbeta (/ dbias = column sums of da) to part[2 or 3][gridDim.x][H]
+template <typename T, bool DROP, bool DBIAS>
 __global__ void __launch_bounds__(kThreads)
 ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ s, const float* __restrict__ mean_in,
               const float* __restrict__ rstd_in, const T* __restrict__ gamma, const uint8_t* __restrict__ mask,
@@ -195,11 +201,14 @@ ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ s, const float* __
   const int nwarps = gridDim.x * kWarpsPerBlock;
   const float scale = DROP ? 1.0f / (1.0f - p) : 1.0f;
   const float inv_h = 1.0f / static_cast<float>(H);
-  float acc_g[kMaxIters][VEC], acc_b[kMaxIters][VEC];
+  float acc_g[kMaxIters][VEC], acc_b[kMaxIters][VEC], acc_a[DBIAS ? kMaxIters : 1][VEC];
 #pragma unroll
   for (int it = 0; it < kMaxIters; ++it) {
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) { acc_g[it][i] = 0.f; acc_b[it][i] = 0.f; }
+    for (int i = 0; i < VEC; ++i) {
+      acc_g[it][i] = 0.f; acc_b[it][i] = 0.f;
+      if (DBIAS) acc_a[it][i] = 0.f;
+    }
   }
   for (int row = warp; row < rows; row += nwarps) {
     const size_t base = static_cast<size_t>(row) * H;
@@ -246,62 +255,127 @@ ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ s, const float* __
           for (int i = 0; i < VEC; ++i) o[i] = m[i] ? o[i] * scale : 0.f;
           Vec<T>::store(da_out + base + c, o);
         }
+        if (DBIAS) {
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) acc_a[it][i] += o[i];
+        }
       }
     }
   }
   // block reduction of the per-warp column partials, one vector slot ("it") at a time
-  float* pg = part + static_cast<size_t>(blockIdx.x) * H;
-  float* pb = part + static_cast<size_t>(gridDim.x + blockIdx.x) * H;
 #pragma unroll
   for (int it = 0; it < kMaxIters; ++it) {
     if (it * 32 * VEC >= H) break;
-    for (int which = 0; which < 2; ++which) {
+    for (int which = 0; which < (DBIAS ? 3 : 2); ++which) {
       __syncthreads();
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) red[wib][lane * VEC + i] = which == 0 ? acc_g[it][i] : acc_b[it][i];
+      for (int i = 0; i < VEC; ++i) {
+        red[wib][lane * VEC + i] = which == 0 ? acc_g[it][i] : (which == 1 ? acc_b[it][i] : acc_a[DBIAS ? it : 0][i]);
+      }
       __syncthreads();
+      float* dst = part + (static_cast<size_t>(which) * gridDim.x + blockIdx.x) * H;
       for (int j = threadIdx.x; j < 32 * VEC; j += kThreads) {
         const int c = it * 32 * VEC + j;
         if (c < H) {
           float t = 0.f;
 #pragma unroll
           for (int w = 0; w < kWarpsPerBlock; ++w) t += red[w][j];
-          (which == 0 ? pg : pb)[c] = t;
+          dst[c] = t;
         }
       }
     }
   }
 }
 
-// dgamma[c] = sum_b part[0][b][c], dbeta[c] = sum_b part[1][b][c].  Block = 32 columns x 16 partial-row groups.
+// out[k][c] = sum_b part[k][b][c] for k < nout (dgamma, dbeta[, dbias]).  Block = 32 columns x 16 partial-row groups.
 template <typename T>
 __global__ void __launch_bounds__(512)
-ln_bwd_finalize(const float* __restrict__ part, T* __restrict__ dgamma, T* __restrict__ dbeta, int nblocks, int H) {
-  __shared__ float sg[16][33], sb[16][33];
+colsum_finalize(const float* __restrict__ part, T* __restrict__ out0, T* __restrict__ out1, T* __restrict__ out2,
+                int nout, int nblocks, int H) {
+  __shared__ float sm[3][16][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
-  float tg = 0.f, tb = 0.f;
+  float t[3] = {0.f, 0.f, 0.f};
   if (c < H) {
-    const float* pg = part + c;
-    const float* pb = part + static_cast<size_t>(nblocks) * H + c;
+    for (int k = 0; k < nout; ++k) {
+      const float* p = part + static_cast<size_t>(k) * nblocks * H + c;
 #pragma unroll 4
-    for (int b = threadIdx.y; b < nblocks; b += 16) {
-      tg += pg[static_cast<size_t>(b) * H];
-      tb += pb[static_cast<size_t>(b) * H];
+      for (int b = threadIdx.y; b < nblocks; b += 16) t[k] += p[static_cast<size_t>(b) * H];
     }
   }
-  sg[threadIdx.y][threadIdx.x] = tg;
-  sb[threadIdx.y][threadIdx.x] = tb;
+  for (int k = 0; k < nout; ++k) sm[k][threadIdx.y][threadIdx.x] = t[k];
   __syncthreads();
   if (threadIdx.y == 0 && c < H) {
+    T* outs[3] = {out0, out1, out2};
+    for (int k = 0; k < nout; ++k) {
+      float v = t[k];
 #pragma unroll
-    for (int j = 1; j < 16; ++j) { tg += sg[j][threadIdx.x]; tb += sb[j][threadIdx.x]; }
-    if (sizeof(T) == 4) {
-      reinterpret_cast<float*>(dgamma)[c] = tg;
-      reinterpret_cast<float*>(dbeta)[c] = tb;
-    } else {
-      reinterpret_cast<__nv_bfloat16*>(dgamma)[c] = __float2bfloat16_rn(tg);
-      reinterpret_cast<__nv_bfloat16*>(dbeta)[c] = __float2bfloat16_rn(tb);
+      for (int j = 1; j < 16; ++j) v += sm[k][j][threadIdx.x];
+      if (sizeof(T) == 4) {
+        reinterpret_cast<float*>(outs[k])[c] = v;
+      } else {
+        reinterpret_cast<__nv_bfloat16*>(outs[k])[c] = __float2bfloat16_rn(v);
+      }
     }
+  }
+}
+
+// ---------------------------------------------------------------------------- bias + GELU (elementwise)
+//   forward :  h = gelu(z + b)                      (z: bias-free GEMM output, b: [N])
+//   backward:  dz = dh * gelu'(z + b),  db = column sums of dz      -- one pass, instead of GeluBackward + a reduction
+// Thread (tx, ty) of a 64x4 block owns one 128-bit column vector and walks rows ty, ty + 4*gridDim.y, ...
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float dgelu_erf(float x) {
+  return 0.5f * (1.0f + erff(x * 0.70710678118654752440f)) + x * 0.39894228040143267794f * __expf(-0.5f * x * x);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+bias_gelu_fwd_kernel(const T* __restrict__ z, const T* __restrict__ bias, T* __restrict__ h, int rows, int N) {
+  constexpr int VEC = Vec<T>::N;
+  const int c = (blockIdx.x * 64 + threadIdx.x) * VEC;
+  if (c >= N) return;
+  float fb[VEC];
+  Vec<T>::load(bias + c, fb);
+  for (int r = blockIdx.y * 4 + threadIdx.y; r < rows; r += gridDim.y * 4) {
+    float f[VEC];
+    Vec<T>::load(z + static_cast<size_t>(r) * N + c, f);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) f[i] = gelu_erf(Vec<T>::round(f[i] + fb[i]));
+    Vec<T>::store(h + static_cast<size_t>(r) * N + c, f);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+bias_gelu_bwd_kernel(const T* __restrict__ dh, const T* __restrict__ z, const T* __restrict__ bias, T* __restrict__ dz,
+                     float* __restrict__ part, int rows, int N) {
+  constexpr int VEC = Vec<T>::N;
+  __shared__ float red[4][64 * VEC + 1];
+  const int c = (blockIdx.x * 64 + threadIdx.x) * VEC;
+  float acc[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+  if (c < N) {
+    float fb[VEC];
+    Vec<T>::load(bias + c, fb);
+    for (int r = blockIdx.y * 4 + threadIdx.y; r < rows; r += gridDim.y * 4) {
+      float fz[VEC], fd[VEC];
+      Vec<T>::load(z + static_cast<size_t>(r) * N + c, fz);
+      Vec<T>::load(dh + static_cast<size_t>(r) * N + c, fd);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        fd[i] = Vec<T>::round(fd[i] * dgelu_erf(Vec<T>::round(fz[i] + fb[i])));
+        acc[i] += fd[i];                             // the bias gradient sums the values the weight gradient sees
+      }
+      Vec<T>::store(dz + static_cast<size_t>(r) * N + c, fd);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) red[threadIdx.y][threadIdx.x * VEC + i] = acc[i];
+  __syncthreads();
+  for (int j = threadIdx.y * 64 + threadIdx.x; j < 64 * VEC; j += 256) {
+    const int cc = blockIdx.x * 64 * VEC + j;
+    if (cc < N) part[static_cast<size_t>(blockIdx.y) * N + cc] = red[0][j] + red[1][j] + red[2][j] + red[3][j];
   }
 }
 
@@ -321,7 +395,7 @@ static int grid_for(int rows, int ctas_per_sm) {
 }
 
 template <typename T>
-static void fwd_launch(const torch::Tensor& a, const torch::Tensor& res, const torch::Tensor& gamma,
+static void fwd_launch(const torch::Tensor& a, const c10::optional<torch::Tensor>& a_bias, const torch::Tensor& res, const torch::Tensor& gamma,
                        const torch::Tensor& beta, torch::Tensor& y, torch::Tensor& s, torch::Tensor& mean,
                        torch::Tensor& rstd, torch::Tensor& mask, int rows, int H, float eps, float p, bool drop) {
   auto stream = at::cuda::getCurrentCUDAStream().stream();
@@ -333,16 +407,17 @@ static void fwd_launch(const torch::Tensor& a, const torch::Tensor& res, const t
     rng = gen->philox_cuda_state(4);        // each Philox subsequence (element index / 4) draws one float4
   }
   const T* pa = reinterpret_cast<const T*>(a.data_ptr());
+  const T* pab = a_bias.has_value() ? reinterpret_cast<const T*>(a_bias->data_ptr()) : nullptr;
   const T* pr = reinterpret_cast<const T*>(res.data_ptr());
   const T* pg = reinterpret_cast<const T*>(gamma.data_ptr());
   const T* pb = reinterpret_cast<const T*>(beta.data_ptr());
   T* py = reinterpret_cast<T*>(y.data_ptr());
   T* ps = reinterpret_cast<T*>(s.data_ptr());
   if (drop) {
-    ln_fwd_kernel<T, true><<<grid, kThreads, 0, stream>>>(pa, pr, pg, pb, py, ps, mean.data_ptr<float>(),
+    ln_fwd_kernel<T, true><<<grid, kThreads, 0, stream>>>(pa, pab, pr, pg, pb, py, ps, mean.data_ptr<float>(),
                                                           rstd.data_ptr<float>(), mask.data_ptr<uint8_t>(), rows, H, eps, p, rng);
   } else {
-    ln_fwd_kernel<T, false><<<grid, kThreads, 0, stream>>>(pa, pr, pg, pb, py, ps, mean.data_ptr<float>(),
+    ln_fwd_kernel<T, false><<<grid, kThreads, 0, stream>>>(pa, pab, pr, pg, pb, py, ps, mean.data_ptr<float>(),
                                                            rstd.data_ptr<float>(), nullptr, rows, H, eps, 0.f, rng);
   }
   C10_CUDA_KERNEL_LAUNCH_CHECK();
@@ -351,7 +426,8 @@ static void fwd_launch(const torch::Tensor& a, const torch::Tensor& res, const t
 
 // returns {y, s, mean, rstd, mask}; mask is an empty tensor when no dropout was applied
 std::vector<torch::Tensor> ln_forward(const torch::Tensor& a, const torch::Tensor& residual, const torch::Tensor& gamma,
-                                      const torch::Tensor& beta, double p, bool training, double eps) {
+                                      const torch::Tensor& beta, double p, bool training, double eps,
+                                      const c10::optional<torch::Tensor>& a_bias) {
   TORCH_CHECK(ln_supported(a), "dropout_add_layer_norm: unsupported tensor (CUDA bf16 with H % 8 == 0 or fp32 with H % 4 == 0, H <= 1024)");
   TORCH_CHECK(a.is_contiguous() && residual.is_contiguous() && gamma.is_contiguous() && beta.is_contiguous(),
               "dropout_add_layer_norm: contiguous tensors expected");
@@ -359,6 +435,8 @@ std::vector<torch::Tensor> ln_forward(const torch::Tensor& a, const torch::Tenso
               gamma.scalar_type() == a.scalar_type() && beta.scalar_type() == a.scalar_type(), "dropout_add_layer_norm: dtype/shape mismatch");
   const int H = a.size(-1);
   TORCH_CHECK(gamma.numel() == H && beta.numel() == H, "dropout_add_layer_norm: weight/bias size");
+  TORCH_CHECK(!a_bias.has_value() || (a_bias->numel() == H && a_bias->scalar_type() == a.scalar_type() && a_bias->is_contiguous()),
+              "dropout_add_layer_norm: branch bias must be a contiguous [H] tensor of the activation dtype");
   TORCH_CHECK(p >= 0.0 && p < 1.0, "dropout probability must be in [0, 1)");
   c10::cuda::CUDAGuard guard(a.device());
   const int rows = a.numel() / H;
@@ -371,9 +449,9 @@ std::vector<torch::Tensor> ln_forward(const torch::Tensor& a, const torch::Tenso
   auto mask = drop ? torch::empty(a.sizes(), a.options().dtype(at::kByte)) : torch::empty({0}, a.options().dtype(at::kByte));
   if (rows > 0) {
     if (a.scalar_type() == at::kFloat) {
-      fwd_launch<float>(a, residual, gamma, beta, y, s, mean, rstd, mask, rows, H, eps, p, drop);
+      fwd_launch<float>(a, a_bias, residual, gamma, beta, y, s, mean, rstd, mask, rows, H, eps, p, drop);
     } else {
-      fwd_launch<__nv_bfloat16>(a, residual, gamma, beta, y, s, mean, rstd, mask, rows, H, eps, p, drop);
+      fwd_launch<__nv_bfloat16>(a, a_bias, residual, gamma, beta, y, s, mean, rstd, mask, rows, H, eps, p, drop);
     }
   }
   return {y, s, mean, rstd, mask};
@@ -382,32 +460,39 @@ std::vector<torch::Tensor> ln_forward(const torch::Tensor& a, const torch::Tenso
 template <typename T>
 static void bwd_launch(const torch::Tensor& dy, const torch::Tensor& s, const torch::Tensor& mean, const torch::Tensor& rstd,
                        const torch::Tensor& gamma, const torch::Tensor& mask, torch::Tensor& ds, torch::Tensor& da,
-                       torch::Tensor& dgamma, torch::Tensor& dbeta, int rows, int H, float p, bool drop) {
+                       torch::Tensor& dgamma, torch::Tensor& dbeta, torch::Tensor& dbias, int rows, int H, float p, bool drop,
+                       bool want_dbias) {
   auto stream = at::cuda::getCurrentCUDAStream().stream();
-  const int grid = grid_for(rows, 1);      // one partial dgamma/dbeta row per CTA
-  auto part = torch::empty({2, grid, H}, dy.options().dtype(at::kFloat));
+  const int grid = grid_for(rows, 1);      // one partial row per CTA and reduced quantity
+  const int nout = want_dbias ? 3 : 2;
+  auto part = torch::empty({nout, grid, H}, dy.options().dtype(at::kFloat));
   const T* pdy = reinterpret_cast<const T*>(dy.data_ptr());
   const T* ps = reinterpret_cast<const T*>(s.data_ptr());
   const T* pg = reinterpret_cast<const T*>(gamma.data_ptr());
   T* pds = reinterpret_cast<T*>(ds.data_ptr());
-  if (drop) {
-    ln_bwd_kernel<T, true><<<grid, kThreads, 0, stream>>>(pdy, ps, mean.data_ptr<float>(), rstd.data_ptr<float>(), pg,
-                                                          mask.data_ptr<uint8_t>(), pds, reinterpret_cast<T*>(da.data_ptr()),
-                                                          part.data_ptr<float>(), rows, H, p);
-  } else {
-    ln_bwd_kernel<T, false><<<grid, kThreads, 0, stream>>>(pdy, ps, mean.data_ptr<float>(), rstd.data_ptr<float>(), pg,
-                                                           nullptr, pds, nullptr, part.data_ptr<float>(), rows, H, 0.f);
-  }
+  T* pda = drop ? reinterpret_cast<T*>(da.data_ptr()) : nullptr;
+  const uint8_t* pm = drop ? mask.data_ptr<uint8_t>() : nullptr;
+  const float* pmean = mean.data_ptr<float>();
+  const float* prstd = rstd.data_ptr<float>();
+  float* pp = part.data_ptr<float>();
+#define DEAR_LN_BWD(DROP, DBIAS) \
+  ln_bwd_kernel<T, DROP, DBIAS><<<grid, kThreads, 0, stream>>>(pdy, ps, pmean, prstd, pg, pm, pds, pda, pp, rows, H, p)
+  if (drop) { if (want_dbias) DEAR_LN_BWD(true, true); else DEAR_LN_BWD(true, false); }
+  else      { if (want_dbias) DEAR_LN_BWD(false, true); else DEAR_LN_BWD(false, false); }
+#undef DEAR_LN_BWD
   C10_CUDA_KERNEL_LAUNCH_CHECK();
-  ln_bwd_finalize<T><<<(H + 31) / 32, dim3(32, 16), 0, stream>>>(part.data_ptr<float>(), reinterpret_cast<T*>(dgamma.data_ptr()),
-                                                         reinterpret_cast<T*>(dbeta.data_ptr()), grid, H);
+  colsum_finalize<T><<<(H + 31) / 32, dim3(32, 16), 0, stream>>>(
+      pp, reinterpret_cast<T*>(dgamma.data_ptr()), reinterpret_cast<T*>(dbeta.data_ptr()),
+      want_dbias ? reinterpret_cast<T*>(dbias.data_ptr()) : nullptr, nout, grid, H);
   C10_CUDA_KERNEL_LAUNCH_CHECK();
   g_launches.fetch_add(2);
 }
 
-// returns {d_residual, d_a, dgamma, dbeta}; d_a aliases d_residual when no dropout was applied
+// returns {d_residual, d_a, dgamma, dbeta, dbias}; d_a aliases d_residual when no dropout was applied; dbias (the
+// column sums of d_a, i.e. the gradient of the branch bias) is empty unless want_dbias
 std::vector<torch::Tensor> ln_backward(const torch::Tensor& dy, const torch::Tensor& s, const torch::Tensor& mean,
-                                       const torch::Tensor& rstd, const torch::Tensor& gamma, const torch::Tensor& mask, double p) {
+                                       const torch::Tensor& rstd, const torch::Tensor& gamma, const torch::Tensor& mask, double p,
+                                       bool want_dbias) {
   TORCH_CHECK(ln_supported(dy) && dy.is_contiguous() && s.is_contiguous(), "dropout_add_layer_norm backward: unsupported tensor");
   c10::cuda::CUDAGuard guard(dy.device());
   const int H = dy.size(-1);
@@ -417,16 +502,86 @@ std::vector<torch::Tensor> ln_backward(const torch::Tensor& dy, const torch::Ten
   auto da = drop ? torch::empty_like(dy) : ds;
   auto dgamma = torch::empty_like(gamma);
   auto dbeta = torch::empty_like(gamma);
+  auto dbias = want_dbias ? torch::empty_like(gamma) : torch::empty({0}, gamma.options());
   if (rows == 0) {
-    dgamma.zero_(); dbeta.zero_();
-    return {ds, da, dgamma, dbeta};
+    dgamma.zero_(); dbeta.zero_(); dbias.zero_();
+    return {ds, da, dgamma, dbeta, dbias};
   }
   if (dy.scalar_type() == at::kFloat) {
-    bwd_launch<float>(dy, s, mean, rstd, gamma, mask, ds, da, dgamma, dbeta, rows, H, p, drop);
+    bwd_launch<float>(dy, s, mean, rstd, gamma, mask, ds, da, dgamma, dbeta, dbias, rows, H, p, drop, want_dbias);
   } else {
-    bwd_launch<__nv_bfloat16>(dy, s, mean, rstd, gamma, mask, ds, da, dgamma, dbeta, rows, H, p, drop);
+    bwd_launch<__nv_bfloat16>(dy, s, mean, rstd, gamma, mask, ds, da, dgamma, dbeta, dbias, rows, H, p, drop, want_dbias);
   }
-  return {ds, da, dgamma, dbeta};
+  return {ds, da, dgamma, dbeta, dbias};
+}
+
+// ---- bias + GELU ------------------------------------------------------------------------------------
+static bool bg_supported(const torch::Tensor& z) {
+  if (!z.is_cuda() || z.dim() < 2 || !z.is_contiguous()) return false;
+  const int64_t N = z.size(-1);
+  return (z.scalar_type() == at::kBFloat16 && N % 8 == 0) || (z.scalar_type() == at::kFloat && N % 4 == 0);
+}
+bool bias_gelu_supported(const torch::Tensor& z) { return bg_supported(z); }
+
+static dim3 bg_grid(int rows, int N, int vec) {
+  const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
+  const int gx = (N / vec + 63) / 64;
+  const int gy = std::max(1, std::min((rows + 3) / 4, std::max(1, 2 * sms / gx)));
+  return dim3(gx, gy);
+}
+
+torch::Tensor bias_gelu_forward(const torch::Tensor& z, const torch::Tensor& bias) {
+  TORCH_CHECK(bg_supported(z), "bias_gelu: unsupported tensor (contiguous CUDA bf16 / fp32, last dim a multiple of one 128-bit vector)");
+  TORCH_CHECK(bias.is_contiguous() && bias.numel() == z.size(-1) && bias.scalar_type() == z.scalar_type(), "bias_gelu: bias");
+  c10::cuda::CUDAGuard guard(z.device());
+  const int N = z.size(-1);
+  const int rows = z.numel() / N;
+  auto h = torch::empty_like(z);
+  if (rows == 0) return h;
+  auto stream = at::cuda::getCurrentCUDAStream().stream();
+  if (z.scalar_type() == at::kFloat) {
+    bias_gelu_fwd_kernel<float><<<bg_grid(rows, N, 4), dim3(64, 4), 0, stream>>>(
+        z.data_ptr<float>(), bias.data_ptr<float>(), h.data_ptr<float>(), rows, N);
+  } else {
+    using B = __nv_bfloat16;
+    bias_gelu_fwd_kernel<B><<<bg_grid(rows, N, 8), dim3(64, 4), 0, stream>>>(
+        reinterpret_cast<const B*>(z.data_ptr()), reinterpret_cast<const B*>(bias.data_ptr()), reinterpret_cast<B*>(h.data_ptr()), rows, N);
+  }
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+  g_launches.fetch_add(1);
+  return h;
+}
+
+// returns {dz, dbias}
+std::vector<torch::Tensor> bias_gelu_backward(const torch::Tensor& dh, const torch::Tensor& z, const torch::Tensor& bias) {
+  TORCH_CHECK(bg_supported(z) && dh.is_contiguous() && dh.sizes() == z.sizes() && dh.scalar_type() == z.scalar_type(),
+              "bias_gelu backward: unsupported tensors");
+  c10::cuda::CUDAGuard guard(z.device());
+  const int N = z.size(-1);
+  const int rows = z.numel() / N;
+  auto dz = torch::empty_like(z);
+  auto dbias = torch::empty_like(bias);
+  if (rows == 0) { dbias.zero_(); return {dz, dbias}; }
+  auto stream = at::cuda::getCurrentCUDAStream().stream();
+  const bool f32 = z.scalar_type() == at::kFloat;
+  const dim3 grid = bg_grid(rows, N, f32 ? 4 : 8);
+  auto part = torch::empty({static_cast<long>(grid.y), N}, z.options().dtype(at::kFloat));
+  if (f32) {
+    bias_gelu_bwd_kernel<float><<<grid, dim3(64, 4), 0, stream>>>(dh.data_ptr<float>(), z.data_ptr<float>(), bias.data_ptr<float>(),
+                                                                  dz.data_ptr<float>(), part.data_ptr<float>(), rows, N);
+    colsum_finalize<float><<<(N + 31) / 32, dim3(32, 16), 0, stream>>>(part.data_ptr<float>(), dbias.data_ptr<float>(), nullptr,
+                                                                       nullptr, 1, grid.y, N);
+  } else {
+    using B = __nv_bfloat16;
+    bias_gelu_bwd_kernel<B><<<grid, dim3(64, 4), 0, stream>>>(
+        reinterpret_cast<const B*>(dh.data_ptr()), reinterpret_cast<const B*>(z.data_ptr()), reinterpret_cast<const B*>(bias.data_ptr()),
+        reinterpret_cast<B*>(dz.data_ptr()), part.data_ptr<float>(), rows, N);
+    colsum_finalize<B><<<(N + 31) / 32, dim3(32, 16), 0, stream>>>(part.data_ptr<float>(), reinterpret_cast<B*>(dbias.data_ptr()),
+                                                                   nullptr, nullptr, 1, grid.y, N);
+  }
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+  g_launches.fetch_add(2);
+  return {dz, dbias};
 }
 
 }  // namespace ln

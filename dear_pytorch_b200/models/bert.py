@@ -12,10 +12,13 @@ from __future__ import annotations
 import math
 from dataclasses import dataclass
 
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from ..ops.bias_gelu import linear_gelu
 from ..ops.fused_ln import FusedDropoutAddLayerNorm
 from ..ops.tc_gemm import fused_ffn
 
@@ -43,6 +46,30 @@ BERT_BASE = BertConfig(hidden_size=768, num_hidden_layers=12, num_attention_head
                        intermediate_size=3072)              # dear/bert_base_config.json
 
 
+class Linear(nn.Linear):
+    """``nn.Linear`` (same parameters and state-dict keys) whose call selects what happens to the bias:
+
+    * ``"bias"`` (default): ``x W^T + b``;
+    * ``"none"``: ``x W^T`` — the bias is consumed by a downstream fused kernel;
+    * ``"gelu"``: ``gelu(x W^T + b)`` with the bias gradient fused into the GELU backward;
+    * ``"params"``: returns ``(W, b)`` for an op that takes the raw parameters.
+
+    Every mode goes through ``Module.__call__`` so forward pre-hooks run: the decoupled all-reduce
+    engine hangs its "this bucket's all-gather has landed" wait on them
+    (parallel/optimizer.py: _make_pre_hook), and a parameter must never be read around them."""
+
+    def forward(self, x, epilogue: str = "bias"):              # type: ignore[override]
+        if epilogue == "bias":
+            return F.linear(x, self.weight, self.bias)
+        if epilogue == "none":
+            return F.linear(x, self.weight)
+        if epilogue == "gelu":
+            return linear_gelu(x, self.weight, self.bias)
+        if epilogue == "params":
+            return self.weight, self.bias
+        raise ValueError("unknown epilogue %r" % (epilogue,))
+
+
 class BertEmbeddings(nn.Module):
     def __init__(self, c: BertConfig, vocab: int):
         super().__init__()
@@ -63,6 +90,14 @@ class BertEmbeddings(nn.Module):
         return self.dropout(self.LayerNorm(x))
 
 
+def _sdpa_backend(name):
+    if not name:
+        return None
+    from torch.nn.attention import SDPBackend
+    return {"cudnn": SDPBackend.CUDNN_ATTENTION, "efficient": SDPBackend.EFFICIENT_ATTENTION,
+            "flash": SDPBackend.FLASH_ATTENTION, "math": SDPBackend.MATH}[name.lower()]
+
+
 class BertSelfAttention(nn.Module):
     def __init__(self, c: BertConfig):
         super().__init__()
@@ -70,26 +105,37 @@ class BertSelfAttention(nn.Module):
         self.hd = c.hidden_size // c.num_attention_heads
         self.qkv = nn.Linear(c.hidden_size, 3 * c.hidden_size)      # fused Q,K,V projection
         self.p_drop = c.attention_probs_dropout_prob
+        # optional pin of the SDPA implementation ("cudnn" | "efficient" | "flash" | "math"); default: PyTorch's choice
+        self.backend = _sdpa_backend(os.environ.get("DEAR_SDPA_BACKEND"))
 
     def forward(self, x, attn_bias):
         B, S, H = x.shape
-        qkv = self.qkv(x).view(B, S, 3, self.nh, self.hd).permute(2, 0, 3, 1, 4)
-        o = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2], attn_mask=attn_bias,
-                                           dropout_p=self.p_drop if self.training else 0.0)
+        # unbind (not indexing): its backward is ONE stack of (dq, dk, dv) instead of three zero-filled
+        # [B,S,3,H] buffers, three copies and two adds
+        q, k, v = self.qkv(x).view(B, S, 3, self.nh, self.hd).unbind(2)
+        p = self.p_drop if self.training else 0.0
+        if self.backend is None:
+            o = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), attn_mask=attn_bias,
+                                               dropout_p=p)
+        else:
+            with torch.nn.attention.sdpa_kernel(self.backend):
+                o = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2),
+                                                   attn_mask=attn_bias, dropout_p=p)
         return o.transpose(1, 2).reshape(B, S, H)
 
 
 class BertLayer(nn.Module):
-    """Post-LN transformer layer.  ``fused_ln``: dropout + add + LayerNorm in one kernel
-    (ops/fused_ln.py); ``tc_ffn``: feed-forward block on the tcgen05 GEMMs with GELU / GELU' in the
+    """Post-LN transformer layer.  ``fused_ln``: bias + dropout + add + LayerNorm in one kernel
+    (ops/fused_ln.py) and bias + GELU in one kernel (ops/bias_gelu.py), bias gradients fused into their
+    backward kernels; ``tc_ffn``: feed-forward block on the tcgen05 GEMMs with GELU / GELU' in the
     epilogues (ops/tc_gemm.py).  Parameters and state-dict keys are identical in every mode."""
 
     def __init__(self, c: BertConfig, fused_ln: bool = False, tc_ffn: bool = False):
         super().__init__()
         self.attention = BertSelfAttention(c)
-        self.attn_out = nn.Linear(c.hidden_size, c.hidden_size)
-        self.intermediate = nn.Linear(c.hidden_size, c.intermediate_size)
-        self.output = nn.Linear(c.intermediate_size, c.hidden_size)
+        self.attn_out = Linear(c.hidden_size, c.hidden_size)
+        self.intermediate = Linear(c.hidden_size, c.intermediate_size)
+        self.output = Linear(c.intermediate_size, c.hidden_size)
         self.fused_ln, self.tc_ffn = fused_ln, tc_ffn
         if fused_ln:
             self.attn_norm = FusedDropoutAddLayerNorm(c.hidden_size, eps=c.layer_norm_eps, p=c.hidden_dropout_prob)
@@ -99,18 +145,24 @@ class BertLayer(nn.Module):
             self.out_norm = nn.LayerNorm(c.hidden_size, eps=c.layer_norm_eps)
             self.dropout = nn.Dropout(c.hidden_dropout_prob)
 
-    def ffn(self, x):
-        if self.tc_ffn:
-            return fused_ffn(x, self.intermediate.weight, self.intermediate.bias, self.output.weight, self.output.bias)
-        return self.output(F.gelu(self.intermediate(x)))
+    def ffn_tc(self, x):
+        w1, b1 = self.intermediate(None, "params")
+        w2, b2 = self.output(None, "params")
+        return fused_ffn(x, w1, b1, w2, b2)
 
     def forward(self, x, attn_bias):
-        a = self.attn_out(self.attention(x, attn_bias))
+        ctx = self.attention(x, attn_bias)
         if self.fused_ln:
-            x = self.attn_norm(a, x)
-            return self.out_norm(self.ffn(x), x)
-        x = self.attn_norm(x + self.dropout(a))
-        return self.out_norm(x + self.dropout(self.ffn(x)))
+            # the two output projections run bias-free; their biases are added inside the fused
+            # dropout+add+LayerNorm kernel, whose backward also yields the bias gradients
+            x = self.attn_norm(self.attn_out(ctx, "none"), x, self.attn_out.bias)
+            if self.tc_ffn:
+                return self.out_norm(self.ffn_tc(x), x)
+            h = self.intermediate(x, "gelu")
+            return self.out_norm(self.output(h, "none"), x, self.output.bias)
+        x = self.attn_norm(x + self.dropout(self.attn_out(ctx)))
+        f = self.ffn_tc(x) if self.tc_ffn else self.output(F.gelu(self.intermediate(x)))
+        return self.out_norm(x + self.dropout(f))
 
 
 class BertModel(nn.Module):

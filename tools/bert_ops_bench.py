@@ -57,32 +57,7 @@ def _graph_time(fn, iters):
     return e0.elapsed_time(e1) * 1e3 / (iters * REPS)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--tokens", type=int, default=2048)
-    ap.add_argument("--hidden", type=int, default=1024)
-    ap.add_argument("--inter", type=int, default=4096)
-    ap.add_argument("--json", default=None)
-    a = ap.parse_args()
-    dev = torch.device("cuda:0")
-    tc = require_tc()
-    M, H, I = a.tokens, a.hidden, a.inter
-    bf = torch.bfloat16
-    torch.manual_seed(0)
-    x = torch.randn(M, H, device=dev).to(bf)
-    w1 = (torch.randn(I, H, device=dev) * H ** -0.5).to(bf)
-    b1 = torch.randn(I, device=dev).to(bf)
-    w2 = (torch.randn(H, I, device=dev) * I ** -0.5).to(bf)
-    b2 = torch.randn(H, device=dev).to(bf)
-    z = torch.randn(M, I, device=dev).to(bf)
-    h = F.gelu(z)
-    dy = torch.randn(M, H, device=dev).to(bf)
-    gamma = torch.ones(H, device=dev, dtype=bf)
-    beta = torch.zeros(H, device=dev, dtype=bf)
-    flops_up = 2.0 * M * H * I
-    out = {"shape": {"tokens": M, "hidden": H, "inter": I}, "variants": tc.variants(), "us": {}}
-    r = out["us"]
-
+def _gemm_section(r, tc, x, w1, b1, w2, b2, h, z, dy):
     # 1. up projection + GELU (forward)
     r["up_gelu_eager"] = graph_time(lambda: F.gelu(F.linear(x, w1, b1)))
     for v, cfg in enumerate(tc.variants()["ffn_up"]):
@@ -106,6 +81,39 @@ def main():
     r["dgrad_dgelu_tcgen05"] = min(r["dgrad_dgelu_tcgen05_v%d" % v] for v in range(len(tc.variants()["ffn_dgelu"])))
     r["dgrad_gemm_only_cublas"] = graph_time(lambda: dy.mm(w2))
 
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--tokens", type=int, default=2048)
+    ap.add_argument("--hidden", type=int, default=1024)
+    ap.add_argument("--inter", type=int, default=4096)
+    ap.add_argument("--json", default=None)
+    ap.add_argument("--sections", default="gemm,ffn,ln,lg,attn",
+                    help="comma list: gemm (tcgen05 variants vs cuBLAS), ffn (whole block), ln, lg (linear+gelu), attn")
+    a = ap.parse_args()
+    sections = set(a.sections.split(","))
+    dev = torch.device("cuda:0")
+    tc = require_tc()
+    M, H, I = a.tokens, a.hidden, a.inter
+    bf = torch.bfloat16
+    torch.manual_seed(0)
+    x = torch.randn(M, H, device=dev).to(bf)
+    w1 = (torch.randn(I, H, device=dev) * H ** -0.5).to(bf)
+    b1 = torch.randn(I, device=dev).to(bf)
+    w2 = (torch.randn(H, I, device=dev) * I ** -0.5).to(bf)
+    b2 = torch.randn(H, device=dev).to(bf)
+    z = torch.randn(M, I, device=dev).to(bf)
+    h = F.gelu(z)
+    dy = torch.randn(M, H, device=dev).to(bf)
+    gamma = torch.ones(H, device=dev, dtype=bf)
+    beta = torch.zeros(H, device=dev, dtype=bf)
+    flops_up = 2.0 * M * H * I
+    out = {"shape": {"tokens": M, "hidden": H, "inter": I}, "variants": tc.variants(), "us": {}}
+    r = out["us"]
+
+    if "gemm" in sections:
+        _gemm_section(r, tc, x, w1, b1, w2, b2, h, z, dy)
     # 4. whole feed-forward block, forward + backward
     xs = x.clone().requires_grad_(True)
     ps = [t.clone().requires_grad_(True) for t in (w1, b1, w2, b2)]
@@ -117,9 +125,10 @@ def main():
     def ffn_fused(down):
         y = fused_ffn(xs, ps[0], ps[1], ps[2], ps[3], tc_down=down)
         return torch.autograd.grad(y, [xs] + ps, dy)
-    r["ffn_fwd_bwd_eager"] = graph_time(ffn_eager)
-    r["ffn_fwd_bwd_tcgen05"] = graph_time(lambda: ffn_fused(True))
-    r["ffn_fwd_bwd_tcgen05_cublas_down"] = graph_time(lambda: ffn_fused(False))
+    if "ffn" in sections:
+        r["ffn_fwd_bwd_eager"] = graph_time(ffn_eager)
+        r["ffn_fwd_bwd_tcgen05"] = graph_time(lambda: ffn_fused(True))
+        r["ffn_fwd_bwd_tcgen05_cublas_down"] = graph_time(lambda: ffn_fused(False))
 
     # 5. dropout + add + LayerNorm, forward + backward
     av = x.clone().requires_grad_(True)
@@ -133,17 +142,75 @@ def main():
     def ln_fused():
         y = dropout_add_layer_norm(av, rv, gv, bv, 0.1, True, 1e-12)
         return torch.autograd.grad(y, [av, rv, gv, bv], dy)
-    r["drop_add_ln_fwd_bwd_eager"] = graph_time(ln_eager)
-    r["drop_add_ln_fwd_bwd_fused"] = graph_time(ln_fused)
-    r["drop_add_ln_fwd_eager"] = graph_time(lambda: F.layer_norm(rv.detach() + F.dropout(av.detach(), 0.1, True), (H,), gamma, beta, 1e-12))
-    r["drop_add_ln_fwd_fused"] = graph_time(lambda: dropout_add_layer_norm(av.detach(), rv.detach(), gamma, beta, 0.1, True, 1e-12))
+    if "ln" in sections:
+        r["drop_add_ln_fwd_bwd_eager"] = graph_time(ln_eager)
+        r["drop_add_ln_fwd_bwd_fused"] = graph_time(ln_fused)
+        r["drop_add_ln_fwd_eager"] = graph_time(
+            lambda: F.layer_norm(rv.detach() + F.dropout(av.detach(), 0.1, True), (H,), gamma, beta, 1e-12))
+        r["drop_add_ln_fwd_fused"] = graph_time(
+            lambda: dropout_add_layer_norm(av.detach(), rv.detach(), gamma, beta, 0.1, True, 1e-12))
+        bbv = b2.clone().requires_grad_(True)
+
+        def ln_bias_eager():       # the bias lives in the GEMM epilogue in eager mode; its gradient is a separate reduction
+            y = F.layer_norm(rv + F.dropout(av + bbv, 0.1, True), (H,), gv, bv, 1e-12)
+            return torch.autograd.grad(y, [av, rv, gv, bv, bbv], dy)
+
+        def ln_bias_fused():
+            y = dropout_add_layer_norm(av, rv, gv, bv, 0.1, True, 1e-12, branch_bias=bbv)
+            return torch.autograd.grad(y, [av, rv, gv, bv, bbv], dy)
+        r["bias_drop_add_ln_fwd_bwd_eager"] = graph_time(ln_bias_eager)
+        r["bias_drop_add_ln_fwd_bwd_fused"] = graph_time(ln_bias_fused)
+
+    # 6. bias + GELU around a bias-free GEMM, forward + backward (bias gradient included)
+    from dear_pytorch_b200.ops.bias_gelu import linear_gelu
+    w1g, b1g = w1.clone().requires_grad_(True), b1.clone().requires_grad_(True)
+    dh = torch.randn(M, I, device=dev).to(bf)
+
+    def lg_eager():
+        return torch.autograd.grad(F.gelu(F.linear(xs, w1g, b1g)), [xs, w1g, b1g], dh)
+
+    def lg_fused():
+        return torch.autograd.grad(linear_gelu(xs, w1g, b1g), [xs, w1g, b1g], dh)
+    if "lg" in sections:
+        r["linear_gelu_fwd_bwd_eager"] = graph_time(lg_eager)
+        r["linear_gelu_fwd_bwd_fused"] = graph_time(lg_fused)
+
+    # 7. attention at the benchmark's shape (batch 32, 16 heads, seq 64, head dim 64), forward + backward
+    from torch.nn.attention import SDPBackend, sdpa_kernel
+    Bq, S, nh, hd = max(1, M // 64), 64, H // 64, 64
+    qkv = torch.randn(Bq, S, 3, nh, hd, device=dev).to(bf).requires_grad_(True)
+    abias = torch.zeros(Bq, 1, 1, S, device=dev, dtype=bf)
+    do = torch.randn(Bq, nh, S, hd, device=dev).to(bf)
+
+    def attn(backend, mask=True, index=False):
+        def f():
+            if index:
+                t = qkv.permute(2, 0, 3, 1, 4)
+                q, k, v = t[0], t[1], t[2]
+            else:
+                q, k, v = (t.transpose(1, 2) for t in qkv.unbind(2))
+            if backend is None:
+                o = F.scaled_dot_product_attention(q, k, v, attn_mask=abias if mask else None, dropout_p=0.1)
+            else:
+                with sdpa_kernel(backend):
+                    o = F.scaled_dot_product_attention(q, k, v, attn_mask=abias if mask else None, dropout_p=0.1)
+            return torch.autograd.grad(o, qkv, do)
+        return f
+    if "attn" in sections:
+        r["attn_fwd_bwd_default_indexing"] = graph_time(attn(None, index=True))
+        r["attn_fwd_bwd_default_unbind"] = graph_time(attn(None))
+        r["attn_fwd_bwd_cudnn"] = graph_time(attn(SDPBackend.CUDNN_ATTENTION))
+        r["attn_fwd_bwd_efficient"] = graph_time(attn(SDPBackend.EFFICIENT_ATTENTION))
+        r["attn_fwd_bwd_flash_nomask"] = graph_time(attn(SDPBackend.FLASH_ATTENTION, mask=False))
+        r["attn_fwd_bwd_math"] = graph_time(attn(SDPBackend.MATH))
 
     for k in list(r):
         r[k] = round(r[k], 2)
-    out["tflops"] = {"up_gelu_tcgen05": round(flops_up / r["up_gelu_tcgen05"] / 1e6, 1),
-                     "up_gemm_only_cublas": round(flops_up / r["up_gemm_only_cublas"] / 1e6, 1),
-                     "dgrad_dgelu_tcgen05": round(flops_up / r["dgrad_dgelu_tcgen05"] / 1e6, 1),
-                     "dgrad_gemm_only_cublas": round(flops_up / r["dgrad_gemm_only_cublas"] / 1e6, 1)}
+    if "gemm" in sections:
+        out["tflops"] = {"up_gelu_tcgen05": round(flops_up / r["up_gelu_tcgen05"] / 1e6, 1),
+                         "up_gemm_only_cublas": round(flops_up / r["up_gemm_only_cublas"] / 1e6, 1),
+                         "dgrad_dgelu_tcgen05": round(flops_up / r["dgrad_dgelu_tcgen05"] / 1e6, 1),
+                         "dgrad_gemm_only_cublas": round(flops_up / r["dgrad_gemm_only_cublas"] / 1e6, 1)}
     print(json.dumps(out, indent=1))
     if a.json:
         with open(a.json, "w") as f:
