@@ -40,6 +40,9 @@ def parse_args(argv=None):
     ap.add_argument("--channels-last", type=int, default=int(os.environ.get("DEAR_BENCH_CL", "1")))
     ap.add_argument("--graph", type=int, default=int(os.environ.get("DEAR_BENCH_GRAPH", "1")),
                     help="replay the whole iteration as one CUDA graph (GPU only; validated at 1/2/8 GPUs)")
+    ap.add_argument("--overlap-update", type=int, default=int(os.environ.get("DEAR_BENCH_OVERLAP", "0")),
+                    help="graph mode: capture step(previous gradients) -> forward -> backward so the update + all-gather "
+                         "kernels overlap the forward inside the graph (utils/train.py)")
     ap.add_argument("--fused-bn", type=int, default=int(os.environ.get("DEAR_BENCH_FUSED_BN", "1")),
                     help="ResNets: fused channels-last BatchNorm(+add)+ReLU kernels (csrc/bn_act.cu)")
     ap.add_argument("--fused-ln", type=int, default=int(os.environ.get("DEAR_BENCH_FUSED_LN", "1")),
@@ -176,7 +179,7 @@ def run_dear(args):
                                     verbose=(rank == 0 and bool(os.environ.get("DEAR_VERBOSE"))))
     dear.broadcast_parameters(model.state_dict(), 0)
     step = TrainStep(model, opt, wl.loss_fn, autocast_dtype=torch.bfloat16 if args.dtype == "amp" else None,
-                     use_graph=bool(args.graph) and cuda)
+                     use_graph=bool(args.graph) and cuda, overlap_update=bool(args.overlap_update) and bool(args.graph) and cuda)
     B = args.batch_size
 
     # ---- device-resident synthetic batch (the reference's protocol) -------------------------
@@ -274,6 +277,7 @@ def run_dear(args):
         cfg = {"model": args.model, "global_batch": B * world, "batch_per_gpu": B, "parallelism": "dp%d" % world,
                "optimizer": "%s lr=%g" % (args.optimizer.upper(), lr), "threshold_mb": args.threshold, "buckets": len(opt.engine.plan.buckets),
                "params": n_params, "backend": dear.backend(), "cuda_graph": bool(args.graph),
+               "update_overlaps_forward_in_graph": bool(step.overlap_update),
                "l2": "no explicit flush: each step streams activations+weights far larger than the 126 MB L2"}
         if wl.is_bert:
             cfg.update(seq_len=args.sentence_len, fused_dropout_add_ln=wl.fused_ln, tcgen05_ffn=wl.tc_ffn)
@@ -288,6 +292,7 @@ def run_dear(args):
             "data": "synthetic", "impl": "dear", "config": cfg, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(out), flush=True)
+    step.finish()                 # rotated loop: the last update is applied here (outside every timed region)
     opt.engine.close()
     dear.shutdown()
     return 0

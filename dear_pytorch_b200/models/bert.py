@@ -98,6 +98,13 @@ def _sdpa_backend(name):
             "flash": SDPBackend.FLASH_ATTENTION, "math": SDPBackend.MATH}[name.lower()]
 
 
+try:
+    from torch.nn.attention import SDPBackend as _SDPBackend
+    _EFFICIENT = _SDPBackend.EFFICIENT_ATTENTION
+except Exception:                      # pragma: no cover - very old torch
+    _EFFICIENT = None
+
+
 class BertSelfAttention(nn.Module):
     def __init__(self, c: BertConfig):
         super().__init__()
@@ -114,11 +121,16 @@ class BertSelfAttention(nn.Module):
         # [B,S,3,H] buffers, three copies and two adds
         q, k, v = self.qkv(x).view(B, S, 3, self.nh, self.hd).unbind(2)
         p = self.p_drop if self.training else 0.0
-        if self.backend is None:
+        backend = self.backend
+        if backend is None and x.is_cuda and S <= 128 and attn_bias is not None and _EFFICIENT is not None:
+            # short sequences with a key-padding bias: the memory-efficient kernel beats cuDNN's 128x128-tile flash
+            # backward (55 vs 77 us forward+backward at batch 32 x 16 heads x 64 x 64, profiles/bert_ops_bench.json)
+            backend = _EFFICIENT
+        if backend is None:
             o = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), attn_mask=attn_bias,
                                                dropout_p=p)
         else:
-            with torch.nn.attention.sdpa_kernel(self.backend):
+            with torch.nn.attention.sdpa_kernel(backend):
                 o = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2),
                                                    attn_mask=attn_bias, dropout_p=p)
         return o.transpose(1, 2).reshape(B, S, H)

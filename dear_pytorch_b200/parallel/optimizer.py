@@ -64,6 +64,7 @@ class DearEngine:
         self.num_nearby_layers = num_nearby_layers
         self._mom_initialised = False
         self.num_updates = 0               # parameter updates applied so far (Adam bias correction)
+        self.flush_callbacks = []          # run by flush(): deferred work of the training loop (TrainStep.finish)
         if isinstance(optimizer, torch.optim.AdamW):
             self.opt_kind = OPT_ADAMW
         elif isinstance(optimizer, torch.optim.Adam):
@@ -333,6 +334,24 @@ class DearEngine:
         for cb in self._step_callbacks:
             cb()
 
+    def flush_reduce_scatter(self):
+        """Issue the reduce-scatter of every bucket that has not been issued yet (absent gradients count as
+        zeros).  ``step()`` does this itself; a loop that defers ``step()`` (utils/train.py, rotated mode)
+        calls it right after backward."""
+        if not self.exclude_reducescatter:
+            self._drain_rs(force=True)
+
+    def join_comm_stream(self):
+        """The current stream waits for everything queued on the communication stream so far."""
+        self.backend.wait_all()
+
+    def flush(self):
+        """User-facing barrier: apply deferred updates (rotated training loops register a callback), then
+        wait until every update is visible to the host."""
+        for cb in list(self.flush_callbacks):
+            cb()
+        self.synchronize(host=True)
+
     def synchronize(self, host: bool = True):
         """Make all outstanding updates visible to the current stream (and the host)."""
         if self._any_pending:
@@ -463,7 +482,7 @@ class _DistributedOptimizer(torch.optim.Optimizer):
 
     def synchronize(self):
         """Block until every outstanding parameter update has landed (host-visible)."""
-        self._dear.synchronize(host=True)
+        self._dear.flush()
 
     flush = synchronize
 

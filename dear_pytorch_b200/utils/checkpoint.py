@@ -47,7 +47,7 @@ def _param_index(optimizer) -> Dict[torch.nn.Parameter, int]:
 def optimizer_state_dict(optimizer) -> dict:
     """Collective.  torch.optim.SGD-compatible state dict with full momentum buffers."""
     eng = optimizer._dear
-    eng.synchronize(host=True)
+    eng.flush()
     carry = eng._gather_state()
     index = _param_index(optimizer)
     state = {}
@@ -78,7 +78,7 @@ def optimizer_state_dict(optimizer) -> dict:
 def load_optimizer_state_dict(optimizer, sd: dict) -> None:
     """Collective.  Accepts a dict from ``optimizer_state_dict`` or from a stock ``torch.optim.SGD``."""
     eng = optimizer._dear
-    eng.synchronize(host=True)
+    eng.flush()
     for g, saved in zip(optimizer.param_groups, sd["param_groups"]):
         for k, v in saved.items():
             if k != "params":

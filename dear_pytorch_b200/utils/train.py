@@ -6,6 +6,15 @@ stream synchronisations for ResNet-50.  With the fused kernels
 needs ~2 launches per bucket and no host synchronisation, and because the cross-GPU epochs live in
 device memory (csrc/kernels.cu) the whole iteration — cuDNN/cuBLAS kernels, Kernel A per bucket on
 the communication stream, Kernel B per bucket — replays as ONE graph launch.
+
+``overlap_update=True`` rotates the loop body to ``step(previous gradients) → forward → backward``.
+Graph launches serialise, so with the natural body the update + all-gather of iteration *t* (issued
+by ``step()`` at the END of the graph) cannot overlap the forward of iteration *t+1* the way it does
+in eager mode — the decoupling the whole method is about would be lost inside a graph.  Rotated, the
+all-gathers are the FIRST nodes of the graph and the forward's per-bucket waits let them overlap
+layer by layer.  Every call still performs one forward/backward and (from the second call on) one
+parameter update; ``finish()`` — also run by ``optimizer.synchronize()`` / ``state_dict()`` — applies
+the last pending update, so nothing is dropped at the end of training.
 """
 from __future__ import annotations
 
@@ -44,7 +53,7 @@ def _first_tensor(obj):
 
 class TrainStep:
     def __init__(self, model: torch.nn.Module, optimizer, loss_fn: Callable, autocast_dtype: Optional[torch.dtype] = None,
-                 use_graph: bool = False, graph_warmup: int = 3):
+                 use_graph: bool = False, graph_warmup: int = 3, overlap_update: bool = False):
         self.model = model
         self.opt = optimizer
         self.loss_fn = loss_fn
@@ -59,9 +68,12 @@ class TrainStep:
         self._debug = bool(os.environ.get("DEAR_GRAPH_DEBUG"))
         self._side = None
         self.eager_calls = 0               # how many times the Python step body ran (incl. the capture)
+        self.overlap_update = overlap_update
+        self._pending_update = False       # rotated mode: gradients reduced, update not yet applied
+        if overlap_update and self._engine is not None:
+            self._engine.flush_callbacks.append(self.finish)
 
-    def _eager(self, *batch):
-        self.eager_calls += 1
+    def _forward_backward(self, *batch):
         *inputs, target = batch
         self.opt.zero_grad()
         if self.autocast_dtype is not None:
@@ -71,8 +83,27 @@ class TrainStep:
             out = self.model(*inputs)
         loss = self.loss_fn(out, target)
         loss.backward()
-        self.opt.step()
         return loss.detach()
+
+    def _eager(self, *batch):
+        self.eager_calls += 1
+        if not self.overlap_update:
+            loss = self._forward_backward(*batch)
+            self.opt.step()
+            return loss
+        if self._pending_update:
+            self.opt.step()                               # update from the previous call's gradients
+        loss = self._forward_backward(*batch)
+        if self._engine is not None:
+            self._engine.flush_reduce_scatter()           # incomplete buckets (unused parameters) too
+        self._pending_update = True
+        return loss
+
+    def finish(self):
+        """Rotated mode: apply the update of the last call's gradients (no-op otherwise)."""
+        if self._pending_update:
+            self._pending_update = False
+            self.opt.step()
 
     def _log(self, msg):
         if self._debug:
@@ -91,6 +122,7 @@ class TrainStep:
             loss = self._eager(*batch)
             if self._engine is not None:
                 self._engine.synchronize(host=False)
+                self._engine.join_comm_stream()
         cur.wait_stream(self._side)
         _tree_map(lambda t: t.record_stream(self._side), batch)
         return loss
@@ -108,6 +140,7 @@ class TrainStep:
             loss = self._eager(*self._static_in)
             if eng is not None:
                 eng.synchronize(host=False)     # join the communication stream back into the capture
+                eng.join_comm_stream()          # (rotated body: the reduce-scatters are its last nodes)
             self._static_loss = loss
         self._log("capture done; first replay")
         # the capture only records: replaying it IS this call's training step
@@ -118,6 +151,10 @@ class TrainStep:
         self._calls += 1
         if not self.use_graph:
             return self._eager(*batch)
+        if self.overlap_update and not self._pending_update:
+            # nothing to apply yet (first call, or right after finish()): the captured body starts with an
+            # update, so prime it with a plain forward/backward
+            return self._eager_on_side_stream(batch)
         if self._graph is None:
             if self._calls <= self.graph_warmup:
                 return self._eager_on_side_stream(batch)

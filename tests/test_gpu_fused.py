@@ -127,7 +127,7 @@ def test_general_collectives():
         torch.testing.assert_close(res["sendrecv"], torch.full((9,), float((r + 1) % world)))
 
 
-def graph_worker(rank, world, use_graph):
+def graph_worker(rank, world, use_graph, overlap=False):
     import dear_pytorch_b200 as dear
     from dear_pytorch_b200.utils.train import TrainStep
     dev = dear.device()
@@ -136,7 +136,7 @@ def graph_worker(rank, world, use_graph):
     opt = torch.optim.SGD(model.parameters(), lr=0.05, momentum=0.9, weight_decay=1e-4)
     opt = dear.DistributedOptimizer(opt, model, threshold=0.05, verbose=False)
     dear.broadcast_parameters(model.state_dict(), 0)
-    step = TrainStep(model, opt, nn.functional.cross_entropy, use_graph=use_graph, graph_warmup=2)
+    step = TrainStep(model, opt, nn.functional.cross_entropy, use_graph=use_graph, graph_warmup=2, overlap_update=overlap)
     g = torch.Generator().manual_seed(100 + rank)
     losses = []
     for t in range(8):
@@ -153,6 +153,20 @@ def test_cuda_graph_replay_matches_eager(world):
     eager = run_ranks(graph_worker, world=world, backend="b200", args=(False,), extra_env=_env(), timeout=300)
     graph = run_ranks(graph_worker, world=world, backend="b200", args=(True,), extra_env=_env(), timeout=300)
     assert graph[0][2] and not eager[0][2]
+    for (le, pe, _), (lg, pg, _) in zip(eager, graph):
+        torch.testing.assert_close(torch.tensor(lg), torch.tensor(le), rtol=1e-4, atol=1e-5)
+        for a, b in zip(pg, pe):
+            torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [1, 2])
+def test_rotated_cuda_graph_matches_eager(world):
+    """overlap_update: the captured body is step(previous gradients) -> forward -> backward, so the update +
+    all-gather kernels are the first nodes of the graph and overlap the forward; same training run."""
+    eager = run_ranks(graph_worker, world=world, backend="b200", args=(False,), extra_env=_env(), timeout=300)
+    graph = run_ranks(graph_worker, world=world, backend="b200", args=(True, True), extra_env=_env(), timeout=300)
+    assert graph[0][2]
     for (le, pe, _), (lg, pg, _) in zip(eager, graph):
         torch.testing.assert_close(torch.tensor(lg), torch.tensor(le), rtol=1e-4, atol=1e-5)
         for a, b in zip(pg, pe):
