@@ -40,9 +40,10 @@ def parse_args(argv=None):
     ap.add_argument("--channels-last", type=int, default=int(os.environ.get("DEAR_BENCH_CL", "1")))
     ap.add_argument("--graph", type=int, default=int(os.environ.get("DEAR_BENCH_GRAPH", "1")),
                     help="replay the whole iteration as one CUDA graph (GPU only; validated at 1/2/8 GPUs)")
-    ap.add_argument("--overlap-update", type=int, default=int(os.environ.get("DEAR_BENCH_OVERLAP", "0")),
+    ap.add_argument("--overlap-update", type=int, default=(int(os.environ["DEAR_BENCH_OVERLAP"]) if "DEAR_BENCH_OVERLAP" in os.environ else None),
                     help="graph mode: capture step(previous gradients) -> forward -> backward so the update + all-gather "
-                         "kernels overlap the forward inside the graph (utils/train.py)")
+                         "kernels overlap the forward inside the graph (utils/train.py); default: on for BERT (73 buckets, "
+                         "+3.5 %% measured on one B200), off for the conv nets (5 buckets: neutral)")
     ap.add_argument("--fused-bn", type=int, default=int(os.environ.get("DEAR_BENCH_FUSED_BN", "1")),
                     help="ResNets: fused channels-last BatchNorm(+add)+ReLU kernels (csrc/bn_act.cu)")
     ap.add_argument("--fused-ln", type=int, default=int(os.environ.get("DEAR_BENCH_FUSED_LN", "1")),
@@ -62,6 +63,8 @@ def parse_args(argv=None):
     if args.dtype is None:
         # BERT-large is specified in bf16 (BASELINE.json); ResNet-50 runs at the reference's precision
         args.dtype = "bf16" if is_bert else "fp32"
+    if args.overlap_update is None:
+        args.overlap_update = 1 if is_bert else 0
     return args
 
 
