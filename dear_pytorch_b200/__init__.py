@@ -18,5 +18,6 @@ from .parallel.optimizer import DistributedOptimizer, DearEngine, THRESHOLD, NUM
 from .parallel.collectives import (allreduce, allreduce_, broadcast_, broadcast_parameters,  # noqa: F401
                                    broadcast_optimizer_state, allgather)
 from .utils.checkpoint import save_checkpoint, load_checkpoint  # noqa: F401
+from .utils.train import TrainStep  # noqa: F401
 
 __version__ = "0.1.0"
