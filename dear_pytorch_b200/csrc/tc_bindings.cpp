@@ -41,6 +41,8 @@ at::Tensor linear_bias_v1(const at::Tensor& x, const at::Tensor& w, const at::Te
 at::Tensor linear_bias_v2(const at::Tensor& x, const at::Tensor& w, const at::Tensor& bias);
 at::Tensor linear_bias_v3(const at::Tensor& x, const at::Tensor& w, const at::Tensor& bias);
 
+std::vector<at::Tensor> ffn_up_hw(const at::Tensor& x, const at::Tensor& w, const at::Tensor& bias);   // tc_ffn_hw.cu
+
 }  // namespace dear_tc
 
 namespace {
@@ -103,5 +105,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     return std::map<std::string, std::vector<std::string>>{
         {"ffn_up", configs(k_ffn_up)}, {"linear_bias", configs(k_linear_bias)}, {"ffn_dgelu", configs(k_ffn_dgelu)}}; },
     "kernel configurations compiled for each op (index = `variant`)");
+  m.def("ffn_up_hw", &dear_tc::ffn_up_hw, py::arg("x"), py::arg("w"), py::arg("bias"),
+        "EXPERIMENTAL hand-written tcgen05 kernel (two-warpgroup epilogue): H, Z = gelu(X W^T + b), X W^T + b");
   m.def("launches", &dear_tc::launches);
 }

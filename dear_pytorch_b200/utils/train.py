@@ -14,7 +14,9 @@ in eager mode — the decoupling the whole method is about would be lost inside 
 all-gathers are the FIRST nodes of the graph and the forward's per-bucket waits let them overlap
 layer by layer.  Every call still performs one forward/backward and (from the second call on) one
 parameter update; ``finish()`` — also run by ``optimizer.synchronize()`` / ``state_dict()`` — applies
-the last pending update, so nothing is dropped at the end of training.
+the last pending update, so nothing is dropped at the end of training.  One visible difference: the
+update for batch *t* runs at the start of call *t+1*, so a learning-rate scheduler stepped between the
+two calls applies its new value one update earlier than in the natural loop.
 """
 from __future__ import annotations
 

@@ -51,7 +51,7 @@ CUTLASS = cutlass_root()
 tc_ext = CUDAExtension(
     name="dear_pytorch_b200._tc",
     # one translation unit per (operation, tile configuration): they compile in parallel
-    sources=[os.path.join(CSRC, "tc_bindings.cpp")] + sorted(
+    sources=[os.path.join(CSRC, "tc_bindings.cpp"), os.path.join(CSRC, "tc_ffn_hw.cu")] + sorted(
         os.path.relpath(f, ROOT) for f in glob.glob(os.path.join(ROOT, CSRC, "tc_gemm_*.cu"))),
     include_dirs=[os.path.join(ROOT, CSRC), os.path.join(CUTLASS, "include"), os.path.join(CUTLASS, "tools", "util", "include")],
     extra_compile_args={"cxx": CXX_FLAGS, "nvcc": NVCC_FLAGS + ["--expt-extended-lambda", "-diag-suppress", "20012"]},

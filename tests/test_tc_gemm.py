@@ -1,4 +1,6 @@
 """tcgen05 GEMMs with fused epilogues (csrc/tc_gemm*.cu) against plain PyTorch fp32 references."""
+import os
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -66,6 +68,23 @@ def test_ffn_dgelu(M, K, N):
     for v in range(len(tc.variants()["ffn_dgelu"])):
         dz = tc.ffn_dgelu(dy, w, z, v)
         torch.testing.assert_close(dz.float(), z32.grad, rtol=1.5e-2, atol=1.5e-2, msg=lambda s: "variant %d: %s" % (v, s))
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.environ.get("DEAR_TC_EXPERIMENTAL"),
+                    reason="hand-written tcgen05 kernel (csrc/tc_ffn_hw.cu) has not been run on hardware yet; "
+                           "set DEAR_TC_EXPERIMENTAL=1 to exercise it")
+@pytest.mark.parametrize("M,K,N", [(128, 64, 256), (2048, 1024, 4096), (300, 72, 264), (1, 8, 8)])
+def test_handwritten_ffn_up(M, K, N):
+    tc = require_tc()
+    dev = torch.device("cuda:0")
+    torch.manual_seed(1)
+    x, w, b = _rand((M, K), dev), _rand((N, K), dev, K ** -0.5), _rand((N,), dev)
+    h, z = tc.ffn_up_hw(x, w, b)
+    torch.cuda.synchronize()
+    z_ref = x.float() @ w.float().t() + b.float()
+    torch.testing.assert_close(z.float(), z_ref, rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close(h.float(), F.gelu(z_ref), rtol=1e-2, atol=1e-2)
 
 
 @pytest.mark.gpu

@@ -63,6 +63,8 @@ def _gemm_section(r, tc, x, w1, b1, w2, b2, h, z, dy):
     for v, cfg in enumerate(tc.variants()["ffn_up"]):
         r["up_gelu_tcgen05_v%d" % v] = graph_time(lambda: tc.ffn_up(x, w1, b1, v))
     r["up_gelu_tcgen05"] = min(r["up_gelu_tcgen05_v%d" % v] for v in range(len(tc.variants()["ffn_up"])))
+    if os.environ.get("DEAR_TC_EXPERIMENTAL"):     # hand-written kernel with the two-warpgroup epilogue (csrc/tc_ffn_hw.cu)
+        r["up_gelu_tcgen05_handwritten"] = graph_time(lambda: tc.ffn_up_hw(x, w1, b1))
     for v, cfg in enumerate(tc.variants()["linear_bias"]):
         r["up_bias_only_tcgen05_v%d" % v] = graph_time(lambda: tc.linear_bias(x, w1, b1, v))
     r["up_gemm_only_cublas"] = graph_time(lambda: F.linear(x, w1, b1))
