@@ -71,10 +71,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 // Bounded wait: a protocol bug must fail the launch (trap -> cudaErrorLaunchFailure), never wedge the GPU.
+// try_wait itself suspends for an implementation-defined time, so the bound is wall time (2 s), not a spin count.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {
-    if (spins > (1u << 26)) __trap();
+  if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = global_timer_ns();
+  while (!mbar_try_wait(bar, parity)) {
+    if (global_timer_ns() - t0 > 2000000000ull) __trap();
   }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
