@@ -79,9 +79,7 @@ def init(backend: Optional[str] = None, device: Optional[torch.device] = None, *
     local_size = _env_int("LOCAL_WORLD_SIZE", world)
 
     use_cuda = torch.cuda.is_available() and (device is None or torch.device(device).type == "cuda")
-    backend = backend or os.environ.get("DEAR_BACKEND") or ("b200" if use_cuda else "gloo")
-    if backend not in _BACKENDS:
-        raise ValueError("unknown backend %r (choose from %s)" % (backend, ", ".join(_BACKENDS)))
+    backend = select_backend(backend or os.environ.get("DEAR_BACKEND"), use_cuda, world, local_size, verbose=(rank == 0))
     if backend in ("b200", "nccl") and not torch.cuda.is_available():
         raise RuntimeError("backend %r needs a CUDA device" % backend)
     if backend in ("emu", "gloo"):
@@ -144,6 +142,29 @@ def init(backend: Optional[str] = None, device: Optional[torch.device] = None, *
 
     _state = _State(backend=backend, rank=rank, world=world, local_rank=local_rank, local_size=local_size,
                     device=device, comm=comm, group=group, owns_pg=owns_pg, options=opts)
+
+
+def select_backend(requested: Optional[str], use_cuda: bool, world: int, local_size: int, verbose: bool = False) -> str:
+    """Resolve the data path.  The fused kernels move data through peer-mapped memory, which exists inside ONE
+    NVLink/NVSwitch domain (one node): a job that spans several nodes (``LOCAL_WORLD_SIZE < WORLD_SIZE``, e.g.
+    ``scripts/launch_multinode.sh``) runs the same engine on the ``nccl`` backend instead — the reference's own
+    transport (common/comm_core/communicator.cpp:85-127) — unless ``b200`` was requested explicitly."""
+    multi_node = 0 < local_size < world
+    if requested is None:
+        if not use_cuda:
+            return "gloo"
+        if multi_node:
+            if verbose:
+                print("[dear] %d ranks over %d nodes: the symmetric-memory kernels span one NVSwitch domain; "
+                      "using the nccl backend" % (world, world // local_size), flush=True)
+            return "nccl"
+        return "b200"
+    if requested not in _BACKENDS:
+        raise ValueError("unknown backend %r (choose from %s)" % (requested, ", ".join(_BACKENDS)))
+    if requested in ("b200", "emu") and multi_node:
+        raise RuntimeError("backend %r needs all %d ranks on one node (LOCAL_WORLD_SIZE=%d); use DEAR_BACKEND=nccl "
+                           "across nodes" % (requested, world, local_size))
+    return requested
 
 
 def shutdown() -> None:

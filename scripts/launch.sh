@@ -8,6 +8,8 @@ dtype="${dtype:-fp32}"; threshold="${threshold:-25}"; exclude_parts="${exclude_p
 nstreams="${nstreams:-1}"; graph="${graph:-0}"
 here="$(cd "$(dirname "$0")/.." && pwd)"
 [ -f "$here/configs/envs.conf" ] && source "$here/configs/envs.conf"
+# cluster=N picks configs/clusterN (the reference selected an MPI hostfile the same way)
+[ -n "$cluster" ] && [ -f "$here/configs/cluster$cluster" ] && source "$here/configs/cluster$cluster"
 if [[ "$dnn" == bert* ]]; then
   driver="$here/benchmarks/bert_benchmark.py"; extra="--sentence-len $senlen"
 else

@@ -168,3 +168,16 @@ def timeout_worker(rank, world):
 def test_missing_peer_is_detected_not_hung():
     outs = run_ranks(timeout_worker, world=2, backend="emu", extra_env={"DEAR_SPIN_TIMEOUT_S": "1"}, timeout=60)
     assert outs[0] == "timeout" and outs[1] == "skipped"
+
+
+def test_backend_selection_single_and_multi_node():
+    from dear_pytorch_b200.runtime import select_backend
+    assert select_backend(None, False, 2, 2) == "gloo"
+    assert select_backend(None, True, 8, 8) == "b200"
+    assert select_backend(None, True, 16, 8) == "nccl"          # two nodes: peer memory does not span them
+    assert select_backend("nccl", True, 16, 8) == "nccl"
+    assert select_backend("emu", False, 3, 3) == "emu"
+    with pytest.raises(RuntimeError):
+        select_backend("b200", True, 16, 8)
+    with pytest.raises(ValueError):
+        select_backend("mpi", True, 8, 8)
