@@ -47,7 +47,8 @@ class DearEngine:
     """Buffers, hooks and the per-bucket state machine behind ``DistributedOptimizer``."""
 
     def __init__(self, optimizer: torch.optim.Optimizer, model: nn.Module, *, threshold=THRESHOLD,
-                 num_nearby_layers=NUM_NEARBY_LAYERS, exclude_parts: str = "", policy=None, verbose=True):
+                 num_nearby_layers=NUM_NEARBY_LAYERS, exclude_parts: str = "", policy=None, verbose=True,
+                 backward_passes_per_step: int = 1):
         if not runtime.is_initialized():
             runtime.init()
         self.opt = optimizer
@@ -65,6 +66,10 @@ class DearEngine:
         self._mom_initialised = False
         self.num_updates = 0               # parameter updates applied so far (Adam bias correction)
         self.flush_callbacks = []          # run by flush(): deferred work of the training loop (TrainStep.finish)
+        if int(backward_passes_per_step) < 1:
+            raise ValueError("backward_passes_per_step must be >= 1")
+        self.passes_per_step = int(backward_passes_per_step)   # gradient accumulation: reduce on the last pass only
+        self._passes_seen = {}             # parameter -> backward passes since the last step()
         if isinstance(optimizer, torch.optim.AdamW):
             self.opt_kind = OPT_ADAMW
         elif isinstance(optimizer, torch.optim.Adam):
@@ -215,21 +220,20 @@ class DearEngine:
     def _on_grad(self, p):
         s = self.plan.slot_of[p]
         g, i = s.bucket, s.index_in_bucket
+        if self.passes_per_step > 1:
+            # gradient accumulation: autograd keeps summing into p.grad; only the last pass hands it over
+            seen = self._passes_seen.get(p, 0) + 1
+            self._passes_seen[p] = seen
+            if seen < self.passes_per_step:
+                return
         if self._rs_launched[g] or self._arrived[g][i]:
             raise RuntimeError(
-                "gradient for %s arrived twice before step(): gradient accumulation over several "
-                "backward passes is not supported by the decoupled all-reduce (call step() after "
-                "every backward, as in the reference)" % s.name)
+                "gradient for %s arrived %s before step(): pass backward_passes_per_step=k to DistributedOptimizer to "
+                "accumulate gradients over k backward passes (the reference has no accumulation: one backward per "
+                "step)" % (s.name, "twice" if self.passes_per_step == 1 else "more than %d times" % self.passes_per_step))
         grad = p.grad
         if self.steal:
-            if (grad.dtype == p.dtype and grad.stride() == p.stride() and grad.data_ptr() % 16 == 0
-                    and not grad.is_sparse):
-                self._src[g][i] = grad.data_ptr()
-            else:
-                self._grad_view[p].copy_(grad)
-                self._src[g][i] = 0
-            self._flags[g][i] = 0
-            self._inflight.append(grad)
+            self._hand_over(g, i, p, grad)
         else:
             gv = self._grad_view[p]
             if grad.data_ptr() != gv.data_ptr():
@@ -243,13 +247,35 @@ class DearEngine:
             self._complete[g] = True
             self._drain_rs()
 
+    def _hand_over(self, g, i, p, grad):
+        """Steal mode: point the pack table of bucket g at this gradient (or stage it in the bucket view)."""
+        if (grad.dtype == p.dtype and grad.stride() == p.stride() and grad.data_ptr() % 16 == 0
+                and not grad.is_sparse):
+            self._src[g][i] = grad.data_ptr()
+        else:
+            self._grad_view[p].copy_(grad)
+            self._src[g][i] = 0
+        self._flags[g][i] = 0
+        self._inflight.append(grad)
+
     def _drain_rs(self, force=False):
         """Launch reduce-scatters in descending bucket order (identical on every rank)."""
         while self._next_rs >= 0 and (force or self._complete[self._next_rs]):
             g = self._next_rs
             if not self._complete[g]:
                 for i, ok in enumerate(self._arrived[g]):
-                    if not ok:        # no gradient this iteration: contribute zeros
+                    if ok:
+                        continue
+                    late = self.plan.buckets[g].slots[i].param.grad if self.passes_per_step > 1 else None
+                    if late is not None:
+                        # accumulated over fewer passes than passes_per_step (unused in some): still a gradient
+                        p = self.plan.buckets[g].slots[i].param
+                        if self.steal:
+                            self._hand_over(g, i, p, late)
+                        elif late.data_ptr() != self._grad_view[p].data_ptr():
+                            self._grad_view[p].copy_(late)
+                            p.grad = self._grad_view[p]
+                    else:                # no gradient this iteration: contribute zeros
                         self._src[g][i] = 0
                         self._flags[g][i] = 1 if self.steal else 0
             if self.steal:
@@ -322,6 +348,7 @@ class DearEngine:
         if self.steal:
             for s in self.plan.slots:
                 s.param.grad = None
+        self._passes_seen.clear()
         # reset the per-iteration state machine
         for g in range(nb):
             if self._n_arrived[g]:
@@ -450,7 +477,7 @@ class _DistributedOptimizer(torch.optim.Optimizer):
     reference uses, dear/dear_dopt.py:395-398)."""
 
     def __init__(self, params, model, threshold=THRESHOLD, num_nearby_layers=NUM_NEARBY_LAYERS,
-                 exclude_parts="", policy=None, verbose=True):
+                 exclude_parts="", policy=None, verbose=True, backward_passes_per_step=1):
         super(self.__class__, self).__init__(params)
         if not isinstance(self, (torch.optim.SGD, torch.optim.Adam, torch.optim.AdamW)):
             raise TypeError(
@@ -464,7 +491,8 @@ class _DistributedOptimizer(torch.optim.Optimizer):
             if g.get("maximize", False):
                 raise ValueError("maximize=True is not supported")
         self._dear = DearEngine(self, model, threshold=threshold, num_nearby_layers=num_nearby_layers,
-                                exclude_parts=exclude_parts, policy=policy, verbose=verbose)
+                                exclude_parts=exclude_parts, policy=policy, verbose=verbose,
+                                backward_passes_per_step=backward_passes_per_step)
 
     # -- torch.optim.Optimizer API ---------------------------------------------------
     def step(self, closure=None):
@@ -502,15 +530,18 @@ class _DistributedOptimizer(torch.optim.Optimizer):
 def DistributedOptimizer(optimizer, model, compression=None, is_sparse=False, density=0.001, seq_layernames=None,
                          layerwise_times=None, norm_clip=None, threshold=None, writer=None, gradient_path=None,
                          fp16=False, mgwfbp=False, rdma=False, multi_job_scheduling=False, exclude_parts="",
-                         num_nearby_layers=None, policy=None, verbose=True, bo_tuning=False, bo_kwargs=None):
-    """Wrap ``optimizer`` (an ``torch.optim.SGD``) for DeAR data-parallel training of ``model``.
+                         num_nearby_layers=None, policy=None, verbose=True, bo_tuning=False, bo_kwargs=None,
+                         backward_passes_per_step=1):
+    """Wrap ``optimizer`` (``torch.optim.SGD`` / ``Adam`` / ``AdamW``) for DeAR data-parallel training of ``model``.
 
     Signature-compatible with the reference factory (dear/dear_dopt.py:381-398): the Horovod-era
     keyword arguments are accepted; those that have no meaning here are ignored.  Unlike the
     reference, ``threshold`` (MB; default 25) and ``num_nearby_layers`` are honoured instead of
     being module constants:  ``threshold=None, num_nearby_layers=k`` selects the nearby-layer
     policy (``k=1`` is "DeAR without tensor fusion").  ``bo_tuning=True`` enables the Bayesian
-    buffer-size tuner (the reference's separate ``dopt_rsag_bo`` module).
+    buffer-size tuner (the reference's separate ``dopt_rsag_bo`` module).  ``backward_passes_per_step=k``
+    (Horovod's name; not in the reference) accumulates gradients locally over k backward passes and
+    reduce-scatters them during the k-th; call ``step()`` once per k passes.
     """
     if threshold in (None, 0) and num_nearby_layers is None:
         threshold = float(os.environ.get("DEAR_THRESHOLD_MB", THRESHOLD))
@@ -519,7 +550,8 @@ def DistributedOptimizer(optimizer, model, compression=None, is_sparse=False, de
     cls = type(optimizer.__class__.__name__, (optimizer.__class__,), dict(_DistributedOptimizer.__dict__))
     opt = cls(optimizer.param_groups, model, threshold=threshold,
               num_nearby_layers=num_nearby_layers if num_nearby_layers is not None else NUM_NEARBY_LAYERS,
-              exclude_parts=exclude_parts, policy=policy, verbose=verbose)
+              exclude_parts=exclude_parts, policy=policy, verbose=verbose,
+              backward_passes_per_step=backward_passes_per_step)
     if bo_tuning:
         # dopt_rsag_bo: Bayesian optimisation of the fusion threshold (dear/dopt_rsag_bo.py:100-101)
         from .tuner import attach_tuner
