@@ -77,7 +77,8 @@ def main(argv=None):
     tasks = [(t.split(":")[0], int(t.split(":")[1])) for t in args.tasks.split(",")]
     gpus = [int(g) for g in args.gpus.split(",")]
     dtypes = args.dtypes.split(",")
-    os.makedirs(os.path.join(ROOT, "logs", args.prefix), exist_ok=True)
+    if not args.dry_run:
+        os.makedirs(os.path.join(ROOT, "logs", args.prefix), exist_ok=True)
     ledger = os.path.join(ROOT, "logs", args.prefix, "exp.log")        # resumable, like the reference (:86-99)
     done = set()
     if os.path.exists(ledger):
