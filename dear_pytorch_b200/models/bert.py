@@ -9,7 +9,6 @@ projections are one fused GEMM.
 """
 from __future__ import annotations
 
-import math
 from dataclasses import dataclass
 
 import os

@@ -1,6 +1,5 @@
 """PyTorch-DDP baseline (+ optional ZeRO-1), as pytorch-ddp/imagenet_benchmark.py:65-70 of the reference."""
 import torch
-import torch.distributed as dist
 
 from ... import runtime
 

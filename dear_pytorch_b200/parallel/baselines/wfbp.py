@@ -17,7 +17,6 @@ from __future__ import annotations
 
 from typing import Dict, List, Optional, Sequence
 
-import numpy as np
 import torch
 import torch.distributed as dist
 import torch.nn as nn

@@ -24,7 +24,7 @@ Layout differences (deliberate, B200-first):
 from __future__ import annotations
 
 from dataclasses import dataclass, field
-from typing import Dict, List, Optional, Sequence
+from typing import Dict, List, Sequence
 
 import torch
 import torch.nn as nn

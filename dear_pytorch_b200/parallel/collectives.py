@@ -10,7 +10,6 @@ symmetric staging buffer; on nccl/gloo they are torch.distributed calls.
 from __future__ import annotations
 
 import collections.abc
-from typing import Iterable
 
 import torch
 import torch.distributed as dist

@@ -10,7 +10,7 @@ barrier`` — every asynchronous op returns a handle.
 """
 from __future__ import annotations
 
-from typing import Callable, List, Optional, Sequence
+from typing import Callable, Sequence
 
 import torch
 import torch.distributed as dist

@@ -13,7 +13,6 @@ import time
 from typing import Dict, List, Optional
 
 import torch
-import torch.nn as nn
 
 from .. import runtime
 from .bucket import BucketPlan

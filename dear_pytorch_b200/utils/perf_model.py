@@ -8,7 +8,6 @@
 from __future__ import annotations
 
 import json
-import math
 import os
 
 import numpy as np

@@ -1,5 +1,4 @@
 """DeAR data-parallel SGD == single-process SGD on the concatenated batch."""
-import copy
 
 import pytest
 import torch

@@ -4,7 +4,6 @@ Numerics oracle: plain PyTorch fp32 SGD on the concatenated batch.  Multi-rank c
 process per rank; with a single GPU all ranks share cuda:0 (CUDA IPC works between processes on one
 device), with >= 2 GPUs each rank gets its own device and the data moves over NVLink.
 """
-import os
 
 import pytest
 import torch

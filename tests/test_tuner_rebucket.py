@@ -1,5 +1,4 @@
 """BO tuner behaviour and re-bucketing at the safe point."""
-import numpy as np
 import torch
 import torch.nn as nn
 
