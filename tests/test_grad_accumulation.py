@@ -5,6 +5,7 @@ import torch
 import torch.nn as nn
 
 from _mp import run_ranks
+from conftest import unvalidated
 from test_dear_equivalence import data, make_model, reference_run
 
 
@@ -53,6 +54,37 @@ def test_accumulation_equals_one_large_batch(backend, k):
     for params in run_ranks(worker, world=world, backend=backend, args=(case, steps, per_rank, k)):
         for a, b in zip(params, ref):
             torch.testing.assert_close(a, b, rtol=5e-5, atol=5e-6)
+
+
+def gpu_worker(rank, world, case, steps, per_rank, k):
+    import dear_pytorch_b200 as dear
+    dev = dear.device()
+    model = make_model().to(dev); model.eval()
+    opt = torch.optim.SGD(model.parameters(), lr=0.05, **case)
+    opt = dear.DistributedOptimizer(opt, model, threshold=0.001, verbose=False, backward_passes_per_step=k)
+    dear.broadcast_parameters(model.state_dict(), 0)
+    micro = per_rank // k
+    for t in range(steps):
+        x, y = data(t, world * per_rank)
+        x, y = x[rank * per_rank:(rank + 1) * per_rank].to(dev), y[rank * per_rank:(rank + 1) * per_rank].to(dev)
+        for j in range(k):
+            (nn.functional.cross_entropy(model(x[j * micro:(j + 1) * micro]), y[j * micro:(j + 1) * micro]) / k).backward()
+        opt.step()
+    opt.synchronize()
+    dear.communicator().check_status()
+    return [p.detach().cpu() for p in model.parameters()]
+
+
+@pytest.mark.gpu
+@unvalidated("gradient accumulation on the fused CUDA path")
+@pytest.mark.parametrize("world", [1, 2])
+def test_accumulation_on_gpu(world):
+    case = dict(momentum=0.9, weight_decay=1e-3)
+    ref = reference_run(case, 3, world, 4)
+    for params in run_ranks(gpu_worker, world=world, backend="b200", args=(case, 3, 4, 2),
+                            extra_env={"DEAR_SPIN_TIMEOUT_S": "15"}, timeout=300):
+        for a, b in zip(params, ref):
+            torch.testing.assert_close(a, b, rtol=2e-4, atol=5e-6)
 
 
 def unused_worker(rank, world, k):

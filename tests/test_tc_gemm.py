@@ -1,10 +1,9 @@
 """tcgen05 GEMMs with fused epilogues (csrc/tc_gemm*.cu) against plain PyTorch fp32 references."""
-import os
-
 import pytest
 import torch
 import torch.nn.functional as F
 
+from conftest import unvalidated
 from dear_pytorch_b200.ops.tc_gemm import fused_ffn, linear_bias, require_tc, tc_launches
 
 
@@ -71,9 +70,7 @@ def test_ffn_dgelu(M, K, N):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(not os.environ.get("DEAR_TC_EXPERIMENTAL"),
-                    reason="hand-written tcgen05 kernel (csrc/tc_ffn_hw.cu) has not been run on hardware yet; "
-                           "set DEAR_TC_EXPERIMENTAL=1 to exercise it")
+@unvalidated("the hand-written tcgen05 kernel (csrc/tc_ffn_hw.cu)")
 @pytest.mark.parametrize("M,K,N", [(128, 64, 256), (2048, 1024, 4096), (300, 72, 264), (1, 8, 8)])
 def test_handwritten_ffn_up(M, K, N):
     tc = require_tc()
