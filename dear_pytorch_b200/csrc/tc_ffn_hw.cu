@@ -20,7 +20,7 @@
 //
 // STATUS: compiles for sm_100a (ptxas-checked SASS contains UTCHMMA / UTMALDG / LDTM); NOT yet run on hardware
 // (written after the round's GPU budget was spent).  It is exported as `_tc.ffn_up_hw` and exercised only by
-// tests/test_tc_gemm.py::test_handwritten_ffn_up when DEAR_TC_EXPERIMENTAL=1; nothing calls it by default.
+// tests/test_tc_gemm.py::test_handwritten_ffn_up when DEAR_TEST_UNVALIDATED=1; nothing calls it by default.
 // Every mbarrier wait is bounded and traps instead of spinning forever.
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/cuda/CUDAGuard.h>
