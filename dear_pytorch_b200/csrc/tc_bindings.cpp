@@ -28,52 +28,13 @@ void* workspace(size_t bytes, int device) {
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 long launches() { return g_launches.load(); }
 
-std::vector<at::Tensor> ffn_up_v0(const at::Tensor& x, const at::Tensor& w, const at::Tensor& bias);
-std::vector<at::Tensor> ffn_up_v1(const at::Tensor& x, const at::Tensor& w, const at::Tensor& bias);
-std::vector<at::Tensor> ffn_up_v2(const at::Tensor& x, const at::Tensor& w, const at::Tensor& bias);
-std::vector<at::Tensor> ffn_up_v3(const at::Tensor& x, const at::Tensor& w, const at::Tensor& bias);
-std::vector<at::Tensor> ffn_up_v4(const at::Tensor& x, const at::Tensor& w, const at::Tensor& bias);
-at::Tensor ffn_dgelu_v0(const at::Tensor& dy, const at::Tensor& w, const at::Tensor& z);
-at::Tensor ffn_dgelu_v1(const at::Tensor& dy, const at::Tensor& w, const at::Tensor& z);
-at::Tensor ffn_dgelu_v2(const at::Tensor& dy, const at::Tensor& w, const at::Tensor& z);
-at::Tensor linear_bias_v0(const at::Tensor& x, const at::Tensor& w, const at::Tensor& bias);
-at::Tensor linear_bias_v1(const at::Tensor& x, const at::Tensor& w, const at::Tensor& bias);
-at::Tensor linear_bias_v2(const at::Tensor& x, const at::Tensor& w, const at::Tensor& bias);
-at::Tensor linear_bias_v3(const at::Tensor& x, const at::Tensor& w, const at::Tensor& bias);
-
 std::vector<at::Tensor> ffn_up_hw(const at::Tensor& x, const at::Tensor& w, const at::Tensor& bias);   // tc_ffn_hw.cu
 
 }  // namespace dear_tc
 
+#include "tc_variants.inc"   // declarations + tables of the generated configurations (tools/gen_tc_variants.py)
+
 namespace {
-
-template <class Fn>
-struct Variant {
-  Fn fn;
-  const char* config;
-};
-
-using Fn3V = std::vector<at::Tensor> (*)(const at::Tensor&, const at::Tensor&, const at::Tensor&);
-using Fn3T = at::Tensor (*)(const at::Tensor&, const at::Tensor&, const at::Tensor&);
-
-const Variant<Fn3V> k_ffn_up[] = {
-    {&dear_tc::ffn_up_v0, "tile/cluster/2sm=(256, 128, 2, 1, true) scheduler=default"},
-    {&dear_tc::ffn_up_v1, "tile/cluster/2sm=(256, 256, 2, 1, true) scheduler=default"},
-    {&dear_tc::ffn_up_v2, "tile/cluster/2sm=(128, 256, 1, 1, false) scheduler=default"},
-    {&dear_tc::ffn_up_v3, "tile/cluster/2sm=(256, 256, 2, 1, true) scheduler=StreamKScheduler"},
-    {&dear_tc::ffn_up_v4, "tile/cluster/2sm=(256, 128, 2, 2, true) scheduler=default"},
-};
-const Variant<Fn3T> k_ffn_dgelu[] = {
-    {&dear_tc::ffn_dgelu_v0, "tile/cluster/2sm=(256, 128, 2, 1, true) scheduler=default"},
-    {&dear_tc::ffn_dgelu_v1, "tile/cluster/2sm=(256, 256, 2, 1, true) scheduler=default"},
-    {&dear_tc::ffn_dgelu_v2, "tile/cluster/2sm=(128, 256, 1, 1, false) scheduler=default"},
-};
-const Variant<Fn3T> k_linear_bias[] = {
-    {&dear_tc::linear_bias_v0, "tile/cluster/2sm=(256, 128, 2, 1, true) scheduler=default"},
-    {&dear_tc::linear_bias_v1, "tile/cluster/2sm=(256, 256, 2, 1, true) scheduler=default"},
-    {&dear_tc::linear_bias_v2, "tile/cluster/2sm=(128, 128, 1, 1, false) scheduler=default"},
-    {&dear_tc::linear_bias_v3, "tile/cluster/2sm=(256, 128, 2, 1, true) scheduler=StreamKScheduler"},
-};
 
 template <class V, size_t N>
 const V& pick(const V (&table)[N], int variant, const char* op) {
