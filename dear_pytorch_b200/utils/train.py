@@ -17,6 +17,9 @@ parameter update; ``finish()`` — also run by ``optimizer.synchronize()`` / ``s
 the last pending update, so nothing is dropped at the end of training.  One visible difference: the
 update for batch *t* runs at the start of call *t+1*, so a learning-rate scheduler stepped between the
 two calls applies its new value one update earlier than in the natural loop.
+
+With ``bo_tuning=True`` the wrapper stays eager while the tuner explores (its timing and re-bucketing live
+in Python hooks) and captures the graph once the final bucket layout is in place.
 """
 from __future__ import annotations
 
@@ -101,6 +104,12 @@ class TrainStep:
         self._pending_update = True
         return loss
 
+    def _tuning_active(self) -> bool:
+        tuner = getattr(self.opt, "tuner", None)
+        if tuner is None or self._graph is not None:
+            return False
+        return (not tuner.finished) or bool(getattr(self._engine, "_safe_point_actions", None))
+
     def finish(self):
         """Rotated mode: apply the update of the last call's gradients (no-op otherwise)."""
         if self._pending_update:
@@ -153,6 +162,11 @@ class TrainStep:
         self._calls += 1
         if not self.use_graph:
             return self._eager(*batch)
+        if self._tuning_active():
+            # the Bayesian buffer-size tuner times iterations and re-buckets from Python hooks, which a replayed
+            # graph never runs: stay eager until it has settled, then warm up and capture the final layout
+            self._calls = 0
+            return self._eager_on_side_stream(batch)
         if self.overlap_update and not self._pending_update:
             # nothing to apply yet (first call, or right after finish()): the captured body starts with an
             # update, so prime it with a plain forward/backward

@@ -10,6 +10,7 @@ import torch
 import torch.nn as nn
 
 from _mp import run_ranks
+from conftest import unvalidated
 from test_dear_equivalence import CASES, data, make_model, reference_run
 
 pytestmark = pytest.mark.gpu
@@ -208,3 +209,38 @@ def test_rebucketing_on_gpu_migrates_sharded_state():
         assert len(set(layouts)) == 3 and layouts[-1] == 1
         for a, b in zip(params, ref):
             torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-5)
+
+
+def bo_graph_worker(rank, world):
+    import dear_pytorch_b200 as dear
+    from dear_pytorch_b200.utils.train import TrainStep
+    dev = dear.device()
+    torch.manual_seed(0)
+    model = nn.Sequential(nn.Linear(64, 256), nn.ReLU(), nn.Linear(256, 256), nn.ReLU(), nn.Linear(256, 10)).to(dev)
+    opt = torch.optim.SGD(model.parameters(), lr=0.05, momentum=0.9)
+    opt = dear.DistributedOptimizer(opt, model, threshold=0.05, verbose=False, bo_tuning=True,
+                                    bo_kwargs=dict(bound=(0.01, 1.0), max_num_steps=3, interval=4))
+    dear.broadcast_parameters(model.state_dict(), 0)
+    step = TrainStep(model, opt, nn.functional.cross_entropy, use_graph=True, graph_warmup=2)
+    g = torch.Generator().manual_seed(100 + rank)
+    captured_at = None
+    for t in range(40):
+        x = torch.randn(32, 64, generator=g).to(dev)
+        y = torch.randint(0, 10, (32,), generator=g).to(dev)
+        loss = float(step(x, y))
+        assert loss == loss
+        if captured_at is None and step._graph is not None:
+            captured_at = t
+            assert opt.tuner.finished
+    opt.synchronize()
+    dear.communicator().check_status()
+    return captured_at, opt.tuner.finished, len(opt.engine.plan.buckets)
+
+
+@pytest.mark.gpu
+@unvalidated("graph capture deferred until the BO tuner has settled")
+def test_graph_capture_waits_for_the_bo_tuner():
+    outs = run_ranks(bo_graph_worker, world=2, backend="b200", extra_env=_env(), timeout=300)
+    assert outs[0] == outs[1]
+    captured_at, finished, _ = outs[0]
+    assert finished and captured_at is not None and captured_at >= 12       # 3 trials x 4-iteration windows first
