@@ -127,13 +127,16 @@ def test_general_collectives():
         torch.testing.assert_close(res["sendrecv"], torch.full((9,), float((r + 1) % world)))
 
 
-def graph_worker(rank, world, use_graph, overlap=False):
+def graph_worker(rank, world, use_graph, overlap=False, adam=False):
     import dear_pytorch_b200 as dear
     from dear_pytorch_b200.utils.train import TrainStep
     dev = dear.device()
     torch.manual_seed(0)
     model = nn.Sequential(nn.Linear(64, 256), nn.ReLU(), nn.Linear(256, 256), nn.ReLU(), nn.Linear(256, 10)).to(dev)
-    opt = torch.optim.SGD(model.parameters(), lr=0.05, momentum=0.9, weight_decay=1e-4)
+    if adam:
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-2, weight_decay=1e-2)
+    else:
+        opt = torch.optim.SGD(model.parameters(), lr=0.05, momentum=0.9, weight_decay=1e-4)
     opt = dear.DistributedOptimizer(opt, model, threshold=0.05, verbose=False)
     dear.broadcast_parameters(model.state_dict(), 0)
     step = TrainStep(model, opt, nn.functional.cross_entropy, use_graph=use_graph, graph_warmup=2, overlap_update=overlap)
@@ -209,6 +212,17 @@ def test_rebucketing_on_gpu_migrates_sharded_state():
         assert len(set(layouts)) == 3 and layouts[-1] == 1
         for a, b in zip(params, ref):
             torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.gpu
+@unvalidated("AdamW inside a replayed CUDA graph (device-resident step counter)")
+def test_adamw_cuda_graph_matches_eager():
+    eager = run_ranks(graph_worker, world=2, backend="b200", args=(False, False, True), extra_env=_env(), timeout=300)
+    graph = run_ranks(graph_worker, world=2, backend="b200", args=(True, True, True), extra_env=_env(), timeout=300)
+    for (le, pe, _), (lg, pg, _) in zip(eager, graph):
+        torch.testing.assert_close(torch.tensor(lg), torch.tensor(le), rtol=1e-4, atol=1e-5)
+        for a, b in zip(pg, pe):
+            torch.testing.assert_close(a, b, rtol=2e-4, atol=2e-5)
 
 
 def bo_graph_worker(rank, world):

@@ -9,5 +9,5 @@ echo "=== hand-written tcgen05 kernel"; timeout 120 python -m pytest tests/test_
 echo "=== its speed vs cuBLAS + GELU and the CUTLASS-collective variants"; timeout 200 python tools/bert_ops_bench.py --sections gemm --json gpurun_out/bert_ops_bench_hw.json 2>&1 | grep -E "up_gelu|up_gemm|failed"
 echo "=== engine on the nccl backend (world 1), gradient accumulation on the fused path"
 timeout 300 python -m pytest tests/test_gpu_nccl_backend.py tests/test_grad_accumulation.py -m gpu -q --timeout 150 2>&1 | tail -8
-echo "=== graph capture deferred until the BO tuner has settled"; timeout 300 python -m pytest tests/test_gpu_fused.py -m gpu -q --timeout 250 -k bo_tuner 2>&1 | tail -6
+echo "=== graph capture deferred until the BO tuner has settled"; timeout 300 python -m pytest tests/test_gpu_fused.py -m gpu -q --timeout 250 -k 'bo_tuner or adamw' 2>&1 | tail -6
 echo "=== done"
