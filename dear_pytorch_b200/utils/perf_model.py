@@ -108,3 +108,34 @@ def ag_roofline_us(bucket_bytes: int, world: int, elem_bytes: int = 4, momentum:
     t_hbm = hbm / (pk["hbm_gbs"] * 1e3)
     t_link = link / (pk["nvlink_gbs_per_dir"] * 1e3)
     return {"hbm_us": t_hbm, "nvlink_us": t_link, "bound_us": max(t_hbm, t_link)}
+
+
+# ---- (3) alpha-beta model of the fused kernels, fitted to the measured sweep -----------------------
+def fit_alpha_beta(rows, key: str):
+    """Least-squares ``time = alpha + beta * bytes`` over a ``tools/kernel_bench.py`` sweep (alpha in s, beta in s/byte)."""
+    xs = [r["bucket_mb"] * 2 ** 20 for r in rows if key in r]
+    ys = [r[key] * 1e-6 for r in rows if key in r]
+    n = len(xs)
+    if n < 2:
+        raise ValueError("need at least two bucket sizes to fit alpha and beta")
+    mx, my = sum(xs) / n, sum(ys) / n
+    beta = sum((x - mx) * (y - my) for x, y in zip(xs, ys)) / sum((x - mx) ** 2 for x in xs)
+    return max(my - beta * mx, 0.0), beta
+
+
+def fused_kernel_model(path: str = None) -> dict:
+    """alpha-beta of Kernel A / Kernel B and of NCCL's reduce-scatter / all-gather on this machine, from the committed
+    8-GPU sweep (``profiles/kernel_bench_p8_ipc.json``) — the counterpart of the reference's hard-coded per-cluster
+    tables (``dear/utils.py:62-104``), which MG-WFBP style planners (baselines/wfbp.py: mgwfbp_groups) consume."""
+    root = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    path = path or os.path.join(root, "profiles", "kernel_bench_p8_ipc.json")
+    with open(path) as f:
+        rows = json.load(f)["rows"]
+    out = {"world": rows[0].get("world"), "source": os.path.basename(path)}
+    for name, key in (("reduce_scatter", "rs_us"), ("allgather_update", "ag_sgd_us"), ("nccl_reduce_scatter", "nccl_rs_us"),
+                      ("nccl_all_gather", "nccl_ag_us")):
+        try:
+            out[name] = fit_alpha_beta(rows, key)
+        except (ValueError, ZeroDivisionError):
+            pass
+    return out

@@ -57,3 +57,17 @@ def test_efsign_residual():
     g = torch.tensor([0.2, -3.0, 0.5])
     c.compress(g.clone(), "w")
     torch.testing.assert_close(c.residuals["w"], g - torch.sign(g))
+
+
+def test_alpha_beta_fit_of_the_measured_kernel_sweep():
+    from dear_pytorch_b200.utils.perf_model import fit_alpha_beta, fused_kernel_model
+    rows = [{"bucket_mb": mb, "t_us": 20.0 + 1.5 * mb} for mb in (1, 4, 24, 64)]
+    a, b = fit_alpha_beta(rows, "t_us")
+    assert abs(a - 20e-6) < 1e-9 and abs(b * 2 ** 20 - 1.5e-6) < 1e-12
+    m = fused_kernel_model()                        # profiles/kernel_bench_p8_ipc.json
+    assert m["world"] == 8
+    # launch + two flag round trips: tens of microseconds; slope between 0.77 and 0.4 of the measured NVLink bandwidth
+    for k in ("reduce_scatter", "allgather_update"):
+        alpha, beta = m[k]
+        assert 5e-6 < alpha < 60e-6 and 1.0e-6 < beta * 2 ** 20 < 3.0e-6
+    assert m["reduce_scatter"][0] < m["nccl_reduce_scatter"][0]      # lower latency than NCCL on small buckets
