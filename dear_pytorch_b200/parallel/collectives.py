@@ -132,15 +132,23 @@ def broadcast_optimizer_state(optimizer: torch.optim.Optimizer, root_rank: int =
     for group in optimizer.param_groups:
         for p in group["params"]:
             st = optimizer.state.get(p, {})
-            keys = runtime.broadcast_object(sorted(k for k, v in st.items()), src=root_rank)
-            for k in keys:
-                v = st.get(k)
-                if torch.is_tensor(v):
+            # the root decides which entries exist and what they look like: a rank that has not stepped yet
+            # (fresh start next to a resumed root) has no state and must allocate before it can receive
+            meta = None
+            if runtime.rank() == root_rank:
+                meta = [(k, (tuple(v.shape), v.dtype) if torch.is_tensor(v) else None) for k, v in sorted(st.items())]
+            meta = runtime.broadcast_object(meta, src=root_rank)
+            for k, tinfo in meta:
+                if tinfo is not None:
+                    v = st.get(k)
+                    if not torch.is_tensor(v) or tuple(v.shape) != tinfo[0] or v.dtype != tinfo[1]:
+                        v = torch.zeros(tinfo[0], dtype=tinfo[1], device=p.device)
+                        st[k] = v
                     broadcast_(v, root_rank)
                 else:
-                    st[k] = runtime.broadcast_object(v, src=root_rank)
-                if p not in optimizer.state:
-                    optimizer.state[p] = st
+                    st[k] = runtime.broadcast_object(st.get(k), src=root_rank)
+            if meta and p not in optimizer.state:
+                optimizer.state[p] = st
 
 
 def allgather(tensor: torch.Tensor) -> torch.Tensor:

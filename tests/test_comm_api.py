@@ -181,3 +181,27 @@ def test_backend_selection_single_and_multi_node():
         select_backend("b200", True, 16, 8)
     with pytest.raises(ValueError):
         select_backend("mpi", True, 8, 8)
+
+
+def bos_worker(rank, world):
+    import dear_pytorch_b200 as dear
+    import torch.nn as nn
+    torch.manual_seed(rank)                       # different initial weights per rank
+    model = nn.Linear(5, 3)
+    opt = torch.optim.SGD(model.parameters(), lr=0.1 * (rank + 1), momentum=0.9)
+    if rank == 0:                                 # only the root has optimizer state (e.g. it resumed a checkpoint)
+        model(torch.ones(2, 5)).sum().backward()
+        opt.step()
+    dear.broadcast_parameters(model.state_dict(), 0)
+    dear.broadcast_optimizer_state(opt, 0)
+    bufs = [opt.state[p]["momentum_buffer"].clone() for p in model.parameters()]
+    return opt.param_groups[0]["lr"], bufs, [p.detach().clone() for p in model.parameters()]
+
+
+def test_broadcast_optimizer_state_to_a_rank_without_state():
+    outs = run_ranks(bos_worker, world=2, backend="gloo")
+    assert outs[0][0] == outs[1][0] == 0.1
+    for a, b in zip(outs[0][1], outs[1][1]):
+        assert torch.equal(a, b) and a.abs().sum() > 0
+    for a, b in zip(outs[0][2], outs[1][2]):
+        assert torch.equal(a, b)
