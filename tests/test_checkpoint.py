@@ -60,3 +60,45 @@ def test_save_resume_matches_uninterrupted_training(backend):
               "param_groups": ckpt["optimizer"]["param_groups"]}
         sgd.load_state_dict(sd)
         assert len(sgd.state) == len(list(m.parameters()))
+
+
+def save_worker(rank, world, path, steps, per_rank):
+    import dear_pytorch_b200 as dear
+    model = make_model(); model.eval()
+    opt = dear.DistributedOptimizer(torch.optim.SGD(model.parameters(), lr=0.05, **CASE), model, threshold=0.001, verbose=False)
+    dear.broadcast_parameters(model.state_dict(), 0)
+    for t in range(steps):
+        x, y = data(t, world * per_rank)
+        opt.zero_grad()
+        nn.functional.cross_entropy(model(x[rank * per_rank:(rank + 1) * per_rank]), y[rank * per_rank:(rank + 1) * per_rank]).backward()
+        opt.step()
+    dear.save_checkpoint(path, model, opt)
+    return True
+
+
+def resume_worker(rank, world, path, t0, steps, global_batch):
+    import dear_pytorch_b200 as dear
+    per_rank = global_batch // world
+    model = make_model(seed=77); model.eval()
+    opt = dear.DistributedOptimizer(torch.optim.SGD(model.parameters(), lr=0.5), model, threshold=0.002, verbose=False)
+    dear.load_checkpoint(path, model, opt)
+    for t in range(t0, t0 + steps):
+        x, y = data(t, global_batch)
+        opt.zero_grad()
+        nn.functional.cross_entropy(model(x[rank * per_rank:(rank + 1) * per_rank]), y[rank * per_rank:(rank + 1) * per_rank]).backward()
+        opt.step()
+    opt.synchronize()
+    return [p.detach().clone() for p in model.parameters()]
+
+
+def test_resume_on_a_different_world_size():
+    """Momentum and parameters are saved per parameter name, so a checkpoint written by 2 ranks resumes on 4 (and the
+    sharding 1/2 -> 1/4 changes underneath); same global batch, so the run equals the uninterrupted one."""
+    global_batch, steps_a, steps_b = 8, 3, 3
+    ref = reference_run(CASE, steps_a + steps_b, 2, global_batch // 2)
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "ckpt.pt")
+        run_ranks(save_worker, world=2, backend="emu", args=(path, steps_a, global_batch // 2))
+        for params in run_ranks(resume_worker, world=4, backend="emu", args=(path, steps_a, steps_b, global_batch)):
+            for a, b in zip(params, ref):
+                torch.testing.assert_close(a, b, rtol=3e-5, atol=3e-6)
