@@ -323,6 +323,8 @@ class DearEngine:
 
     # ------------------------------------------------------------------ step
     def step(self):
+        if self.backend is None:
+            raise RuntimeError("this DistributedOptimizer was closed (engine.close()): its buckets are released")
         be = self.backend
         nb = len(self.plan.buckets)
         if not self.exclude_reducescatter:
@@ -381,6 +383,8 @@ class DearEngine:
 
     def synchronize(self, host: bool = True):
         """Make all outstanding updates visible to the current stream (and the host)."""
+        if self.backend is None:           # closed: everything was synchronised and handed back in close()
+            return
         if self._any_pending:
             self.backend.wait_all()
             self._pending = [False] * len(self._pending)
@@ -464,9 +468,18 @@ class DearEngine:
         for h in self._hooks:
             h.remove()
         self._hooks.clear()
-        self.synchronize(host=True)
+        self.flush()                       # deferred updates of a rotated training loop, then wait for everything
         if getattr(self, "timeline", None) is not None:
             self.timeline.close()
+        # Hand the parameters back: they are views of the (symmetric) parameter buckets, which must be released before
+        # the communicator — and with it the rendezvous store — can go away (runtime.shutdown, re-initialisation).
+        with torch.no_grad():
+            for s in self.plan.slots:
+                s.param.data = s.param.data.clone(memory_format=torch.preserve_format)
+                s.param.grad = None
+        self._inflight.clear()
+        self._grad_view = {}
+        self.backend = None
 
 
 # =====================================================================================

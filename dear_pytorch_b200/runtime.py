@@ -93,7 +93,9 @@ def init(backend: Optional[str] = None, device: Optional[torch.device] = None, *
     else:
         device = torch.device("cpu")
 
-    owns_pg = False
+    global _kept_pg
+    owns_pg = _kept_pg and dist.is_initialized()       # a group this module created and kept over a shutdown()
+    _kept_pg = False
     group = None
     store = None
     if world > 1 or dist.is_initialized():
@@ -137,11 +139,19 @@ def init(backend: Optional[str] = None, device: Optional[torch.device] = None, *
         o.rs_grid = _env_int("DEAR_RS_GRID", 128 if world == 1 else 32)
         o.ag_grid = _env_int("DEAR_AG_GRID", 128 if world == 1 else 32)
         o.gen_grid = _env_int("DEAR_GEN_GRID", 8)
-        comm = C.Communicator(rank, world, store, "dear%d" % _env_int("DEAR_JOB_SEQ", 0), o)
+        # rendezvous keys must be unique per init(): a re-initialised process group can land on the SAME TCPStore server
+        # (multi-tenant stores are shared per port), where the previous communicator's barrier counters still exist
+        global _init_seq
+        _init_seq += 1
+        comm = C.Communicator(rank, world, store, "dear%d_%d" % (_env_int("DEAR_JOB_SEQ", 0), _init_seq), o)
         opts = dict(provider=prov, multicast=o.multicast, rs_grid=o.rs_grid, ag_grid=o.ag_grid)
 
     _state = _State(backend=backend, rank=rank, world=world, local_rank=local_rank, local_size=local_size,
                     device=device, comm=comm, group=group, owns_pg=owns_pg, options=opts)
+
+
+_kept_pg = False       # shutdown(destroy_process_group=False) left a group that this module owns
+_init_seq = 0          # init() calls that created a native communicator in this process (identical on every rank)
 
 
 def select_backend(requested: Optional[str], use_cuda: bool, world: int, local_size: int, verbose: bool = False) -> str:
@@ -167,8 +177,13 @@ def select_backend(requested: Optional[str], use_cuda: bool, world: int, local_s
     return requested
 
 
-def shutdown() -> None:
-    """Tear the runtime down (streams, arenas, process group)."""
+def shutdown(destroy_process_group: bool = True) -> None:
+    """Tear the runtime down (streams, arenas, process group).
+
+    To re-initialise inside the same process pass ``destroy_process_group=False``: the next ``init()`` then reuses the
+    ``torch.distributed`` group (re-creating one on the same MASTER_PORT races with peers that still see the old
+    rendezvous store), while the native communicator, its streams and every symmetric arena are released — provided the
+    engines were closed first (``optimizer.engine.close()`` hands the parameters back from the buckets)."""
     global _state
     if _state is None:
         return
@@ -176,11 +191,22 @@ def shutdown() -> None:
     try:
         if st.comm is not None:
             st.comm.synchronize()
+        if st.owns_pg and destroy_process_group and dist.is_initialized() and st.world > 1:
+            # leave together: rank 0 hosts the rendezvous store, and a later init() in the same process re-creates it
+            # on the same port — a rank still inside the old group would see its connection reset
+            try:
+                dist.barrier(group=st.group)
+            except Exception:      # a peer already died: tear down anyway
+                pass
     finally:
         _state = None
         st.comm = None
         if st.owns_pg and dist.is_initialized():
-            dist.destroy_process_group()
+            if destroy_process_group:
+                dist.destroy_process_group()
+            else:
+                global _kept_pg
+                _kept_pg = True
 
 
 def rank() -> int:
