@@ -91,3 +91,38 @@ def test_unused_parameters_do_not_hang_or_move(backend):
     assert outs[0][0] and outs[1][0]
     for a, b in zip(outs[0][1], outs[1][1]):
         assert torch.equal(a, b)
+
+
+def frozen_worker(rank, world, steps, per):
+    import dear_pytorch_b200 as dear
+    from test_dear_equivalence import data, make_model
+    m = make_model(); m.eval()
+    for p in m[0].parameters():
+        p.requires_grad_(False)
+    opt = torch.optim.SGD([p for p in m.parameters() if p.requires_grad], lr=0.05, momentum=0.9, weight_decay=1e-3)
+    opt = dear.DistributedOptimizer(opt, m, threshold=0.001, verbose=False)
+    dear.broadcast_parameters(m.state_dict(), 0)
+    for t in range(steps):
+        x, y = data(t, world * per)
+        opt.zero_grad()
+        nn.functional.cross_entropy(m(x[rank * per:(rank + 1) * per]), y[rank * per:(rank + 1) * per]).backward()
+        opt.step()
+    opt.synchronize()
+    return [p.detach().clone() for p in m.parameters()]
+
+
+@pytest.mark.parametrize("backend", ["gloo", "emu"])
+def test_frozen_parameters_stay_out_of_the_buckets(backend):
+    from test_dear_equivalence import data, make_model
+    ref = make_model(); ref.eval()
+    for p in ref[0].parameters():
+        p.requires_grad_(False)
+    opt = torch.optim.SGD([p for p in ref.parameters() if p.requires_grad], lr=0.05, momentum=0.9, weight_decay=1e-3)
+    for t in range(3):
+        x, y = data(t, 8)
+        opt.zero_grad()
+        nn.functional.cross_entropy(ref(x), y).backward()
+        opt.step()
+    for params in run_ranks(frozen_worker, world=2, backend=backend, args=(3, 4)):
+        for a, b in zip(params, ref.parameters()):
+            torch.testing.assert_close(a, b.detach(), rtol=3e-5, atol=3e-6)
