@@ -1,0 +1,57 @@
+"""Small utilities: clock-sample summary (bench.py's `clocks` field), the input prefetcher on a CPU device, the ncu
+launch-list aggregator."""
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_clock_sampler_summary_and_missing_nvidia_smi():
+    from dear_pytorch_b200.utils.clocks import ClockSampler
+    s = ClockSampler()
+    now = time.time()
+    s.rows = [(now - 3, 1965.0, 1965.0, 310.0, ["Not Active"] * 4),
+              (now - 2, 1950.0, 1965.0, 320.0, ["Not Active", "Not Active", "Not Active", "Active"]),
+              (now - 1, 1965.0, 1965.0, 300.0, ["Not Active"] * 4)]
+    out = s.summary()
+    assert out["sm_mhz"] == 1965.0 and out["sm_max_mhz"] == 1965.0 and out["reasons"] == ["sw_power_cap"] and out["samples"] == 3
+    assert s.summary(now - 1.5, now)["samples"] == 1
+    empty = ClockSampler()
+    assert empty.summary()["samples"] == 0
+    empty.start()          # no nvidia-smi on the CPU box: must not raise
+    empty.stop()
+
+
+def test_prefetcher_on_cpu_yields_batches_in_order():
+    from dear_pytorch_b200.utils.data import PinnedPrefetcher, SyntheticImages
+    src = SyntheticImages(2, image_size=8, num_classes=5, n_buffers=3)
+    feed = PinnedPrefetcher(iter(src), torch.device("cpu"), depth=2)
+    got = [next(feed) for _ in range(5)]
+    for i, (x, y) in enumerate(got):
+        ex, ey = src.batches[i % 3]
+        assert torch.equal(x, ex) and torch.equal(y, ey)
+    finite = PinnedPrefetcher(iter(src.batches[:2]), torch.device("cpu"))
+    assert len(list(finite)) == 2
+
+
+def test_ncu_launch_list_aggregation():
+    csv = ('"ID","Process ID","Process Name","Host Name","Kernel Name","Context","Stream","Block Size","Grid Size","Device",'
+           '"CC","Section Name","Metric Name","Metric Unit","Metric Value"\n'
+           '"0","1","python","h","dear::rs_kernel<float, 1, false>(dear::RSParams)","1","7","(512, 1, 1)","(128, 1, 1)","0","10.0","X","gpu__time_duration.sum","us","10.0"\n'
+           '"1","1","python","h","dear::rs_kernel<float, 1, false>(dear::RSParams)","1","7","(512, 1, 1)","(128, 1, 1)","0","10.0","X","gpu__time_duration.sum","us","14.0"\n'
+           '"2","1","python","h","void cudnn::conv(float*)","1","7","(256, 1, 1)","(64, 1, 1)","0","10.0","X","gpu__time_duration.sum","ns","6000"\n')
+    with tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False) as f:
+        f.write("==PROF== Connected\n" + csv)
+        path = f.name
+    try:
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), path], capture_output=True, text=True,
+                             check=True).stdout
+    finally:
+        os.unlink(path)
+    assert "total 30.0 us over 3 launches" in out
+    assert "dear::rs_kernel" in out and "n=   2" in out and "80.0%" in out
