@@ -295,8 +295,12 @@ def run_dear(args):
             "data": "synthetic", "impl": "dear", "config": cfg, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(out), flush=True)
-    step.finish()                 # rotated loop: the last update is applied here (outside every timed region)
-    opt.engine.close()
+    try:
+        step.finish()             # rotated loop: the last update is applied here (outside every timed region)
+        opt.engine.close()
+    except Exception:             # the measurement is complete and printed: a teardown problem must not void it
+        import traceback
+        traceback.print_exc()
     dear.shutdown()
     return 0
 
