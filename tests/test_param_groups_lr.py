@@ -126,3 +126,37 @@ def test_frozen_parameters_stay_out_of_the_buckets(backend):
     for params in run_ranks(frozen_worker, world=2, backend=backend, args=(3, 4)):
         for a, b in zip(params, ref.parameters()):
             torch.testing.assert_close(a, b.detach(), rtol=3e-5, atol=3e-6)
+
+
+def sched_worker(rank, world):
+    import dear_pytorch_b200 as dear
+    from test_dear_equivalence import data, make_model
+    m = make_model(); m.eval()
+    opt = dear.DistributedOptimizer(torch.optim.SGD(m.parameters(), lr=0.1, momentum=0.9), m, threshold=0.001, verbose=False)
+    sch = torch.optim.lr_scheduler.StepLR(opt, step_size=2, gamma=0.5)          # wraps optimizer.step like for any optimizer
+    dear.broadcast_parameters(m.state_dict(), 0)
+    for t in range(6):
+        x, y = data(t, 4 * world)
+        opt.zero_grad()
+        nn.functional.cross_entropy(m(x[rank * 4:(rank + 1) * 4]), y[rank * 4:(rank + 1) * 4]).backward()
+        opt.step()
+        sch.step()
+    opt.synchronize()
+    return [p.detach().clone() for p in m.parameters()]
+
+
+@pytest.mark.parametrize("backend", ["gloo", "emu"])
+def test_torch_lr_scheduler_drives_the_fused_update(backend):
+    from test_dear_equivalence import data, make_model
+    ref = make_model(); ref.eval()
+    opt = torch.optim.SGD(ref.parameters(), lr=0.1, momentum=0.9)
+    sch = torch.optim.lr_scheduler.StepLR(opt, step_size=2, gamma=0.5)
+    for t in range(6):
+        x, y = data(t, 8)
+        opt.zero_grad()
+        nn.functional.cross_entropy(ref(x), y).backward()
+        opt.step()
+        sch.step()
+    for params in run_ranks(sched_worker, world=2, backend=backend):
+        for a, b in zip(params, ref.parameters()):
+            torch.testing.assert_close(a, b.detach(), rtol=3e-5, atol=3e-6)
