@@ -29,6 +29,7 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 long launches() { return g_launches.load(); }
 
 std::vector<at::Tensor> ffn_up_hw(const at::Tensor& x, const at::Tensor& w, const at::Tensor& bias);   // tc_ffn_hw.cu
+at::Tensor ffn_dgelu_hw(const at::Tensor& dy, const at::Tensor& wt, const at::Tensor& z);
 
 }  // namespace dear_tc
 
@@ -68,5 +69,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     "kernel configurations compiled for each op (index = `variant`)");
   m.def("ffn_up_hw", &dear_tc::ffn_up_hw, py::arg("x"), py::arg("w"), py::arg("bias"),
         "EXPERIMENTAL hand-written tcgen05 kernel (two-warpgroup epilogue): H, Z = gelu(X W^T + b), X W^T + b");
+  m.def("ffn_dgelu_hw", &dear_tc::ffn_dgelu_hw, py::arg("dy"), py::arg("wt"), py::arg("z"),
+        "EXPERIMENTAL hand-written tcgen05 kernel: dZ = (dY Wt^T) * gelu'(Z), Wt = transposed down-projection weight [N, K]");
   m.def("launches", &dear_tc::launches);
 }

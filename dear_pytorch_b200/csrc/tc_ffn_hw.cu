@@ -1,6 +1,8 @@
-// tc_ffn_hw.cu — hand-written tcgen05 GEMM + bias + GELU with a TWO-WARPGROUP epilogue.
+// tc_ffn_hw.cu — hand-written tcgen05 GEMMs for the transformer FFN with a TWO-WARPGROUP epilogue.
 //
-//     H = gelu(Z),  Z = X W^T + b        X [M,K], W [N,K], b [N]  (bf16, fp32 accumulate)  ->  H, Z [M,N] bf16
+//     ffn_up_hw    : H = gelu(Z),  Z = X W^T + b      X [M,K], W [N,K], b [N]  (bf16, fp32 accumulate)  ->  H, Z [M,N]
+//     ffn_dgelu_hw : dZ = (dY Wt^T) * gelu'(Z)        dY [M,K], Wt [N,K] (= transposed down-projection weight), Z [M,N]
+//   (one kernel template, two epilogue modes; both operands K-major)
 //
 // Why this kernel exists: the CUTLASS-collective variants (tc_gemm.h) run the same op but are
 // epilogue-issue-bound — ncu (profiles/prof_bert_ops_summary.md) shows the tensor pipe falling from 59 %
@@ -19,8 +21,8 @@
 //               arrive on "accumulator empty" so the MMA warp can start tile i+2 while tile i drains
 //
 // STATUS: compiles for sm_100a (ptxas-checked SASS contains UTCHMMA / UTMALDG / LDTM); NOT yet run on hardware
-// (written after the round's GPU budget was spent).  It is exported as `_tc.ffn_up_hw` and exercised only by
-// tests/test_tc_gemm.py::test_handwritten_ffn_up when DEAR_TEST_UNVALIDATED=1; nothing calls it by default.
+// (written after the round's GPU budget was spent).  Exported as `_tc.ffn_up_hw` / `_tc.ffn_dgelu_hw`, exercised only by
+// tests/test_tc_gemm.py::test_handwritten_* when DEAR_TEST_UNVALIDATED=1; nothing calls it by default.
 // Every mbarrier wait is bounded and traps instead of spinning forever.
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/cuda/CUDAGuard.h>
@@ -169,16 +171,35 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return x * (x < 0.f ? q : 1.0f - q);
 }
 
+// d/dz [z Phi(z)] = Phi(z) + z phi(z); phi shares exp(-z^2/2) with the tail
+__device__ __forceinline__ float dgelu_fast(float z) {
+  const float az = fabsf(z);
+  const float e = __expf(-0.5f * z * z);
+  const float t = __fdividef(1.0f, fmaf(0.3275911f * 0.70710678118654752440f, az, 1.0f));
+  float p = 1.061405429f;
+  p = fmaf(p, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float q = 0.5f * p * t * e;
+  return fmaf(z, 0.39894228040143267794f * e, z < 0.f ? q : 1.0f - q);
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
 // -------------------------------------------------------------------------------------------- kernel
+// MODE_UP   : aux = bias [N];      out0 = H = gelu(acc + bias), out1 = Z = acc + bias
+// MODE_DGELU: aux = Z [M,N] (read); out0 = dZ = acc * gelu'(Z),  out1 unused
+enum EpilogueMode { MODE_UP = 0, MODE_DGELU = 1 };
+
+template <int MODE>
 __global__ void __launch_bounds__(kNumThreads, 1)
-ffn_up_hw_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 const __nv_bfloat16* __restrict__ bias, __nv_bfloat16* __restrict__ h_out, __nv_bfloat16* __restrict__ z_out,
-                 int M, int N, int K) {
+ffn_hw_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+              const __nv_bfloat16* __restrict__ aux, __nv_bfloat16* __restrict__ out0, __nv_bfloat16* __restrict__ out1,
+              int M, int N, int K) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
@@ -273,19 +294,32 @@ ffn_up_hw_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         for (int j = 0; j < 4; ++j) {                                  // 8 columns = one 16-byte vector of bf16
           const int cj = gcol + j * 8;
           if (cj < N) {                                                // N % 8 == 0: a vector is all-in or all-out
-            const uint4 bv = __ldg(reinterpret_cast<const uint4*>(bias + cj));
-            const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
-            uint32_t zq[4], hq[4];
+            if (MODE == MODE_UP) {
+              const uint4 bv = __ldg(reinterpret_cast<const uint4*>(aux + cj));
+              const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+              uint32_t zq[4], hq[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float b0 = __uint_as_float(bw[i] << 16), b1 = __uint_as_float(bw[i] & 0xffff0000u);
-              const float z0 = __uint_as_float(v[j * 8 + 2 * i]) + b0, z1 = __uint_as_float(v[j * 8 + 2 * i + 1]) + b1;
-              zq[i] = pack_bf16(z0, z1);
-              hq[i] = pack_bf16(gelu_fast(z0), gelu_fast(z1));
-            }
-            if (row < M) {
-              *reinterpret_cast<uint4*>(z_out + row_off + cj) = make_uint4(zq[0], zq[1], zq[2], zq[3]);
-              *reinterpret_cast<uint4*>(h_out + row_off + cj) = make_uint4(hq[0], hq[1], hq[2], hq[3]);
+              for (int i = 0; i < 4; ++i) {
+                const float b0 = __uint_as_float(bw[i] << 16), b1 = __uint_as_float(bw[i] & 0xffff0000u);
+                const float z0 = __uint_as_float(v[j * 8 + 2 * i]) + b0, z1 = __uint_as_float(v[j * 8 + 2 * i + 1]) + b1;
+                zq[i] = pack_bf16(z0, z1);
+                hq[i] = pack_bf16(gelu_fast(z0), gelu_fast(z1));
+              }
+              if (row < M) {
+                *reinterpret_cast<uint4*>(out1 + row_off + cj) = make_uint4(zq[0], zq[1], zq[2], zq[3]);
+                *reinterpret_cast<uint4*>(out0 + row_off + cj) = make_uint4(hq[0], hq[1], hq[2], hq[3]);
+              }
+            } else if (row < M) {                                      // (per-lane predicate: no collective below)
+              const uint4 zv = __ldg(reinterpret_cast<const uint4*>(aux + row_off + cj));
+              const uint32_t zw[4] = {zv.x, zv.y, zv.z, zv.w};
+              uint32_t dq[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float z0 = __uint_as_float(zw[i] << 16), z1 = __uint_as_float(zw[i] & 0xffff0000u);
+                dq[i] = pack_bf16(__uint_as_float(v[j * 8 + 2 * i]) * dgelu_fast(z0),
+                                  __uint_as_float(v[j * 8 + 2 * i + 1]) * dgelu_fast(z1));
+              }
+              *reinterpret_cast<uint4*>(out0 + row_off + cj) = make_uint4(dq[0], dq[1], dq[2], dq[3]);
             }
           }
         }
@@ -338,12 +372,34 @@ static CUtensorMap make_tmap(const void* base, int64_t rows, int64_t cols, int b
 
 }  // namespace hw
 
+static void check_bf16(const at::Tensor& t, const char* what) {
+  TORCH_CHECK(t.is_cuda() && t.scalar_type() == at::kBFloat16 && t.is_contiguous() &&
+              reinterpret_cast<uintptr_t>(t.data_ptr()) % 16 == 0, what, ": contiguous 16-byte aligned CUDA bf16 tensor expected");
+}
+
+template <int MODE>
+static void launch_hw(const at::Tensor& a, const at::Tensor& b, const __nv_bfloat16* aux, at::Tensor& out0, at::Tensor* out1,
+                      int M, int N, int K) {
+  const CUtensorMap ta = hw::make_tmap(a.data_ptr(), M, K, hw::kTileM);
+  const CUtensorMap tb = hw::make_tmap(b.data_ptr(), N, K, hw::kTileN);
+  static std::once_flag attr_once;
+  std::call_once(attr_once, [] {
+    C10_CUDA_CHECK(cudaFuncSetAttribute(hw::ffn_hw_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, hw::kSmemBytes));
+  });
+  const int tiles = ((M + hw::kTileM - 1) / hw::kTileM) * ((N + hw::kTileN - 1) / hw::kTileN);
+  const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
+  const int grid = std::min(tiles, sms);
+  auto stream = at::cuda::getCurrentCUDAStream().stream();
+  hw::ffn_hw_kernel<MODE><<<grid, hw::kNumThreads, hw::kSmemBytes, stream>>>(
+      ta, tb, aux, reinterpret_cast<__nv_bfloat16*>(out0.data_ptr()),
+      out1 != nullptr ? reinterpret_cast<__nv_bfloat16*>(out1->data_ptr()) : nullptr, M, N, K);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+  count_launch();
+}
+
 // H, Z = gelu(X W^T + b), X W^T + b      (experimental: see the header of this file)
 std::vector<at::Tensor> ffn_up_hw(const at::Tensor& x, const at::Tensor& w, const at::Tensor& bias) {
-  for (const at::Tensor* t : {&x, &w, &bias}) {
-    TORCH_CHECK(t->is_cuda() && t->scalar_type() == at::kBFloat16 && t->is_contiguous() &&
-                reinterpret_cast<uintptr_t>(t->data_ptr()) % 16 == 0, "ffn_up_hw: contiguous 16-byte aligned CUDA bf16 tensors expected");
-  }
+  check_bf16(x, "ffn_up_hw x"); check_bf16(w, "ffn_up_hw w"); check_bf16(bias, "ffn_up_hw bias");
   TORCH_CHECK(x.dim() == 2 && w.dim() == 2 && x.size(1) == w.size(1) && bias.numel() == w.size(0), "ffn_up_hw: shape mismatch");
   const int M = x.size(0), K = x.size(1), N = w.size(0);
   TORCH_CHECK(K % 8 == 0 && N % 8 == 0, "ffn_up_hw: K and N must be multiples of 8");
@@ -351,22 +407,23 @@ std::vector<at::Tensor> ffn_up_hw(const at::Tensor& x, const at::Tensor& w, cons
   auto h = at::empty({M, N}, x.options());
   auto z = at::empty({M, N}, x.options());
   if (M == 0) return {h, z};
-  const CUtensorMap ta = hw::make_tmap(x.data_ptr(), M, K, hw::kTileM);
-  const CUtensorMap tb = hw::make_tmap(w.data_ptr(), N, K, hw::kTileN);
-  static std::once_flag attr_once;
-  std::call_once(attr_once, [] {
-    C10_CUDA_CHECK(cudaFuncSetAttribute(hw::ffn_up_hw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hw::kSmemBytes));
-  });
-  const int tiles = ((M + hw::kTileM - 1) / hw::kTileM) * ((N + hw::kTileN - 1) / hw::kTileN);
-  const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
-  const int grid = std::min(tiles, sms);
-  auto stream = at::cuda::getCurrentCUDAStream().stream();
-  hw::ffn_up_hw_kernel<<<grid, hw::kNumThreads, hw::kSmemBytes, stream>>>(
-      ta, tb, reinterpret_cast<const __nv_bfloat16*>(bias.data_ptr()), reinterpret_cast<__nv_bfloat16*>(h.data_ptr()),
-      reinterpret_cast<__nv_bfloat16*>(z.data_ptr()), M, N, K);
-  C10_CUDA_KERNEL_LAUNCH_CHECK();
-  count_launch();
+  launch_hw<hw::MODE_UP>(x, w, reinterpret_cast<const __nv_bfloat16*>(bias.data_ptr()), h, &z, M, N, K);
   return {h, z};
+}
+
+// dZ = (dY Wt^T) * gelu'(Z)   with   Wt = W^T stored [N, K] row-major (K-major operand: the caller keeps a transposed
+// copy of the down-projection weight W [K, N]; an MN-major operand path is the next step, tools/checks/README.md)
+at::Tensor ffn_dgelu_hw(const at::Tensor& dy, const at::Tensor& wt, const at::Tensor& z) {
+  check_bf16(dy, "ffn_dgelu_hw dy"); check_bf16(wt, "ffn_dgelu_hw wt"); check_bf16(z, "ffn_dgelu_hw z");
+  TORCH_CHECK(dy.dim() == 2 && wt.dim() == 2 && z.dim() == 2 && dy.size(1) == wt.size(1) && z.size(0) == dy.size(0) &&
+              z.size(1) == wt.size(0), "ffn_dgelu_hw: shape mismatch (dy [M,K], wt [N,K], z [M,N])");
+  const int M = dy.size(0), K = dy.size(1), N = wt.size(0);
+  TORCH_CHECK(K % 8 == 0 && N % 8 == 0, "ffn_dgelu_hw: K and N must be multiples of 8");
+  c10::cuda::CUDAGuard guard(dy.device());
+  auto dz = at::empty({M, N}, dy.options());
+  if (M == 0) return dz;
+  launch_hw<hw::MODE_DGELU>(dy, wt, reinterpret_cast<const __nv_bfloat16*>(z.data_ptr()), dz, nullptr, M, N, K);
+  return dz;
 }
 
 }  // namespace dear_tc

@@ -85,6 +85,21 @@ def test_handwritten_ffn_up(M, K, N):
 
 
 @pytest.mark.gpu
+@unvalidated("the hand-written tcgen05 kernel (csrc/tc_ffn_hw.cu)")
+@pytest.mark.parametrize("M,K,N", [(128, 64, 256), (2048, 1024, 4096), (300, 72, 264), (5, 8, 16)])
+def test_handwritten_ffn_dgelu(M, K, N):
+    tc = require_tc()
+    dev = torch.device("cuda:0")
+    torch.manual_seed(2)
+    dy, w, z = _rand((M, K), dev), _rand((K, N), dev, K ** -0.5), _rand((M, N), dev)
+    dz = tc.ffn_dgelu_hw(dy, w.t().contiguous(), z)         # the kernel takes the transposed weight [N, K]
+    torch.cuda.synchronize()
+    z32 = z.float().requires_grad_(True)
+    F.gelu(z32).backward(dy.float() @ w.float())
+    torch.testing.assert_close(dz.float(), z32.grad, rtol=1.5e-2, atol=1.5e-2)
+
+
+@pytest.mark.gpu
 def test_fused_ffn_autograd_matches_eager_bf16():
     dev = torch.device("cuda:0")
     torch.manual_seed(3)

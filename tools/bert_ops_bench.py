@@ -81,6 +81,10 @@ def _gemm_section(r, tc, x, w1, b1, w2, b2, h, z, dy):
     for v, cfg in enumerate(tc.variants()["ffn_dgelu"]):
         r["dgrad_dgelu_tcgen05_v%d" % v] = graph_time(lambda: tc.ffn_dgelu(dy, w2, z, v))
     r["dgrad_dgelu_tcgen05"] = min(r["dgrad_dgelu_tcgen05_v%d" % v] for v in range(len(tc.variants()["ffn_dgelu"])))
+    if os.environ.get("DEAR_TC_EXPERIMENTAL"):
+        w2t = w2.t().contiguous()
+        r["dgrad_dgelu_tcgen05_handwritten"] = graph_time(lambda: tc.ffn_dgelu_hw(dy, w2t, z))
+        r["weight_transpose_for_handwritten_dgrad"] = graph_time(lambda: w2.t().contiguous())
     r["dgrad_gemm_only_cublas"] = graph_time(lambda: dy.mm(w2))
 
 
