@@ -61,6 +61,11 @@ def _eligible(x: torch.Tensor, *ws: torch.Tensor) -> bool:
     return all(w.dtype == torch.bfloat16 and w.shape[-1] % 8 == 0 and w.shape[0] % 8 == 0 for w in ws if w.dim() == 2)
 
 
+# DEAR_TC_FFN_IMPL=hw routes the two fused GEMMs of `fused_ffn` to the hand-written kernels of csrc/tc_ffn_hw.cu
+# (two-warpgroup epilogue; experimental until they have run on hardware).  Default: the CUTLASS-collective variants.
+HANDWRITTEN = os.environ.get("DEAR_TC_FFN_IMPL", "").lower() == "hw"
+
+
 class _FusedFFN(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w1, b1, w2, b2, tc_down):
@@ -68,7 +73,7 @@ class _FusedFFN(torch.autograd.Function):
         x2 = x.reshape(-1, x.shape[-1])
         if not x2.is_contiguous():
             x2 = x2.contiguous()
-        h, z = tc.ffn_up(x2, w1, b1, VARIANT["ffn_up"])
+        h, z = tc.ffn_up_hw(x2, w1, b1) if HANDWRITTEN else tc.ffn_up(x2, w1, b1, VARIANT["ffn_up"])
         y = tc.linear_bias(h, w2, b2, VARIANT["linear_bias"]) if tc_down else torch.addmm(b2, h, w2.t())
         ctx.save_for_backward(x2, w1, w2, h, z)
         ctx.x_shape = x.shape
@@ -81,7 +86,10 @@ class _FusedFFN(torch.autograd.Function):
         dy2 = dy.reshape(-1, dy.shape[-1])
         if not dy2.is_contiguous():
             dy2 = dy2.contiguous()
-        dz = tc.ffn_dgelu(dy2, w2, z, VARIANT["ffn_dgelu"])                     # (dy W2) * gelu'(z), one kernel
+        if HANDWRITTEN:     # K-major operands only: one 8 MB transpose of W2 per layer and step (~3 us)
+            dz = tc.ffn_dgelu_hw(dy2, w2.t().contiguous(), z)
+        else:
+            dz = tc.ffn_dgelu(dy2, w2, z, VARIANT["ffn_dgelu"])              # (dy W2) * gelu'(z), one kernel
         dw2 = dy2.t().mm(h) if ctx.needs_input_grad[3] else None
         db2 = dy2.sum(0) if ctx.needs_input_grad[4] else None
         dw1 = dz.t().mm(x2) if ctx.needs_input_grad[1] else None

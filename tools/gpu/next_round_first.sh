@@ -10,4 +10,8 @@ echo "=== its speed vs cuBLAS + GELU and the CUTLASS-collective variants"; timeo
 echo "=== engine on the nccl backend (world 1), gradient accumulation on the fused path"
 timeout 300 python -m pytest tests/test_gpu_nccl_backend.py tests/test_grad_accumulation.py -m gpu -q --timeout 150 2>&1 | tail -8
 echo "=== graph capture deferred until the BO tuner has settled"; timeout 300 python -m pytest tests/test_gpu_fused.py -m gpu -q --timeout 250 -k 'bo_tuner or adamw' 2>&1 | tail -6
+echo "=== BERT with the hand-written FFN kernels (only meaningful if the tests above passed)"
+B="timeout 200 python bench.py --model bert --steps 20 --warmup 8 --no-e2e"
+$B 2>&1 | grep -E '"metric"|Error|error' | cut -c1-200
+DEAR_TC_FFN_IMPL=hw DEAR_TC_DOWN=0 $B --tc-ffn 1 2>&1 | grep -E '"metric"|Error|error' | cut -c1-200
 echo "=== done"
