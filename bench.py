@@ -279,7 +279,7 @@ def run_dear(args):
         n_params = sum(p.numel() for p in model.parameters())
         cfg = {"model": args.model, "global_batch": B * world, "batch_per_gpu": B, "parallelism": "dp%d" % world,
                "optimizer": "%s lr=%g" % (args.optimizer.upper(), lr), "threshold_mb": args.threshold, "buckets": len(opt.engine.plan.buckets),
-               "params": n_params, "backend": dear.backend(), "cuda_graph": bool(args.graph),
+               "params": n_params, "backend": dear.backend(), "cuda_graph": bool(step.use_graph),
                "update_overlaps_forward_in_graph": bool(step.overlap_update),
                "l2": "no explicit flush: each step streams activations+weights far larger than the 126 MB L2"}
         if wl.is_bert:
