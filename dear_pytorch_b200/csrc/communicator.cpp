@@ -397,8 +397,10 @@ BucketSet::BucketSet(std::shared_ptr<Communicator> comm, std::vector<int64_t> pa
       b.ev_in = make_event();
       b.rs_done = make_event();
       b.ag_done = make_event();
-      b.pinned_ev[0] = make_event();
-      b.pinned_ev[1] = make_event();
+      for (auto* st : {&b.stage_pack, &b.stage_hyper}) {
+        st->ev[0] = make_event();
+        st->ev[1] = make_event();
+      }
     }
   }
 }
@@ -407,11 +409,14 @@ BucketSet::~BucketSet() {
   if (comm_->is_cuda()) {
     if (stream_) cudaStreamSynchronize(S(stream_));
     for (auto& b : buckets_) {
-      for (void* e : {b.ev_in, b.rs_done, b.ag_done, b.pinned_ev[0], b.pinned_ev[1]})
-        if (e) cudaEventDestroy(E(e));
+      for (void* e : {b.ev_in, b.rs_done, b.ag_done}) if (e) cudaEventDestroy(E(e));
+      for (auto* st : {&b.stage_pack, &b.stage_hyper}) {
+        for (void* e : st->ev) if (e) cudaEventDestroy(E(e));
+        for (void* p : st->pinned) if (p) cudaFreeHost(p);
+      }
+      for (void* p : b.captured_pinned) cudaFreeHost(p);
       if (b.pack_dev) cudaFree(b.pack_dev);
       if (b.hyper_dev) cudaFree(b.hyper_dev);
-      for (void* p : b.pinned) if (p) cudaFreeHost(p);
     }
     if (ev_fence_) cudaEventDestroy(E(ev_fence_));
     if (stream_) cudaStreamDestroy(S(stream_));
@@ -467,11 +472,13 @@ void BucketSet::set_shards(int g, torch::Tensor grad_shard, std::optional<torch:
   // (low-precision buckets must have a master shard by the time allgather_update() runs)
 }
 
-void BucketSet::upload(Bucket& b, const void* host, size_t bytes, void** dev, size_t* cap) {
+void BucketSet::upload(Bucket& b, bool is_pack, const void* host, size_t bytes, void** dev, size_t* cap) {
   if (bytes == 0) return;
+  const cudaStream_t cur = current_stream(comm_->options().device);
+  // a capture may be in progress on the compute stream before the comm stream has joined it
+  const bool capturing = is_capturing(S(stream_)) || is_capturing(cur);
   if (*cap < bytes) {
-    DEAR_CHECK(!(is_capturing(S(stream_)) || is_capturing(current_stream(comm_->options().device))),
-               "device table would have to grow during CUDA-graph capture; run a few eager steps first");
+    DEAR_CHECK(!capturing, "device table would have to grow during CUDA-graph capture; run a few eager steps first");
     // the old table may still be read by an in-flight kernel on the comm stream
     DEAR_CUDA(cudaStreamSynchronize(S(stream_)));
     if (*dev) DEAR_CUDA(cudaFree(*dev));
@@ -479,24 +486,44 @@ void BucketSet::upload(Bucket& b, const void* host, size_t bytes, void** dev, si
     DEAR_CUDA(cudaMalloc(dev, ncap));
     *cap = ncap;
   }
-  const int slot = b.pinned_next;
-  b.pinned_next ^= 1;
-  // a capture may be in progress on the compute stream before the comm stream has joined it
-  const bool capturing = is_capturing(S(stream_)) || is_capturing(current_stream(comm_->options().device));
-  if (b.pinned_cap[slot] < bytes) {
-    if (b.pinned[slot]) {
-      if (!capturing) DEAR_CUDA(cudaEventSynchronize(E(b.pinned_ev[slot])));
-      DEAR_CUDA(cudaFreeHost(b.pinned[slot]));
+  if (capturing) {
+    // The copy becomes a memcpy NODE that re-reads its host source on every replay.
+    //  * hyper-parameters must never be frozen into a graph (an LR scheduler could not change them any more):
+    //    TrainStep uploads them before the capture starts and after every change, outside the graph;
+    //  * a pack table (the gradient addresses of THIS capture) gets a dedicated pinned buffer that nobody
+    //    writes again, and the copy is forced INTO the graph (the comm stream joins the capture first), so a
+    //    replay always restores the table its kernels were captured with — whatever eager steps ran in between.
+    DEAR_CHECK(is_pack, "optimizer hyper-parameters changed during CUDA-graph capture; upload them before capturing "
+                        "(DearEngine.refresh_hyper_outside_graph)");
+    if (!is_capturing(S(stream_))) fence_current_to_comm();
+    void* pin = nullptr;
+    {
+      // allocation calls are "potentially unsafe" under a thread-local capture: relax the mode around this one
+      cudaStreamCaptureMode mode = cudaStreamCaptureModeRelaxed;
+      DEAR_CUDA(cudaThreadExchangeStreamCaptureMode(&mode));
+      cudaError_t err = cudaHostAlloc(&pin, bytes, cudaHostAllocDefault);
+      cudaThreadExchangeStreamCaptureMode(&mode);
+      DEAR_CUDA(err);
     }
-    size_t ncap = std::max<size_t>(bytes * 2, 4096);
-    DEAR_CUDA(cudaHostAlloc(&b.pinned[slot], ncap, cudaHostAllocDefault));
-    b.pinned_cap[slot] = ncap;
-  } else if (!capturing) {
-    DEAR_CUDA(cudaEventSynchronize(E(b.pinned_ev[slot])));   // normally long complete
+    b.captured_pinned.push_back(pin);
+    std::memcpy(pin, host, bytes);
+    DEAR_CUDA(cudaMemcpyAsync(*dev, pin, bytes, cudaMemcpyHostToDevice, S(stream_)));
+    b.pack_captured = true;
+    return;
   }
-  std::memcpy(b.pinned[slot], host, bytes);
-  DEAR_CUDA(cudaMemcpyAsync(*dev, b.pinned[slot], bytes, cudaMemcpyHostToDevice, S(stream_)));
-  if (!capturing) DEAR_CUDA(cudaEventRecord(E(b.pinned_ev[slot]), S(stream_)));
+  Bucket::Staging& st = is_pack ? b.stage_pack : b.stage_hyper;
+  const int slot = st.next;
+  st.next ^= 1;
+  DEAR_CUDA(cudaEventSynchronize(E(st.ev[slot])));   // the copy that last read this slot; normally long complete
+  if (st.cap[slot] < bytes) {
+    if (st.pinned[slot]) DEAR_CUDA(cudaFreeHost(st.pinned[slot]));
+    size_t ncap = std::max<size_t>(bytes * 2, 4096);
+    DEAR_CUDA(cudaHostAlloc(&st.pinned[slot], ncap, cudaHostAllocDefault));
+    st.cap[slot] = ncap;
+  }
+  std::memcpy(st.pinned[slot], host, bytes);
+  DEAR_CUDA(cudaMemcpyAsync(*dev, st.pinned[slot], bytes, cudaMemcpyHostToDevice, S(stream_)));
+  DEAR_CUDA(cudaEventRecord(E(st.ev[slot]), S(stream_)));
 }
 
 bool BucketSet::set_pack(int g, const std::vector<int64_t>& src_ptrs, const std::vector<int64_t>& dst_off_bytes,
@@ -527,11 +554,12 @@ bool BucketSet::set_pack(int g, const std::vector<int64_t>& src_ptrs, const std:
   const bool same = segs.size() == b.pack_host.size() &&
                     (segs.empty() || std::memcmp(segs.data(), b.pack_host.data(), segs.size() * sizeof(PackSeg)) == 0);
   b.pack_inplace = inplace;
-  if (same) return false;
+  // once a graph owns a memcpy node for this table, the device copy is whatever the last replay restored
+  if (same && !b.pack_captured) return false;
   b.pack_host = std::move(segs);
   b.ntiles = tiles;
   if (comm_->is_cuda())
-    upload(b, b.pack_host.data(), b.pack_host.size() * sizeof(PackSeg), reinterpret_cast<void**>(&b.pack_dev), &b.pack_cap);
+    upload(b, true, b.pack_host.data(), b.pack_host.size() * sizeof(PackSeg), reinterpret_cast<void**>(&b.pack_dev), &b.pack_cap);
   return true;
 }
 
@@ -550,7 +578,7 @@ bool BucketSet::set_hyper(int g, const std::vector<int64_t>& ends, const std::ve
     segs[i].weight_decay = static_cast<float>(wd[i]);
     segs[i].momentum = static_cast<float>(mom[i]);
     segs[i].dampening = static_cast<float>(damp[i]);
-    segs[i].nesterov = nesterov[i] ? 1u : 0u;
+    segs[i].nesterov = static_cast<uint32_t>(nesterov[i]) & (HYPER_NESTEROV | HYPER_SKIP);
     segs[i].opt = i < opt.size() ? static_cast<uint32_t>(opt[i]) : OPT_SGD;
     segs[i].beta2 = i < beta2.size() ? static_cast<float>(beta2[i]) : 0.f;
     segs[i].eps = i < eps.size() ? static_cast<float>(eps[i]) : 0.f;
@@ -566,7 +594,7 @@ bool BucketSet::set_hyper(int g, const std::vector<int64_t>& ends, const std::ve
   if (same) return false;
   b.hyper_host = std::move(segs);
   if (comm_->is_cuda())
-    upload(b, b.hyper_host.data(), b.hyper_host.size() * sizeof(HyperSeg), reinterpret_cast<void**>(&b.hyper_dev), &b.hyper_cap);
+    upload(b, false, b.hyper_host.data(), b.hyper_host.size() * sizeof(HyperSeg), reinterpret_cast<void**>(&b.hyper_dev), &b.hyper_cap);
   return true;
 }
 

@@ -151,16 +151,24 @@ class BucketSet {
     size_t pack_cap = 0;
     HyperSeg* hyper_dev = nullptr;
     size_t hyper_cap = 0;
-    void* pinned[2] = {nullptr, nullptr};
-    size_t pinned_cap[2] = {0, 0};
-    void* pinned_ev[2] = {nullptr, nullptr};
-    int pinned_next = 0;
+    // Host staging of the two device tables.  Each table kind has its OWN double-buffered pinned area, and an
+    // upload that is captured into a CUDA graph gets a dedicated buffer that is never written again (the graph's
+    // memcpy node re-reads it on every replay).
+    struct Staging {
+      void* pinned[2] = {nullptr, nullptr};
+      size_t cap[2] = {0, 0};
+      void* ev[2] = {nullptr, nullptr};
+      int next = 0;
+    };
+    Staging stage_pack, stage_hyper;
+    std::vector<void*> captured_pinned;   // owned by captured memcpy nodes; freed with the BucketSet
+    bool pack_captured = false;           // a graph restores pack_dev on replay: eager uploads can never be skipped
     void* ev_in = nullptr;
     void* rs_done = nullptr;
     void* ag_done = nullptr;
     bool ag_pending = false, rs_pending = false;
   };
-  void upload(Bucket& b, const void* host, size_t bytes, void** dev, size_t* cap);
+  void upload(Bucket& b, bool is_pack, const void* host, size_t bytes, void** dev, size_t* cap);
   int grid_for(int64_t shard_elems, int max_grid) const;
 
   std::shared_ptr<Communicator> comm_;

@@ -90,11 +90,16 @@ struct HyperSeg {
   float weight_decay;
   float momentum;         // SGD momentum, or Adam beta1
   float dampening;
-  uint32_t nesterov;
+  uint32_t nesterov;      // bit0: Nesterov momentum; bit1 (HYPER_SKIP): this rank saw no gradient for the range in
+                          // this step — where the REDUCED gradient is exactly zero too (absent on every rank), leave
+                          // parameter and state untouched, like torch.optim skips ``p.grad is None``
   uint32_t opt;           // OptKind
   float beta2;            // Adam only
   float eps;              // Adam only
 };
+
+constexpr uint32_t HYPER_NESTEROV = 1u;
+constexpr uint32_t HYPER_SKIP = 2u;
 
 // ---- per-element math shared by the CUDA kernels and the host emulation ----
 
@@ -104,11 +109,12 @@ struct HyperSeg {
 // `g` is already averaged (the 1/P scale is fused into the reduce-scatter).
 DEAR_HD float sgd_update(float p, float g, float& mom, const HyperSeg& h, bool first_step,
                          bool has_mom_buf) {
+  if ((h.nesterov & HYPER_SKIP) && g == 0.f) return p;
   if (h.weight_decay != 0.f) g = g + h.weight_decay * p;
   if (h.momentum > 0.f && has_mom_buf) {
     float buf = first_step ? g : (h.momentum * mom + (1.f - h.dampening) * g);
     mom = buf;
-    g = h.nesterov ? (g + h.momentum * buf) : buf;
+    g = (h.nesterov & HYPER_NESTEROV) ? (g + h.momentum * buf) : buf;
   }
   return p - h.lr * g;
 }
@@ -117,6 +123,7 @@ DEAR_HD float sgd_update(float p, float g, float& mom, const HyperSeg& h, bool f
 // bc1 = 1 - beta1^t, bc2 = 1 - beta2^t.  This extends the reference, whose DeAR path is SGD-only
 // (dear/dear_dopt.py:310-336; its BERT driver had to drop AdamW, dear/bert_benchmark.py:118-122).
 DEAR_HD float adam_update(float p, float g, float& m, float& v, const HyperSeg& h, float bc1, float sqrt_bc2) {
+  if ((h.nesterov & HYPER_SKIP) && g == 0.f) return p;
   if (h.opt == OPT_ADAM && h.weight_decay != 0.f) g = g + h.weight_decay * p;
   m = h.momentum * m + (1.f - h.momentum) * g;
   v = h.beta2 * v + (1.f - h.beta2) * g * g;

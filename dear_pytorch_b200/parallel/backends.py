@@ -29,6 +29,7 @@ _DT_CODE = {torch.float32: "DT_F32", torch.bfloat16: "DT_BF16", torch.float16: "
 
 
 OPT_SGD, OPT_ADAM, OPT_ADAMW = 0, 1, 2
+HYPER_NESTEROV, HYPER_SKIP = 1, 2        # bits of the ``nesterov`` field of a hyper segment (csrc/dear_common.h)
 
 
 class HyperSpec:
@@ -101,6 +102,10 @@ class _BackendBase:
         self.hyper[g] = spec
 
     def launches(self) -> int:
+        return 0
+
+    def stream_key(self, g: int) -> int:
+        """Buckets with the same key share one communication stream (ordering domain)."""
         return 0
 
 
@@ -201,6 +206,9 @@ class NativeBackend(_BackendBase):
     def launches(self):
         return self.comm.launches()
 
+    def stream_key(self, g):
+        return id(self.where[g][0])
+
 
 # =====================================================================================
 # torch.distributed: nccl / gloo
@@ -271,6 +279,9 @@ class TorchBackend(_BackendBase):
             start = end
             if a >= z:
                 continue
+            if int(nesterov) & HYPER_SKIP and not bool(self.grad_shard[g][a - lo:z - lo].any()):
+                continue                          # no gradient on ANY rank this step: parameter and state stay as they are
+            nesterov = bool(int(nesterov) & HYPER_NESTEROV)
             sl = slice(a - lo, z - lo)
             p = master[sl] if master is not None else self._pbuf[g][a:z]
             d = self.grad_shard[g][sl]

@@ -108,6 +108,11 @@ def broadcast_parameters(params, root_rank: int = 0) -> None:
         comm.synchronize()
     elif runtime.device().type == "cuda":
         torch.cuda.current_stream().synchronize()
+    # parameters that already live in DeAR buckets: their sharded fp32 masters were snapshotted when the optimizer
+    # was wrapped and must follow the broadcast values (bf16 / fp16 models)
+    from .optimizer import live_engines
+    for eng in live_engines():
+        eng.params_changed()
 
 
 def broadcast_optimizer_state(optimizer: torch.optim.Optimizer, root_rank: int = 0) -> None:

@@ -31,10 +31,17 @@ import torch
 import torch.nn as nn
 
 from .. import runtime
-from .backends import OPT_ADAM, OPT_ADAMW, OPT_SGD, HyperSpec, NativeBackend, TorchBackend
+from .backends import HYPER_SKIP, OPT_ADAM, OPT_ADAMW, OPT_SGD, HyperSpec, NativeBackend, TorchBackend
 from .bucket import BucketPlan
 
+import weakref
+
 THRESHOLD = 25            # MB, reference default (dear/dear_dopt.py:43)
+_LIVE_ENGINES = weakref.WeakSet()   # engines whose buckets currently hold their model's parameters
+
+
+def live_engines():
+    return [e for e in list(_LIVE_ENGINES) if not e._closed and e.backend is not None]
 NUM_NEARBY_LAYERS = 4     # reference default (dear/dear_dopt.py:42)
 
 
@@ -105,6 +112,9 @@ class DearEngine:
         self._check_plan_consistency()
         self._build(initial=True)
         self._register_hooks()
+        _LIVE_ENGINES.add(self)
+        # model.load_state_dict() after wrapping writes into the bucket views: the fp32 master shards follow
+        self._hooks.append(model.register_load_state_dict_post_hook(lambda module, incompatible: self.params_changed()))
         if os.environ.get("DEAR_TIMELINE"):
             from ..utils import trace
             trace.attach(self)
@@ -177,12 +187,14 @@ class DearEngine:
         self._next_rs = nb - 1
         self._pending = [False] * nb
         self._any_pending = False
-        self._inflight: List[torch.Tensor] = []
+        # stolen gradients still read by Kernel A, per communication stream (one BucketSet per dtype)
+        self._inflight: Dict[int, List[torch.Tensor]] = {}
         self._src = [[0] * n for n in self._n_params]
         self._flags = [[0] * n for n in self._n_params]
         self._dst_off = [[s.start * s.param.element_size() for s in b.slots] for b in plan.buckets]
         self._nbytes = [[s.numel * s.param.element_size() for s in b.slots] for b in plan.buckets]
         self._hyper_key = [None] * nb
+        self._absent = [()] * nb           # per bucket: slots that received no gradient in the current step
         self._module_bucket = list(plan.module_bucket)
         if getattr(self, "timeline", None) is not None:
             from ..utils import trace
@@ -211,9 +223,10 @@ class DearEngine:
         if self._pending[g]:
             self.backend.wait_bucket(g)
             self._pending[g] = False
-            # every all-gather is queued behind every reduce-scatter of the same step, so once
-            # the compute stream has waited on any of them the gradients may be released
-            self._inflight.clear()
+            # inside ONE BucketSet every all-gather is queued behind every reduce-scatter of the same step, so
+            # once the compute stream has waited on one of its all-gathers that set's gradients may be released;
+            # another dtype's set has its own stream and keeps its gradients until one of ITS buckets was waited on
+            self._inflight.pop(self.backend.stream_key(g), None)
             if not any(self._pending):
                 self._any_pending = False
 
@@ -256,12 +269,13 @@ class DearEngine:
             self._grad_view[p].copy_(grad)
             self._src[g][i] = 0
         self._flags[g][i] = 0
-        self._inflight.append(grad)
+        self._inflight.setdefault(self.backend.stream_key(g), []).append(grad)
 
     def _drain_rs(self, force=False):
         """Launch reduce-scatters in descending bucket order (identical on every rank)."""
         while self._next_rs >= 0 and (force or self._complete[self._next_rs]):
             g = self._next_rs
+            absent = []
             if not self._complete[g]:
                 for i, ok in enumerate(self._arrived[g]):
                     if ok:
@@ -275,9 +289,11 @@ class DearEngine:
                         elif late.data_ptr() != self._grad_view[p].data_ptr():
                             self._grad_view[p].copy_(late)
                             p.grad = self._grad_view[p]
-                    else:                # no gradient this iteration: contribute zeros
+                    else:                # no gradient this iteration: contribute zeros, skip the update
                         self._src[g][i] = 0
                         self._flags[g][i] = 1 if self.steal else 0
+                        absent.append(i)
+            self._absent[g] = tuple(absent)
             if self.steal:
                 self.backend.set_pack(g, self._src[g], self._dst_off[g], self._nbytes[g], self._flags[g])
             self.backend.reduce_scatter(g, True)
@@ -290,13 +306,31 @@ class DearEngine:
     def _refresh_hyper(self):
         key_all = self._hyper_key_now()
         for b in self.plan.buckets:
-            if self._hyper_key[b.index] == key_all:
+            absent = self._absent[b.index]
+            key = (key_all, absent)
+            if self._hyper_key[b.index] == key:
                 continue
             segs = []
-            for end, gi in self.plan.hyper_segments(b.index, self.group_of):
-                segs.append((int(end),) + key_all[gi])
+            if not absent:
+                for end, gi in self.plan.hyper_segments(b.index, self.group_of):
+                    segs.append((int(end),) + key_all[gi])
+            else:
+                # parameters that received no gradient on this rank carry HYPER_SKIP: where the reduced gradient is
+                # zero as well (absent on every rank) the update leaves them alone, like torch.optim skips
+                # ``p.grad is None`` (no weight decay, no momentum / moment decay)
+                gone, prev = set(absent), None
+                for i, sl in enumerate(b.slots):
+                    gi, skip = self.group_of[sl.param], i in gone
+                    end = b.slots[i + 1].start if i + 1 < len(b.slots) else b.padded_numel
+                    k = key_all[gi]
+                    seg = (int(end),) + k[:4] + (int(k[4]) | (HYPER_SKIP if skip else 0),) + k[5:]
+                    if prev == (gi, skip):
+                        segs[-1] = seg
+                    else:
+                        segs.append(seg)
+                    prev = (gi, skip)
             self.backend.set_hyper(b.index, HyperSpec(segs))
-            self._hyper_key[b.index] = key_all
+            self._hyper_key[b.index] = key
 
     def _hyper_key_now(self):
         """Per param group: (lr, wd, momentum|beta1, dampening, nesterov, opt, beta2, eps)."""
@@ -313,13 +347,22 @@ class DearEngine:
 
     def hyper_changed(self) -> bool:
         key = self._hyper_key_now()
-        return any(k != key for k in self._hyper_key)
+        return any(k is None or k[0] != key for k in self._hyper_key)
 
     def refresh_hyper_outside_graph(self):
         """An LR scheduler changed ``param_groups`` while the step is replayed from a CUDA graph:
         re-upload the device hyper-parameter tables and order the replay after the upload."""
         self._refresh_hyper()
         self.backend.wait_all()
+
+    def params_changed(self):
+        """The parameter VALUES were overwritten from outside (``broadcast_parameters``, ``load_state_dict``,
+        manual ``p.data.copy_``): re-derive the fp32 master shards of low-precision buckets from the bucket
+        contents, otherwise the next update would push the stale masters back over the new values."""
+        if self.backend is None:
+            return
+        self.synchronize(host=True)
+        self.backend.init_master_shards()
 
     # ------------------------------------------------------------------ step
     def step(self):

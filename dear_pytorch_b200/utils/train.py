@@ -143,6 +143,9 @@ class TrainStep:
         dev = _first_tensor(batch).device
         self._static_in = _tree_map(lambda t: torch.empty_like(t).copy_(t), batch)
         if eng is not None:
+            # hyper-parameter tables are uploaded OUTSIDE the graph (before the capture and after every change), so
+            # an LR scheduler keeps working on a replayed graph; the native runtime refuses to capture such an upload
+            eng.refresh_hyper_outside_graph()
             eng.synchronize(host=True)
         torch.cuda.synchronize(dev)
         self._log("capturing")
