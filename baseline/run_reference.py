@@ -1,4 +1,11 @@
-"""`bench.py --impl reference`: the reference's own DeAR optimizer (baseline/_ref/dear/dopt_rsag.py,
+"""`bench.py --impl reference --model bert --dtype bf16` (the default dtype for BERT, as BASELINE.json names the
+config "BERT-large pretraining bf16"): the reference's DeAR path is fp32-only, so the same-precision baseline is the
+reference's PyTorch-DDP recipe (baseline/_ref/pytorch-ddp/bert_benchmark.py:58-126: HF ``BertForPreTraining``,
+``DistributedDataParallel`` over NCCL, SGD lr=2e-5, its synthetic batch, criterion and ``benchmark_step`` incl. the
+``torch.cuda.synchronize()``) with the model cast to bf16 — BASELINE.md section 2.  ``--dtype fp32`` runs the
+reference's DeAR optimizer below.
+
+`bench.py --impl reference`: the reference's own DeAR optimizer (baseline/_ref/dear/dopt_rsag.py,
 tensorfusion.py — unmodified) driven exactly as its benchmark driver does
 (baseline/_ref/dear/imagenet_benchmark.py:73-136: torchvision model, SGD lr=0.01*size,
 DistributedOptimizer iff size>1, broadcast_parameters, benchmark_step incl. its
@@ -51,6 +58,7 @@ def run(args):
     cudnn.benchmark = True
     rank, world = hvd.rank(), hvd.size()
     is_bert = args.model in ("bert", "bert_large", "bert_base")
+    bf16_ddp = is_bert and getattr(args, "dtype", "fp32") == "bf16"
     B = args.batch_size
     if is_bert:
         # dear/bert_benchmark.py:72-122, with the installed transformers (5.x returns ModelOutput, so
@@ -65,6 +73,8 @@ def run(args):
             config.vocab_size += 8 - (config.vocab_size % 8)
         vocab_size = config.vocab_size
         model = BertForPreTraining(config).cuda()
+        if bf16_ddp:
+            model = model.to(torch.bfloat16)
         max_len = args.sentence_len
         input_ids = (torch.rand(B, max_len) * 2000).long().cuda()
         attention_masks = torch.rand(B, max_len).long().cuda()
@@ -85,8 +95,14 @@ def run(args):
         data = torch.randn(B, 3, size, size).cuda()
         target = torch.LongTensor(B).random_() % 1000
         target = target.cuda()
-        unit, metric = "images/s", "images/sec (ResNet-50 synthetic ImageNet training, DeAR tensor fusion)"
-    if world > 1:
+        unit = "images/s"
+        metric = "images/sec (ResNet-50 synthetic ImageNet training, DeAR tensor fusion)" if args.model == "resnet50" \
+            else "images/sec (%s synthetic training, DeAR tensor fusion)" % args.model
+    if bf16_ddp:
+        if world > 1:       # pytorch-ddp/bert_benchmark.py:84 (DDP broadcasts the parameters itself)
+            model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[torch.cuda.current_device()])
+            optimizer = optim.SGD(model.parameters(), lr=2e-5)
+    elif world > 1:
         optimizer = hvd.DistributedOptimizer(optimizer, model=model)
         hvd.broadcast_parameters(model.state_dict(), root_rank=0)
 
@@ -178,10 +194,13 @@ def run(args):
             "metric": metric, "value": round(value, 2),
             "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "fp32 (TF32 convolutions, torch defaults)", "data": "synthetic", "impl": "reference",
+            "dtype": "bf16" if bf16_ddp else ("fp32" if is_bert else "fp32 (TF32 convolutions, torch defaults)"),
+            "data": "synthetic", "impl": "reference",
             "config": {"model": args.model, "global_batch": B * world, "batch_per_gpu": B, ("seq_len" if is_bert else "image"): size,
                        "parallelism": "dp%d" % world, "optimizer": "SGD",
-                       "path": "baseline/_ref/dear/dopt_rsag.py over NCCL (comm_core stand-in: torch.distributed)",
+                       "path": ("baseline/_ref/pytorch-ddp/bert_benchmark.py recipe (DistributedDataParallel over NCCL), model in bf16"
+                                if bf16_ddp else
+                                "baseline/_ref/dear/dopt_rsag.py over NCCL (comm_core stand-in: torch.distributed)"),
                        "l2": "no explicit flush: working set far larger than L2"},
             "e2e": e2e, "gpu_launches": 0, "clocks": clocks}), flush=True)
     if world > 1:

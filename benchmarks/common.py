@@ -77,7 +77,6 @@ def wrap_optimizer(method, args, model, optimizer, profile_fn=None):
     """Returns (model, optimizer) for the chosen method."""
     from dear_pytorch_b200.parallel import variants
     from dear_pytorch_b200.parallel import baselines
-    from dear_pytorch_b200.parallel.baselines import horovod_like
     from dear_pytorch_b200.parallel.compression import compressors
     world = dear.size()
     if method == "single" or (world == 1 and not method.startswith("dear")):
@@ -107,11 +106,11 @@ def wrap_optimizer(method, args, model, optimizer, profile_fn=None):
         return model, baselines.WFBPDistributedOptimizer(
             optimizer, model=model, compression=comp, is_sparse=args.density < 1, density=args.density,
             seq_layernames=seq, layerwise_times=times, threshold=thr, mgwfbp=(method == "mgwfbp"), asc=(method == "asc"),
-            rdma=args.rdma)
+            rdma=args.rdma, momentum_correction=getattr(args, "momentum_correction", False))
     if method == "horovod":
-        return model, horovod_like.HorovodLikeOptimizer(optimizer, model)
+        return model, baselines.HorovodOptimizer(optimizer, model)        # HOROVOD_FUSION_THRESHOLD / HOROVOD_CYCLE_TIME
     if method == "bytescheduler":
-        return model, horovod_like.ByteSchedulerLikeOptimizer(optimizer, model)
+        return model, baselines.ByteSchedulerOptimizer(optimizer, model)  # BYTESCHEDULER_PARTITION / BYTESCHEDULER_CREDIT
     if method in ("ddp", "ddp-zero"):
         kw = dict(optimizer.defaults)
         ddp_model, opt = baselines.wrap_ddp(model, type(optimizer), {k: v for k, v in kw.items() if k in

@@ -62,7 +62,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def_readwrite("rendezvous_timeout_s", &CommOptions::rendezvous_timeout_s)
       .def_readwrite("rs_grid", &CommOptions::rs_grid)
       .def_readwrite("ag_grid", &CommOptions::ag_grid)
-      .def_readwrite("gen_grid", &CommOptions::gen_grid);
+      .def_readwrite("gen_grid", &CommOptions::gen_grid)
+      .def_readwrite("rs_algo", &CommOptions::rs_algo)
+      .def_readwrite("pipe_min_bytes", &CommOptions::pipe_min_bytes)
+      .def_readwrite("stripe_target_bytes", &CommOptions::stripe_target_bytes)
+      .def_readwrite("separate_ag_stream", &CommOptions::separate_ag_stream);
 
   py::class_<Communicator, std::shared_ptr<Communicator>>(m, "Communicator")
       .def(py::init([](int rank, int world, py::object store, std::string name, CommOptions opt) {
@@ -107,6 +111,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
            py::arg("momentum"), py::arg("dampening"), py::arg("nesterov"), py::arg("opt") = std::vector<int64_t>{},
            py::arg("beta2") = std::vector<double>{}, py::arg("eps") = std::vector<double>{})
       .def("reduce_scatter", &BucketSet::reduce_scatter, py::arg("bucket"), py::arg("pack") = true)
+      .def("rs_plan", &BucketSet::rs_plan, py::arg("bucket"))
       .def("allgather_update", &BucketSet::allgather_update, py::arg("bucket"), py::arg("do_update") = true,
            py::arg("first_step") = false, py::arg("entry_barrier") = true, py::arg("zero_grad") = false)
       .def("fence_current_to_comm", &BucketSet::fence_current_to_comm)

@@ -4,8 +4,9 @@
 #include <c10/cuda/CUDAStream.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstring>
-#include <sstream>
+#include "dear_msg.h"
 #include <stdexcept>
 
 namespace dear {
@@ -13,7 +14,7 @@ namespace dear {
 #define DEAR_CHECK(cond, msg)                                                        \
   do {                                                                               \
     if (!(cond)) {                                                                   \
-      std::ostringstream _oss;                                                       \
+      dear::Msg _oss;                                                                     \
       _oss << "dear: " << msg;                                                       \
       throw std::runtime_error(_oss.str());                                          \
     }                                                                                \
@@ -23,7 +24,7 @@ namespace dear {
   do {                                                                               \
     cudaError_t _e = (expr);                                                         \
     if (_e != cudaSuccess) {                                                         \
-      std::ostringstream _oss;                                                       \
+      dear::Msg _oss;                                                                     \
       _oss << "dear: CUDA error '" << cudaGetErrorString(_e) << "' in " #expr " ("   \
            << __FILE__ << ":" << __LINE__ << ")";                                    \
       throw std::runtime_error(_oss.str());                                          \
@@ -390,9 +391,36 @@ BucketSet::BucketSet(std::shared_ptr<Communicator> comm, std::vector<int64_t> pa
   }
   arena_ = SymmArena::create(off, comm_->rank(), world, comm_->store(), comm_->unique_key("buckets"),
                              comm_->arena_options());
+  // ---- per-bucket reduce-scatter plan (north star: "picked per bucket size") -------------------------------
+  const CommOptions& o = comm_->options();
+  for (auto& b : buckets_) {
+    const int64_t bytes = b.padded * static_cast<int64_t>(es);
+    const int64_t shard_bytes = b.shard * static_cast<int64_t>(es);
+    int algo = o.rs_algo;
+    if (algo < 0) algo = (world > 1 && bytes >= o.pipe_min_bytes) ? RS_ALGO_PIPE : RS_ALGO_ONESHOT;
+    if (world == 1 || !comm_->is_cuda()) algo = RS_ALGO_ONESHOT;
+    if (algo == RS_ALGO_NVLS && !arena_->has_multicast()) algo = RS_ALGO_ONESHOT;
+    b.rs_algo = algo;
+    if (algo == RS_ALGO_PIPE) {
+      int64_t k = std::max<int64_t>(1, std::min<int64_t>(16, bytes / std::max<int64_t>(1, o.stripe_target_bytes)));
+      int64_t cs = (shard_bytes + k - 1) / k;
+      cs = (cs + kPipePackPiece - 1) / kPipePackPiece * kPipePackPiece;
+      b.stripe_bytes = static_cast<uint64_t>(cs);
+      b.nstripes = static_cast<uint32_t>((shard_bytes + cs - 1) / cs);
+      // one CTA per 16 KB chunk of a stripe is the most that can be busy
+      const int64_t chunks = std::max<int64_t>(1, std::min<int64_t>(cs, shard_bytes) / kPipeChunk);
+      b.rs_grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(o.rs_grid, chunks)));
+    } else {
+      b.nstripes = 1;
+      b.stripe_bytes = static_cast<uint64_t>(shard_bytes);
+      b.rs_grid = grid_for(bytes, o.rs_grid);
+    }
+  }
   if (comm_->is_cuda()) {
     stream_ = make_priority_stream();
+    ag_stream_ = o.separate_ag_stream ? make_priority_stream() : stream_;
     ev_fence_ = make_event();
+    ev_fence_ag_ = make_event();
     for (auto& b : buckets_) {
       b.ev_in = make_event();
       b.rs_done = make_event();
@@ -408,6 +436,7 @@ BucketSet::BucketSet(std::shared_ptr<Communicator> comm, std::vector<int64_t> pa
 BucketSet::~BucketSet() {
   if (comm_->is_cuda()) {
     if (stream_) cudaStreamSynchronize(S(stream_));
+    if (ag_stream_) cudaStreamSynchronize(S(ag_stream_));
     for (auto& b : buckets_) {
       for (void* e : {b.ev_in, b.rs_done, b.ag_done}) if (e) cudaEventDestroy(E(e));
       for (auto* st : {&b.stage_pack, &b.stage_hyper}) {
@@ -419,6 +448,11 @@ BucketSet::~BucketSet() {
       if (b.hyper_dev) cudaFree(b.hyper_dev);
     }
     if (ev_fence_) cudaEventDestroy(E(ev_fence_));
+    if (ev_fence_ag_) cudaEventDestroy(E(ev_fence_ag_));
+    if (ag_stream_ && ag_stream_ != stream_) {
+      cudaStreamSynchronize(S(ag_stream_));
+      cudaStreamDestroy(S(ag_stream_));
+    }
     if (stream_) cudaStreamDestroy(S(stream_));
     cudaGetLastError();
   }
@@ -447,6 +481,7 @@ void BucketSet::set_step(int g, int64_t t) {
   uint32_t* dst = arena_->ctrl() + 2 * kNumChannels + g;
   if (comm_->is_cuda()) {
     DEAR_CUDA(cudaStreamSynchronize(S(stream_)));
+    if (ag_stream_ != stream_) DEAR_CUDA(cudaStreamSynchronize(S(ag_stream_)));
     DEAR_CUDA(cudaMemcpy(dst, &v, sizeof(v), cudaMemcpyHostToDevice));
   } else {
     *dst = v;
@@ -479,8 +514,9 @@ void BucketSet::upload(Bucket& b, bool is_pack, const void* host, size_t bytes, 
   const bool capturing = is_capturing(S(stream_)) || is_capturing(cur);
   if (*cap < bytes) {
     DEAR_CHECK(!capturing, "device table would have to grow during CUDA-graph capture; run a few eager steps first");
-    // the old table may still be read by an in-flight kernel on the comm stream
+    // the old table may still be read by an in-flight kernel on the comm streams
     DEAR_CUDA(cudaStreamSynchronize(S(stream_)));
+    if (ag_stream_ != stream_) DEAR_CUDA(cudaStreamSynchronize(S(ag_stream_)));
     if (*dev) DEAR_CUDA(cudaFree(*dev));
     size_t ncap = std::max<size_t>(bytes * 2, 4096);
     DEAR_CUDA(cudaMalloc(dev, ncap));
@@ -511,6 +547,11 @@ void BucketSet::upload(Bucket& b, bool is_pack, const void* host, size_t bytes, 
     b.pack_captured = true;
     return;
   }
+  if (!is_pack && ag_stream_ != stream_) {
+    // the hyper table is read by update kernels on the all-gather stream: overwrite it only after they finished
+    DEAR_CUDA(cudaEventRecord(E(ev_fence_ag_), S(ag_stream_)));
+    DEAR_CUDA(cudaStreamWaitEvent(S(stream_), E(ev_fence_ag_), 0));
+  }
   Bucket::Staging& st = is_pack ? b.stage_pack : b.stage_hyper;
   const int slot = st.next;
   st.next ^= 1;
@@ -536,7 +577,12 @@ bool BucketSet::set_pack(int g, const std::vector<int64_t>& src_ptrs, const std:
   segs.reserve(n);
   uint32_t tiles = 0;
   bool inplace = false;
-  for (size_t i = 0; i < n; ++i) {
+  // the stripe-pipelined kernel walks the table in bucket order
+  std::vector<size_t> order(n);
+  for (size_t i = 0; i < n; ++i) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b2) { return dst_off_bytes[a] < dst_off_bytes[b2]; });
+  for (size_t oi = 0; oi < n; ++oi) {
+    const size_t i = order[oi];
     if (nbytes[i] == 0) continue;
     if (src_ptrs[i] == 0 && !(flags[i] & SEG_ZERO_FILL)) { inplace = true; continue; }   // already in the bucket
     PackSeg s;
@@ -548,6 +594,7 @@ bool BucketSet::set_pack(int g, const std::vector<int64_t>& src_ptrs, const std:
     DEAR_CHECK(s.dst_off % 16 == 0, "set_pack: destination offsets must be 16-byte aligned");
     DEAR_CHECK((reinterpret_cast<uintptr_t>(s.src) % 16) == 0, "set_pack: gradient storage must be 16-byte aligned");
     DEAR_CHECK(s.nbytes % 2 == 0 && s.dst_off + s.nbytes <= static_cast<uint64_t>(b.padded) * es, "set_pack: segment out of range");
+    DEAR_CHECK(segs.empty() || segs.back().dst_off + segs.back().nbytes <= s.dst_off, "set_pack: segments overlap");
     tiles += static_cast<uint32_t>((s.nbytes + kPackTileBytes - 1) / kPackTileBytes);
     segs.push_back(s);
   }
@@ -609,6 +656,7 @@ void BucketSet::fence_current_to_comm() {
   if (!comm_->is_cuda()) return;
   DEAR_CUDA(cudaEventRecord(E(ev_fence_), current_stream(comm_->options().device)));
   DEAR_CUDA(cudaStreamWaitEvent(S(stream_), E(ev_fence_), 0));
+  if (ag_stream_ != stream_) DEAR_CUDA(cudaStreamWaitEvent(S(ag_stream_), E(ev_fence_), 0));
 }
 
 void BucketSet::reduce_scatter(int g, bool pack) {
@@ -640,7 +688,17 @@ void BucketSet::reduce_scatter(int g, bool pack) {
   if (cuda) {
     DEAR_CUDA(cudaEventRecord(E(b.ev_in), current_stream(comm_->options().device)));
     DEAR_CUDA(cudaStreamWaitEvent(S(stream_), E(b.ev_in), 0));
-    launch_rs(p, grid_for(b.padded * static_cast<int64_t>(dtype_size(dtype_)), comm_->options().rs_grid), S(stream_));
+    // the previous update kernel of this bucket (other stream) must have consumed the reduced shard it overwrites
+    if (ag_stream_ != stream_ && b.ag_pending) DEAR_CUDA(cudaStreamWaitEvent(S(stream_), E(b.ag_done), 0));
+    if (b.rs_algo == RS_ALGO_PIPE) {
+      p.nstripes = b.nstripes;
+      p.stripe_bytes = b.stripe_bytes;
+      p.mc_grad = nullptr;
+      launch_rs_pipe(p, b.rs_grid, S(stream_));
+    } else {
+      if (b.rs_algo != RS_ALGO_NVLS) p.mc_grad = nullptr;
+      launch_rs(p, b.rs_grid, S(stream_));
+    }
     DEAR_CUDA(cudaEventRecord(E(b.rs_done), S(stream_)));
   } else {
     emu_rs(p);
@@ -689,8 +747,13 @@ void BucketSet::allgather_update(int g, bool do_update, bool first_step, bool en
   p.status = cuda ? status_word_device() : status_word_host();
   p.timeout_ns = comm_->timeout_ns();
   if (cuda) {
-    launch_ag(p, grid_for(b.shard * 16, comm_->options().ag_grid), S(stream_));
-    DEAR_CUDA(cudaEventRecord(E(b.ag_done), S(stream_)));
+    if (ag_stream_ != stream_) {
+      // everything queued on the reduce-scatter stream so far (this step's reduce-scatters, table uploads)
+      DEAR_CUDA(cudaEventRecord(E(ev_fence_ag_), S(stream_)));
+      DEAR_CUDA(cudaStreamWaitEvent(S(ag_stream_), E(ev_fence_ag_), 0));
+    }
+    launch_ag(p, grid_for(b.shard * 16, comm_->options().ag_grid), S(ag_stream_));
+    DEAR_CUDA(cudaEventRecord(E(b.ag_done), S(ag_stream_)));
   } else {
     emu_ag(p);
   }
@@ -712,13 +775,28 @@ void BucketSet::wait_rs(int g) {
 
 void BucketSet::wait_all() {
   if (!comm_->is_cuda()) return;
-  // everything on the comm stream is ordered, so one fresh event covers all buckets
+  // each comm stream is ordered, so one fresh event per stream covers all buckets
   DEAR_CUDA(cudaEventRecord(E(ev_fence_), S(stream_)));
   DEAR_CUDA(cudaStreamWaitEvent(current_stream(comm_->options().device), E(ev_fence_), 0));
+  if (ag_stream_ != stream_) {
+    DEAR_CUDA(cudaEventRecord(E(ev_fence_ag_), S(ag_stream_)));
+    DEAR_CUDA(cudaStreamWaitEvent(current_stream(comm_->options().device), E(ev_fence_ag_), 0));
+  }
+}
+
+std::string BucketSet::rs_plan(int g) const {
+  const auto& b = buckets_.at(g);
+  static const char* names[] = {"oneshot", "pipe", "nvls"};
+  Msg o;
+  o << names[b.rs_algo] << ":grid=" << b.rs_grid << ":stripes=" << b.nstripes << ":stripe_bytes=" << b.stripe_bytes;
+  return o.str();
 }
 
 void BucketSet::synchronize() {
-  if (comm_->is_cuda()) DEAR_CUDA(cudaStreamSynchronize(S(stream_)));
+  if (comm_->is_cuda()) {
+    DEAR_CUDA(cudaStreamSynchronize(S(stream_)));
+    if (ag_stream_ != stream_) DEAR_CUDA(cudaStreamSynchronize(S(ag_stream_)));
+  }
   comm_->check_status();
 }
 

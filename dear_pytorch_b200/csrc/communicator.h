@@ -37,6 +37,12 @@ struct CommOptions {
   int rs_grid = 96;
   int ag_grid = 96;
   int gen_grid = 8;
+  // Kernel A variant per bucket: -1 = pick by bucket size (one-shot below `pipe_min_bytes`, stripe-pipelined TMA
+  // pull above, NVLS ld_reduce only on request); 0 / 1 / 2 force RS_ALGO_ONESHOT / _PIPE / _NVLS for every bucket.
+  int rs_algo = -1;
+  int64_t pipe_min_bytes = 2ll << 20;
+  int64_t stripe_target_bytes = 8ll << 20;   // bucket bytes per stripe the pipelined kernel aims for
+  bool separate_ag_stream = true;            // all-gathers on their own stream (reference: three communicators)
 };
 
 class Communicator : public std::enable_shared_from_this<Communicator> {
@@ -128,6 +134,8 @@ class BucketSet {
                  const std::vector<int64_t>& opt, const std::vector<double>& beta2, const std::vector<double>& eps);
 
   void reduce_scatter(int g, bool pack);
+  // (algorithm, stripes, grid) chosen for bucket g at construction time: {"algo": "oneshot|pipe|nvls", ...}
+  std::string rs_plan(int g) const;
   void allgather_update(int g, bool do_update, bool first_step, bool entry_barrier, bool zero_grad);
   void fence_current_to_comm();
   void wait_bucket(int g);
@@ -163,6 +171,10 @@ class BucketSet {
     Staging stage_pack, stage_hyper;
     std::vector<void*> captured_pinned;   // owned by captured memcpy nodes; freed with the BucketSet
     bool pack_captured = false;           // a graph restores pack_dev on replay: eager uploads can never be skipped
+    int rs_algo = RS_ALGO_ONESHOT;
+    uint32_t nstripes = 1;
+    uint64_t stripe_bytes = 0;
+    int rs_grid = 1;
     void* ev_in = nullptr;
     void* rs_done = nullptr;
     void* ag_done = nullptr;
@@ -176,12 +188,15 @@ class BucketSet {
   std::vector<Bucket> buckets_;
   int dtype_;
   bool with_grad_;
-  void* stream_ = nullptr;   // cudaStream_t (high priority)
+  void* stream_ = nullptr;      // cudaStream_t (high priority): reduce-scatters, table uploads
+  void* ag_stream_ = nullptr;   // cudaStream_t: update + all-gather kernels (== stream_ unless separate_ag_stream)
   void* ev_fence_ = nullptr;
+  void* ev_fence_ag_ = nullptr;
 };
 
 // device launchers (kernels.cu) and host emulation (emu.cpp)
 void launch_rs(const RSParams& p, int grid, cudaStream_t s);
+void launch_rs_pipe(const RSParams& p, int grid, cudaStream_t s);
 void launch_ag(const AGParams& p, int grid, cudaStream_t s);
 void launch_gen(const GenParams& p, int grid, cudaStream_t s);
 void emu_rs(const RSParams& p);

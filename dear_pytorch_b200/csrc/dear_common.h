@@ -178,6 +178,24 @@ struct RSParams {
   int dtype;               // DType of the gradient bucket
   uint32_t* status;        // host-mapped status word
   uint64_t timeout_ns;
+  // stripe-pipelined variant (rs_pipe.cu): the shard is cut into `nstripes` stripes of `stripe_bytes`
+  // (a multiple of kPipePackPiece); stripe k of EVERY shard is packed and published before stripe k+1
+  uint32_t nstripes;
+  uint32_t reserved;
+  uint64_t stripe_bytes;
+};
+
+// RS_READY flag encoding shared by both reduce-scatter kernels: (epoch << 8) | stripes_published; the one-shot
+// kernel publishes kAllStripes.  Monotonic, so the wrap-safe ">=" wait works for either producer.
+constexpr uint32_t kAllStripes = 255u;
+constexpr uint32_t kMaxStripes = 64u;
+constexpr uint32_t kPipeChunk = 16384;        // bytes per TMA bulk copy of the pull ring
+constexpr uint32_t kPipePackPiece = 32768;    // bytes per pack work item
+
+enum RsAlgo : int {
+  RS_ALGO_ONESHOT = 0,    // pack, one cross-GPU flag round, pull with 128-bit loads (small buckets: fewest sync rounds)
+  RS_ALGO_PIPE = 1,       // stripe-pipelined: pack warps + TMA (cp.async.bulk) pull ring + shared-memory reduce
+  RS_ALGO_NVLS = 2,       // pack, then multimem.ld_reduce (the NVSwitch reduces); needs a multicast-bound arena
 };
 
 // Kernel B: fused [sharded SGD/momentum update] + push of the updated

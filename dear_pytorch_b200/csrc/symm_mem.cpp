@@ -13,7 +13,7 @@
 
 #include <chrono>
 #include <cstring>
-#include <sstream>
+#include "dear_msg.h"
 #include <stdexcept>
 #include <thread>
 
@@ -22,7 +22,7 @@ namespace dear {
 #define DEAR_CHECK(cond, msg)                                                        \
   do {                                                                               \
     if (!(cond)) {                                                                   \
-      std::ostringstream _oss;                                                       \
+      dear::Msg _oss;                                                                     \
       _oss << "dear: " << msg << " (" << __FILE__ << ":" << __LINE__ << ")";         \
       throw std::runtime_error(_oss.str());                                          \
     }                                                                                \
@@ -32,7 +32,7 @@ namespace dear {
   do {                                                                               \
     cudaError_t _e = (expr);                                                         \
     if (_e != cudaSuccess) {                                                         \
-      std::ostringstream _oss;                                                       \
+      dear::Msg _oss;                                                                     \
       _oss << "dear: CUDA error '" << cudaGetErrorString(_e) << "' in " #expr " ("   \
            << __FILE__ << ":" << __LINE__ << ")";                                    \
       throw std::runtime_error(_oss.str());                                          \
@@ -61,7 +61,7 @@ Fn driver_fn(const char* name) {
   do {                                                                               \
     CUresult _r = (call);                                                            \
     if (_r != CUDA_SUCCESS) {                                                        \
-      std::ostringstream _oss;                                                       \
+      dear::Msg _oss;                                                                     \
       _oss << "dear: driver error " << int(_r) << " in " #call " (" << __FILE__      \
            << ":" << __LINE__ << ")";                                                \
       throw std::runtime_error(_oss.str());                                          \

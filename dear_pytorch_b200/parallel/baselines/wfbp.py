@@ -8,7 +8,12 @@ Horovod).  Behaviour kept:
     (wfbp/dopt.py:380-486), ASC variant (hv_distributed_optimizer.py:353-427);
   * dense path = one all-reduce per group launched from the gradient hook; ``step()`` =
     synchronise, average, then the wrapped optimizer's own ``step()`` (wfbp/dopt.py:694-701,807-968);
-  * sparse path = compress + all-gather of (values, indices) (wfbp/dopt.py:703-742).
+  * sparse path = compress + all-gather of (values, indices) (wfbp/dopt.py:703-742), or — for the ``gtopk*``
+    compressors — the log2(P)-round gTop-k exchange over ``Comm.sendrecv`` (wfbp/dopt.py:50-106,725-728);
+  * momentum correction for sparsified training (``momentum_correction=True``; wfbp/dopt.py:769-775,906-953): the
+    velocity ``u = m*u + g`` is accumulated locally BEFORE sparsification and is what gets compressed and
+    communicated; ``step()`` then applies ``p -= lr*(avg + wd*p)`` without another momentum pass and masks the
+    velocity where it was sent (momentum-factor masking via the compressor's ``zero_conditions``).
 Deliberate differences: the comm stream waits on the compute stream with an event (the reference
 synchronises the host inside the hook, wfbp/dopt.py:696); collectives are torch.distributed NCCL
 (comm_core / Horovod are not installable here).
@@ -142,7 +147,7 @@ def mgs_groups(sizes: Sequence[int], tb: Sequence[float], world: int, density: f
 class _DistributedOptimizer(torch.optim.Optimizer):
     def __init__(self, params, named_parameters, compression=None, is_sparse=False, density=0.001,
                  seq_layernames=None, layerwise_times=None, norm_clip=None, threshold=0, fp16=False, mgwfbp=False,
-                 asc=False, mgs=False, rdma=False, alpha=None, beta=None, verbose=True):
+                 asc=False, mgs=False, rdma=False, alpha=None, beta=None, verbose=True, momentum_correction=False):
         super(self.__class__, self).__init__(params)
         if not runtime.is_initialized():
             runtime.init()
@@ -152,6 +157,11 @@ class _DistributedOptimizer(torch.optim.Optimizer):
         self._sparse = bool(is_sparse) and not isinstance(self._compression, NoneCompressor)
         self._density = density
         self._norm_clip = norm_clip
+        self._gtopk = self._sparse and "gtopk" in getattr(self._compression, "name", "")
+        self._mc = bool(momentum_correction) and self._sparse
+        if self._mc and not isinstance(self, torch.optim.SGD):
+            raise TypeError("momentum correction is defined for SGD with momentum (wfbp/dopt.py:906-953)")
+        self._comm = None
         named = list(named_parameters)
         self._names = {p: n for n, p in named if p.requires_grad}
         self._params = [p for _, p in named if p.requires_grad]
@@ -216,10 +226,25 @@ class _DistributedOptimizer(torch.optim.Optimizer):
         n = self._names[p]
         gi = self._group_of[n]
         a, b = self._offsets[n]
-        self._buffers[gi][a:b].copy_(p.grad.reshape(-1))
+        d_p = p.grad
+        if self._mc:
+            # momentum correction: sparsify the locally accumulated velocity, not the raw gradient
+            st = self.state[p]
+            buf = st.get("momentum_buffer")
+            if buf is None:
+                buf = st["momentum_buffer"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            buf.mul_(self._momentum_of(p)).add_(d_p)
+            d_p = buf
+        self._buffers[gi][a:b].copy_(d_p.reshape(-1))
         self._arrived[gi] += 1
         if self._arrived[gi] == len(self._groups[gi]):
             self._launch(gi)
+
+    def _momentum_of(self, p):
+        for g in self.param_groups:
+            if any(q is p for q in g["params"]):
+                return g.get("momentum", 0.0)
+        return 0.0
 
     def _launch(self, gi):
         buf = self._buffers[gi]
@@ -232,6 +257,20 @@ class _DistributedOptimizer(torch.optim.Optimizer):
                 name = "group-%d" % gi
                 _, idx, vals = self._compression.compress(buf, name, ratio=self._density)
                 k = idx.numel()
+                if self._gtopk:
+                    # global top-k of the SUM in log2(P) pairwise rounds; every rank ends with the same k entries
+                    from ..comm import Comm
+                    from .gtopk import gtopk_sparse_recursive_allreduce
+                    if self._comm is None:
+                        self._comm = Comm()
+                    gv, gidx = gtopk_sparse_recursive_allreduce(self._comm, vals, idx, buf.numel(), k)
+                    # locally selected values that did not survive the global cut return to the residual
+                    lost = (~torch.isin(idx, gidx)).nonzero().view(-1)
+                    keep = torch.ones(k, dtype=torch.bool, device=idx.device)
+                    keep[lost] = False
+                    self._compression.add_residuals(keep.nonzero().view(-1), name)
+                    self._launched[gi] = ("gtopk", gv, gidx)
+                    return
                 all_vals = torch.empty(k * self._world, dtype=vals.dtype, device=buf.device)
                 all_idx = torch.empty(k * self._world, dtype=idx.dtype, device=buf.device)
                 dist.all_gather_into_tensor(all_vals, vals.contiguous(), group=self._group)
@@ -255,7 +294,11 @@ class _DistributedOptimizer(torch.optim.Optimizer):
         for gi, g in enumerate(self._groups):
             buf = self._buffers[gi]
             res = self._launched.pop(gi)
-            if self._sparse:
+            if self._sparse and res[0] == "gtopk":
+                _, gv, gidx = res
+                buf.zero_()
+                buf.index_add_(0, gidx, gv.to(buf.dtype))
+            elif self._sparse:
                 all_vals, all_idx = res
                 buf.zero_()
                 buf.scatter_add_(0, all_idx, all_vals)
@@ -265,6 +308,8 @@ class _DistributedOptimizer(torch.optim.Optimizer):
                 p = self._by_name[n]
                 if p.grad is not None:
                     p.grad.copy_(buf[a:b].view_as(p.grad))
+            if not self._sparse:
+                buf.zero_()          # a parameter that misses its gradient next iteration must contribute zeros
             self._arrived[gi] = 0
         if self._norm_clip is not None:
             torch.nn.utils.clip_grad_norm_(self._params, self._norm_clip)
@@ -275,14 +320,41 @@ class _DistributedOptimizer(torch.optim.Optimizer):
             with torch.enable_grad():
                 loss = closure()
         self.synchronize()
-        super(self.__class__, self).step()
+        if self._mc and self._world > 1:
+            self._step_with_momentum_correction()
+        else:
+            super(self.__class__, self).step()
         return loss
+
+    @torch.no_grad()
+    def _step_with_momentum_correction(self):
+        """wfbp/dopt.py:906-953: the communicated quantity already IS the (sparsified, averaged) velocity."""
+        for group in self.param_groups:
+            wd, lr = group["weight_decay"], group["lr"]
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                d_p = p.grad
+                if wd != 0:
+                    d_p = d_p.add(p, alpha=wd)
+                p.add_(d_p, alpha=-lr)
+                n = self._names.get(p)
+                if n is None:
+                    continue
+                # momentum-factor masking: forget the velocity where it was just sent
+                gi = self._group_of[n]
+                zc = self._compression.zero_conditions.get("group-%d" % gi)
+                buf = self.state[p].get("momentum_buffer")
+                if zc is not None and buf is not None:
+                    a, b = self._offsets[n]
+                    buf.view(-1).mul_(zc[a:b].to(buf.dtype))
 
 
 def DistributedOptimizer(optimizer, named_parameters=None, model: Optional[nn.Module] = None, compression=None,
                          is_sparse=False, density=0.001, seq_layernames=None, layerwise_times=None, norm_clip=None,
                          threshold=0, writer=None, gradient_path=None, fp16=False, mgwfbp=False, asc=False, mgs=False,
-                         rdma=False, multi_job_scheduling=False, alpha=None, beta=None, verbose=True, **ignored):
+                         rdma=False, multi_job_scheduling=False, alpha=None, beta=None, verbose=True,
+                         momentum_correction=False, **ignored):
     """WFBP (``threshold=0``), threshold fusion, MG-WFBP (``mgwfbp=True``) or ASC (``asc=True``)."""
     if named_parameters is None:
         if model is None:
@@ -294,4 +366,4 @@ def DistributedOptimizer(optimizer, named_parameters=None, model: Optional[nn.Mo
     return cls(optimizer.param_groups, list(named_parameters), compression=compression, is_sparse=is_sparse,
                density=density, seq_layernames=seq_layernames, layerwise_times=layerwise_times, norm_clip=norm_clip,
                threshold=threshold, fp16=fp16, mgwfbp=mgwfbp, asc=asc, mgs=mgs, rdma=rdma, alpha=alpha, beta=beta,
-               verbose=verbose)
+               verbose=verbose, momentum_correction=momentum_correction)

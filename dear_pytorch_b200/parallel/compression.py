@@ -69,13 +69,19 @@ class TopKCompressor:
         vals = flat[idx]
         res.copy_(flat)
         res[idx] = 0.0
-        self.values[name], self.indexes[name] = vals, idx
         zc = self.zero_conditions.get(name)
         if zc is None or zc.numel() != flat.numel():
             zc = self.zero_conditions[name] = torch.ones_like(flat, dtype=torch.float32)
         zc.fill_(1.0)
         zc[idx] = 0.0
         self.zc = zc
+        if idx.numel() < k:
+            # data-dependent selectors (gaussian) may return fewer than k entries: every rank must contribute the
+            # SAME number to the all-gather, so pad with (index 0, value 0), which adds nothing when scattered
+            pad = k - idx.numel()
+            idx = torch.cat([idx, idx.new_zeros(pad)])
+            vals = torch.cat([vals, vals.new_zeros(pad)])
+        self.values[name], self.indexes[name] = vals, idx
         return tensor, idx, vals
 
     @torch.no_grad()
@@ -93,6 +99,20 @@ class TopKCompressor:
 
 class EFTopKCompressor(TopKCompressor):
     name = "eftopk"
+    error_feedback = True
+
+
+class GTopKCompressor(TopKCompressor):
+    """Local top-k selection for the gTop-k sparse all-reduce (Shi et al., ICDCS 2019): the optimizer exchanges the
+    selections pairwise in log2(P) rounds (``baselines.gtopk``) and calls ``add_residuals`` so that locally selected
+    values that did not survive the global cut go back into the residual.  The reference keys this path off the
+    compressor's name (``'gtopk' in name``, wfbp/dopt.py:725-726) but never registers such a compressor."""
+    name = "gtopk"
+    error_feedback = False
+
+
+class EFGTopKCompressor(GTopKCompressor):
+    name = "gtopkef"
     error_feedback = True
 
 
@@ -198,6 +218,8 @@ compressors = {
     "topk": TopKCompressor,
     "eftopk": EFTopKCompressor,
     "gaussian": GaussianCompressor,
+    "gtopk": GTopKCompressor,
+    "gtopkef": EFGTopKCompressor,
     "signum": SignCompressor,
     "efsignum": EFSignCompressor,
 }

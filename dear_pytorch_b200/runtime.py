@@ -139,12 +139,21 @@ def init(backend: Optional[str] = None, device: Optional[torch.device] = None, *
         o.rs_grid = _env_int("DEAR_RS_GRID", 128 if world == 1 else 32)
         o.ag_grid = _env_int("DEAR_AG_GRID", 128 if world == 1 else 32)
         o.gen_grid = _env_int("DEAR_GEN_GRID", 8)
+        # Kernel A variant per bucket: by size unless forced (DEAR_RS_ALGO=oneshot|pipe|nvls); csrc/communicator.h
+        algo = os.environ.get("DEAR_RS_ALGO", "auto").lower()
+        if algo not in ("auto", "oneshot", "pipe", "nvls"):
+            raise ValueError("DEAR_RS_ALGO must be auto, oneshot, pipe or nvls")
+        o.rs_algo = {"auto": -1, "oneshot": 0, "pipe": 1, "nvls": 2}[algo]
+        o.pipe_min_bytes = int(float(os.environ.get("DEAR_PIPE_MIN_MB", "2")) * (1 << 20))
+        o.stripe_target_bytes = int(float(os.environ.get("DEAR_STRIPE_MB", "8")) * (1 << 20))
+        o.separate_ag_stream = os.environ.get("DEAR_AG_STREAM", "1") not in ("0", "false", "False")
         # rendezvous keys must be unique per init(): a re-initialised process group can land on the SAME TCPStore server
         # (multi-tenant stores are shared per port), where the previous communicator's barrier counters still exist
         global _init_seq
         _init_seq += 1
         comm = C.Communicator(rank, world, store, "dear%d_%d" % (_env_int("DEAR_JOB_SEQ", 0), _init_seq), o)
-        opts = dict(provider=prov, multicast=o.multicast, rs_grid=o.rs_grid, ag_grid=o.ag_grid)
+        opts = dict(provider=prov, multicast=o.multicast, rs_grid=o.rs_grid, ag_grid=o.ag_grid, rs_algo=algo,
+                    separate_ag_stream=o.separate_ag_stream)
 
     _state = _State(backend=backend, rank=rank, world=world, local_rank=local_rank, local_size=local_size,
                     device=device, comm=comm, group=group, owns_pg=owns_pg, options=opts)

@@ -25,7 +25,7 @@ CXX_FLAGS = ["-O2", "-std=c++17", "-Wno-unused-function"]
 ext = CUDAExtension(
     name="dear_pytorch_b200._C",
     sources=[os.path.join(CSRC, f) for f in
-             ("bindings.cpp", "communicator.cpp", "symm_mem.cpp", "emu.cpp", "kernels.cu", "bn_act.cu", "ln_fused.cu")],
+             ("bindings.cpp", "communicator.cpp", "symm_mem.cpp", "emu.cpp", "kernels.cu", "rs_pipe.cu", "bn_act.cu", "ln_fused.cu")],
     include_dirs=[os.path.join(ROOT, CSRC)],
     extra_compile_args={"cxx": CXX_FLAGS, "nvcc": NVCC_FLAGS},
     libraries=["rt"],

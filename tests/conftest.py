@@ -9,13 +9,6 @@ if ROOT not in sys.path:
 os.environ.setdefault("PYTHONPATH", ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
 
 
-def unvalidated(what):
-    """Marker for GPU tests of code that was written after a round's GPU budget was spent and has therefore never
-    run on hardware: skipped unless DEAR_TEST_UNVALIDATED=1 (tools/gpu/next_round_first.sh sets it)."""
-    return pytest.mark.skipif(not os.environ.get("DEAR_TEST_UNVALIDATED"),
-                              reason="%s has not been run on hardware yet; set DEAR_TEST_UNVALIDATED=1" % what)
-
-
 def pytest_configure(config):
     import torch
     torch.set_num_threads(1)      # no OpenMP pool in the parent: children are forked

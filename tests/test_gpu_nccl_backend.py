@@ -46,8 +46,6 @@ def _gpus():
 def test_dear_engine_on_nccl_backend(world):
     if world > 1 and _gpus() < world:
         pytest.skip("needs %d physical GPUs" % world)
-    if world == 1 and not os.environ.get("DEAR_TEST_UNVALIDATED"):
-        pytest.skip("the CUDA path of the nccl backend has not been run on hardware yet; set DEAR_TEST_UNVALIDATED=1")
     case = dict(momentum=0.9, weight_decay=1e-3)
     ref = reference_run(case, 4, world, 4)
     for params in run_ranks(nccl_worker, world=world, backend="nccl", args=(case, 4, 4, "dear"), timeout=300):

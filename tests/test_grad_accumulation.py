@@ -5,7 +5,6 @@ import torch
 import torch.nn as nn
 
 from _mp import run_ranks
-from conftest import unvalidated
 from test_dear_equivalence import data, make_model, reference_run
 
 
@@ -76,7 +75,6 @@ def gpu_worker(rank, world, case, steps, per_rank, k):
 
 
 @pytest.mark.gpu
-@unvalidated("gradient accumulation on the fused CUDA path")
 @pytest.mark.parametrize("world", [1, 2])
 def test_accumulation_on_gpu(world):
     case = dict(momentum=0.9, weight_decay=1e-3)

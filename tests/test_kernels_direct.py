@@ -115,6 +115,62 @@ def test_cuda_kernels_match_reference(world, dtype_name):
     assert all(o == outs[0] for o in outs)
 
 
+PIPE_ENV = {"DEAR_SPIN_TIMEOUT_S": "15", "DEAR_RS_ALGO": "pipe", "DEAR_PIPE_MIN_MB": "0", "DEAR_STRIPE_MB": "0.0625"}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype_name", ["fp32", "bf16"])
+@pytest.mark.parametrize("world", [2, 4])
+def test_cuda_pipelined_reduce_scatter_matches_reference(world, dtype_name):
+    """Kernel A, stripe-pipelined variant (csrc/rs_pipe.cu: pack warps + TMA bulk-copy pull ring + shared-memory
+    reduce) forced onto the small test bucket with 64 KB stripes, so several stripes, partial chunks, segment tails,
+    zero-fill and in-place segments all go through it; same fp32 oracle as the one-shot kernel."""
+    ngpu = torch.cuda.device_count()
+    if ngpu > 1 and ngpu < world:
+        pytest.skip("needs %d GPUs (or exactly one, shared)" % world)
+    outs = run_ranks(kernel_worker, world=world, backend="b200", args=(True, dtype_name, 5), extra_env=PIPE_ENV, timeout=300)
+    assert all(o == outs[0] for o in outs)
+
+
+def plan_worker(rank, world):
+    import dear_pytorch_b200 as dear
+    from dear_pytorch_b200 import ops
+    C = ops.require_native()
+    bs = C.BucketSet(dear.communicator(), [world * 65536, world * 8 * 1024 * 1024], C.DT_F32, True)
+    return [bs.rs_plan(0), bs.rs_plan(1)]
+
+
+@pytest.mark.gpu
+def test_reduce_scatter_algorithm_is_picked_per_bucket_size():
+    small, big = run_ranks(plan_worker, world=2, backend="b200", extra_env={"DEAR_SPIN_TIMEOUT_S": "15"}, timeout=300)[0]
+    assert small.startswith("oneshot"), small      # 512 KB: latency-bound, fewest flag rounds
+    assert big.startswith("pipe") and "stripes=8" in big, big      # 64 MB: stripe-pipelined TMA pull
+
+
+def nvls_worker(rank, world, dtype_name):
+    import dear_pytorch_b200 as dear
+    from dear_pytorch_b200 import ops
+    C = ops.require_native()
+    probe = C.BucketSet(dear.communicator(), [world * 4096], C.DT_F32, True)
+    if not probe.has_multicast():
+        return "no-multicast"
+    del probe
+    return kernel_worker(rank, world, True, dtype_name, 5)
+
+
+@pytest.mark.gpu
+@pytest.mark.multigpu
+@pytest.mark.parametrize("dtype_name", ["fp32", "bf16"])
+def test_cuda_nvls_multicast_kernels_match_reference(dtype_name):
+    """The MC=true instantiations: multimem.ld_reduce in Kernel A, multimem.st in Kernel B (VMM arena bound to an
+    NVLS multicast object).  Needs >= 2 GPUs behind an NVSwitch."""
+    env = {"DEAR_SPIN_TIMEOUT_S": "15", "DEAR_PROVIDER": "vmm", "DEAR_MULTICAST": "1", "DEAR_RS_ALGO": "nvls"}
+    outs = run_ranks(nvls_worker, world=2, backend="b200", args=(dtype_name,), extra_env=env, timeout=300)
+    if outs[0] == "no-multicast":
+        pytest.skip("this box cannot create an NVLS multicast object")
+    assert all(o == outs[0] for o in outs)
+
+
 def adam_worker(rank, world, use_cuda, dtype_name, seed):
     """Kernel B with the Adam / AdamW epilogue against torch.optim.Adam(W) on the averaged gradient."""
     import dear_pytorch_b200 as dear

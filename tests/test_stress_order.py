@@ -1,6 +1,8 @@
 """Skewed ranks, many tiny buckets, shared parameters, execution order != registration order, eval-mode
 forwards between training steps (protocol robustness; §8.2 ordering rules)."""
 import random
+
+import pytest
 import time
 
 import torch
@@ -107,3 +109,46 @@ def test_unused_layer_and_single_bucket_emu():
     outs = run_ranks(worker, world=3, backend="emu", args=(4, 2, -1, 0.001))
     assert outs[0][1] == 1
     check(outs, ref)
+
+
+def _skip_worker(rank, world):
+    """A parameter without a gradient is skipped like torch.optim does (no weight decay, no momentum decay)."""
+    import torch
+    import torch.nn as nn
+    import dear_pytorch_b200 as dear
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.used = nn.Linear(8, 8)
+            self.unused = nn.Linear(8, 8)
+
+        def forward(self, x):
+            return self.used(x)
+
+    torch.manual_seed(0)
+    model, ref = Net(), Net()
+    ref.load_state_dict(model.state_dict())
+    kw = dict(lr=0.1, weight_decay=0.1, momentum=0.9)
+    opt = dear.DistributedOptimizer(torch.optim.SGD(model.parameters(), **kw), model, threshold=None, num_nearby_layers=1,
+                                    verbose=False)
+    ropt = torch.optim.SGD(ref.parameters(), **kw)
+    g = torch.Generator().manual_seed(5)
+    for _ in range(3):
+        x = torch.randn(world * 4, 8, generator=g)
+        opt.zero_grad()
+        model(x[rank * 4:(rank + 1) * 4]).pow(2).mean().backward()
+        opt.step()
+        ropt.zero_grad()
+        ref(x).pow(2).mean().backward()
+        ropt.step()
+    opt.synchronize()
+    return [(n, p.detach().clone(), dict(ref.named_parameters())[n].detach().clone()) for n, p in model.named_parameters()]
+
+
+@pytest.mark.parametrize("backend", ["gloo", "emu"])
+def test_parameters_without_gradient_are_not_updated(backend):
+    from _mp import run_ranks
+    for out in run_ranks(_skip_worker, world=2, backend=backend):
+        for n, a, b in out:
+            torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-6, msg=lambda m: "%s: %s" % (n, m))

@@ -3,7 +3,6 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from conftest import unvalidated
 from dear_pytorch_b200.ops.tc_gemm import fused_ffn, linear_bias, require_tc, tc_launches
 
 
@@ -70,7 +69,6 @@ def test_ffn_dgelu(M, K, N):
 
 
 @pytest.mark.gpu
-@unvalidated("the hand-written tcgen05 kernel (csrc/tc_ffn_hw.cu)")
 @pytest.mark.parametrize("M,K,N", [(128, 64, 256), (2048, 1024, 4096), (300, 72, 264), (1, 8, 8)])
 def test_handwritten_ffn_up(M, K, N):
     tc = require_tc()
@@ -85,7 +83,6 @@ def test_handwritten_ffn_up(M, K, N):
 
 
 @pytest.mark.gpu
-@unvalidated("the hand-written tcgen05 kernel (csrc/tc_ffn_hw.cu)")
 @pytest.mark.parametrize("M,K,N", [(128, 64, 256), (2048, 1024, 4096), (300, 72, 264), (5, 8, 16)])
 def test_handwritten_ffn_dgelu(M, K, N):
     tc = require_tc()

@@ -13,7 +13,7 @@ def worker(rank, world, kind, steps, per_rank):
     import dear_pytorch_b200 as dear
     from dear_pytorch_b200.parallel import variants
     from dear_pytorch_b200.parallel.baselines import WFBPDistributedOptimizer, wrap_ddp
-    from dear_pytorch_b200.parallel.baselines.horovod_like import ByteSchedulerLikeOptimizer, HorovodLikeOptimizer
+    from dear_pytorch_b200.parallel.baselines import ByteSchedulerOptimizer, HorovodOptimizer
     from dear_pytorch_b200.utils.profiling import benchmark
     model = make_model()
     model.eval()
@@ -36,9 +36,9 @@ def worker(rank, world, kind, steps, per_rank):
         opt = WFBPDistributedOptimizer(opt, model=model, seq_layernames=seq, layerwise_times=times, mgwfbp=(kind == "mgwfbp"),
                                        asc=(kind == "asc"), alpha=1e-4, beta=1e-9, verbose=False)
     elif kind == "horovod":
-        opt = HorovodLikeOptimizer(opt, model, verbose=False)
+        opt = HorovodOptimizer(opt, model, cycle_time_ms=0.2, fusion_threshold_mb=0.002, negotiation_steps=2, verbose=False)
     elif kind == "bytescheduler":
-        opt = ByteSchedulerLikeOptimizer(opt, model, partition_mb=0.001, verbose=False)
+        opt = ByteSchedulerOptimizer(opt, model, partition=100, credit=250, verbose=False)
     elif kind in ("ddp", "ddp-zero"):
         fwd, opt = wrap_ddp(model, torch.optim.SGD, dict(lr=0.05, **CASE), zero=(kind == "ddp-zero"))
     if kind not in ("ddp", "ddp-zero"):
@@ -49,11 +49,15 @@ def worker(rank, world, kind, steps, per_rank):
         opt.zero_grad()
         nn.functional.cross_entropy(fwd(x), y).backward()
         opt.step()
-    if hasattr(opt, "synchronize") and kind in ("naive", "wt", "rb"):
+    if hasattr(opt, "synchronize") and kind in ("naive", "wt", "rb", "bytescheduler"):
         opt.synchronize()
     info = None
     if kind == "wt":
         info = (opt.wait_time.done, len(opt.engine.plan.buckets))
+    elif kind == "horovod":
+        info = (opt.groups, len(list(model.parameters())))
+    elif kind == "bytescheduler":
+        info = (list(opt.launch_log), opt.partition, opt.credit)
     return [p.detach().clone() for p in model.parameters()], info
 
 
@@ -68,6 +72,62 @@ def test_variant_matches_sgd(kind):
             torch.testing.assert_close(a, b, rtol=3e-5, atol=3e-6)
         if kind == "wt":
             assert info[0] and info[1] >= 1
+        if kind == "horovod":
+            groups, ntensors = info
+            assert groups is not None and sum(len(g) for g in groups) == ntensors      # response cache was built
+            assert groups == outs[0][1][0]                                             # identical on every rank
+        if kind == "bytescheduler":
+            log, partition, credit = info
+            assert log == outs[0][1][0]                                                # same collective order on every rank
+            assert max(n for _, _, n in log) <= partition and any(i > 0 for _, i, _ in log)   # tensors were partitioned
+
+
+def test_horovod_cycle_grouping():
+    from dear_pytorch_b200.parallel.baselines import cycle_groups
+    t = [0.0, 1.0, 4.9, 5.1, 6.0, 20.0]                    # ms since the first gradient
+    nb = [10, 10, 10, 10, 10, 10]
+    assert cycle_groups(t, nb, 5.0, 1 << 20) == [[0, 1, 2], [3, 4], [5]]           # cut at cycle boundaries
+    assert cycle_groups(t, nb, 5.0, 25) == [[0, 1], [2], [3, 4], [5]]              # ... and at the fusion threshold
+    assert cycle_groups(t, nb, 0.0, 1 << 20) == [[i] for i in range(6)]            # HOROVOD_CYCLE_TIME=0: no fusion
+    assert cycle_groups(t, [100] * 6, 5.0, 50) == [[i] for i in range(6)]          # oversized tensors travel alone
+
+
+def test_bytescheduler_priority_and_credit():
+    """Single process, fake collectives: chunks leave in forward-priority order under the credit."""
+    import heapq
+    from dear_pytorch_b200.parallel.baselines import partition_sizes
+    from dear_pytorch_b200.parallel.baselines.bytescheduler import _Chunk
+    assert partition_sizes(10, 4) == [4, 4, 2] and partition_sizes(3, 4) == [3] and partition_sizes(8, 0) == [8]
+    heap = []
+    for prio, n in [(5, 3), (2, 2), (7, 1), (0, 2)]:           # arrival order = backward order (last layers first)
+        for i in range(n):
+            heapq.heappush(heap, _Chunk(prio, i, torch.zeros(1), None))
+    order = [(c.prio, c.idx) for c in (heapq.heappop(heap) for _ in range(len(heap)))]
+    assert order == [(0, 0), (0, 1), (2, 0), (2, 1), (5, 0), (5, 1), (5, 2), (7, 0)]
+
+
+@pytest.mark.parametrize("compressor,mc", [("gtopk", False), ("gtopkef", False), ("topk", True), ("gaussian", False)])
+def test_sparse_paths_stay_rank_consistent(compressor, mc):
+    def sparse_worker(rank, world, compressor, mc):
+        import dear_pytorch_b200 as dear
+        from dear_pytorch_b200.parallel.baselines import WFBPDistributedOptimizer
+        model = make_model()
+        opt = torch.optim.SGD(model.parameters(), lr=0.05, momentum=0.9 if mc else 0.0)
+        opt = WFBPDistributedOptimizer(opt, model=model, compression=compressor, is_sparse=True, density=0.25,
+                                       threshold=10 ** 9, momentum_correction=mc, verbose=False)
+        dear.broadcast_parameters(model.state_dict(), 0)
+        losses = []
+        for t in range(8):
+            x, y = data(0, 8)
+            opt.zero_grad()
+            loss = nn.functional.cross_entropy(model(x[rank * 4:(rank + 1) * 4]), y[rank * 4:(rank + 1) * 4])
+            loss.backward()
+            opt.step()
+            losses.append(float(loss))
+        return losses, [p.detach().clone() for p in model.parameters()]
+    outs = run_ranks(sparse_worker, world=2, backend="gloo", args=(compressor, mc))
+    assert all(torch.equal(a, b) for a, b in zip(outs[0][1], outs[1][1]))
+    assert outs[0][0][-1] < outs[0][0][0]            # the sparsified run still trains
 
 
 def test_sparse_topk_allgather_path_runs():

@@ -86,7 +86,7 @@ def main():
         t_rs = timed(lambda: bs.reduce_scatter(g, True), args.iters)
         t_rs_nopack = timed(lambda: bs.reduce_scatter(g, False), args.iters)
         t_ag = timed(lambda: bs.allgather_update(g, True, False, True, False), args.iters)
-        row = {"bucket_mb": round(nbytes / 2 ** 20, 2), "dtype": args.dtype, "world": world,
+        row = {"bucket_mb": round(nbytes / 2 ** 20, 2), "dtype": args.dtype, "world": world, "rs_plan": bs.rs_plan(g),
                "rs_us": round(t_rs, 2), "rs_nopack_us": round(t_rs_nopack, 2), "ag_sgd_us": round(t_ag, 2)}
         rr = perf_model.rs_roofline_us(nbytes, world, es, peaks)
         ar = perf_model.ag_roofline_us(nbytes, world, es, True, peaks)
@@ -114,6 +114,19 @@ def main():
                 return maxr(e0.elapsed_time(e1) / args.iters * 1e3)
             row["nccl_rs_us"] = round(nccl_timed(lambda: dist.reduce_scatter_tensor(out, full)), 2)
             row["nccl_ag_us"] = round(nccl_timed(lambda: dist.all_gather_into_tensor(full, out)), 2)
+            # the work Kernel A actually replaces (dear/dear_dopt.py:265 + communicator.cpp:157-169 + :306): copy the
+            # gradients into the flat buffer (ONE copy kernel here; the reference launches one per parameter), the
+            # NCCL reduce-scatter, and the division by the world size
+            src = torch.randn(n, device=dev).to(tdt)
+
+            def ref_path():
+                full.copy_(src)
+                dist.reduce_scatter_tensor(out, full)
+                out.div_(world)
+            row["nccl_copy_rs_div_us"] = round(nccl_timed(ref_path), 2)
+            row["rs_vs_nccl"] = round(t_rs / row["nccl_rs_us"], 3)
+            row["rs_vs_nccl_copy_rs_div"] = round(t_rs / row["nccl_copy_rs_div_us"], 3)
+            del src
         results.append(row)
         if rank == 0:
             print(json.dumps(row), flush=True)
