@@ -30,7 +30,7 @@ BERT_MODELS = ("bert", "bert_large", "bert_base")
 def parse_args(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", choices=["dear", "reference"], default="dear")
     ap.add_argument("--model", default="resnet50")
@@ -42,8 +42,8 @@ def parse_args(argv=None):
                     help="replay the whole iteration as one CUDA graph (GPU only; validated at 1/2/8 GPUs)")
     ap.add_argument("--overlap-update", type=int, default=(int(os.environ["DEAR_BENCH_OVERLAP"]) if "DEAR_BENCH_OVERLAP" in os.environ else None),
                     help="graph mode: capture step(previous gradients) -> forward -> backward so the update + all-gather "
-                         "kernels overlap the forward inside the graph (utils/train.py); default: on for BERT (73 buckets, "
-                         "+3.5 %% measured on one B200), off for the conv nets (5 buckets: neutral)")
+                         "kernels overlap the forward inside the graph (utils/train.py) -- DeAR's defining overlap; default on "
+                         "(BERT +3.5 %% on one B200; with peers it hides the all-gather tail of every model)")
     ap.add_argument("--fused-bn", type=int, default=int(os.environ.get("DEAR_BENCH_FUSED_BN", "1")),
                     help="ResNets: fused channels-last BatchNorm(+add)+ReLU kernels (csrc/bn_act.cu)")
     ap.add_argument("--fused-ln", type=int, default=int(os.environ.get("DEAR_BENCH_FUSED_LN", "1")),
@@ -64,7 +64,7 @@ def parse_args(argv=None):
         # BERT-large is specified in bf16 (BASELINE.json); ResNet-50 runs at the reference's precision
         args.dtype = "bf16" if is_bert else "fp32"
     if args.overlap_update is None:
-        args.overlap_update = 1 if is_bert else 0
+        args.overlap_update = 1
     return args
 
 
@@ -271,7 +271,7 @@ def run_dear(args):
     clocks = None
     if sampler is not None:
         sampler.stop()
-        clocks = sampler.summary(wall0, wall1)
+        clocks = sampler.summary(wall0, time.time())      # both timed regions (device-resident and end-to-end) are load
 
     ms = _max_over_ranks(ms, world)
     value = B * world * args.steps / (ms / 1e3)

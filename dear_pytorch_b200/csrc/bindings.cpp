@@ -84,6 +84,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def("allReduceRB", &Communicator::allreduce_rb_, py::arg("tensor"), py::arg("scale") = 1.0)
       .def("bcast", &Communicator::bcast_, py::arg("tensor"), py::arg("root"))
       .def("reduce", &Communicator::reduce_, py::arg("tensor"), py::arg("root"), py::arg("scale") = 1.0)
+      .def("extendStreams", &Communicator::extend_streams, py::arg("nstreams"))
+      .def("numStreams", &Communicator::num_streams)
       .def("reduceScatter", &Communicator::reduce_scatter, py::arg("send"), py::arg("recv"), py::arg("scale") = 1.0)
       .def("allGather", &Communicator::allgather, py::arg("send"), py::arg("recv"))
       .def("sendrecv", &Communicator::sendrecv, py::arg("send"), py::arg("recv"), py::arg("peer"))
@@ -112,6 +114,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
            py::arg("beta2") = std::vector<double>{}, py::arg("eps") = std::vector<double>{})
       .def("reduce_scatter", &BucketSet::reduce_scatter, py::arg("bucket"), py::arg("pack") = true)
       .def("rs_plan", &BucketSet::rs_plan, py::arg("bucket"))
+      .def("set_grad_scale", &BucketSet::set_grad_scale, py::arg("scale"))
       .def("allgather_update", &BucketSet::allgather_update, py::arg("bucket"), py::arg("do_update") = true,
            py::arg("first_step") = false, py::arg("entry_barrier") = true, py::arg("zero_grad") = false)
       .def("fence_current_to_comm", &BucketSet::fence_current_to_comm)

@@ -103,17 +103,25 @@ Communicator::Communicator(int rank, int world, c10::intrusive_ptr<c10d::Store> 
     DEAR_CHECK(cuda_runtime_usable(), "CUDA device requested but no CUDA runtime/driver is usable");
     DEAR_CUDA(cudaSetDevice(opt_.device));
   }
-  general_ = SymmArena::create(static_cast<size_t>(opt_.staging_bytes) * opt_.nstreams, rank_, world_, store_,
-                               unique_key("general"), arena_options());
-  slots_.resize(opt_.nstreams);
-  if (is_cuda()) {
-    for (auto& s : slots_) {
-      s.stream = make_priority_stream();
-      s.ev_in = make_event();
-      s.ev_out = make_event();
-    }
-  }
+  for (int i = 0; i < opt_.nstreams; ++i) add_slot();
   (void)status_word_host();
+}
+
+void Communicator::add_slot() {
+  arenas_.push_back(SymmArena::create(static_cast<size_t>(opt_.staging_bytes), rank_, world_, store_, unique_key("general"),
+                                      arena_options()));
+  Slot s;
+  if (is_cuda()) {
+    s.stream = make_priority_stream();
+    s.ev_in = make_event();
+    s.ev_out = make_event();
+  }
+  slots_.push_back(s);
+}
+
+void Communicator::extend_streams(int n) {
+  DEAR_CHECK(n >= 1 && n <= 16, "nstreams must be in [1,16]");
+  while (static_cast<int>(slots_.size()) < n) add_slot();
 }
 
 Communicator::~Communicator() {
@@ -153,18 +161,18 @@ void Communicator::check_status() {
 
 void Communicator::gen_chunked(int slot, int op, const char* src, char* dst, uint64_t nelems, int dtype,
                                uint32_t elem_bytes, int root_or_peer, float scale, uint64_t dst_stride_elems) {
-  const size_t stage_off = static_cast<size_t>(slot) * opt_.staging_bytes;
+  SymmArena& arena = *arenas_.at(slot);
   GenParams p;
   std::memset(&p, 0, sizeof(p));
-  p.stage = general_->data_table(stage_off);
+  p.stage = arena.data_table(0);
   p.mc_stage = nullptr;
   p.op = op;
   p.root_or_peer = root_or_peer;
   p.scale = scale;
-  p.ready_chan = 1 + 2 * slot;
-  p.done_chan = 2 + 2 * slot;
-  p.sig = general_->sig_table();
-  p.ctrl = general_->ctrl();
+  p.ready_chan = 1;
+  p.done_chan = 2;
+  p.sig = arena.sig_table();
+  p.ctrl = arena.ctrl();
   p.rank = rank_;
   p.world = world_;
   p.dtype = dtype < 0 ? DT_F32 : dtype;
@@ -274,7 +282,7 @@ int Communicator::reduce_scatter(torch::Tensor send, torch::Tensor recv, double 
   const uint32_t eb = send.element_size();
   const char* sp = reinterpret_cast<const char*>(send.data_ptr());
   char* rp = reinterpret_cast<char*>(recv.data_ptr());
-  char* stage = general_->local_data() + static_cast<size_t>(slot) * opt_.staging_bytes;
+  char* stage = arenas_.at(slot)->local_data();
   cudaStream_t st = is_cuda() ? S(slots_[slot].stream) : nullptr;
   if (is_cuda()) {
     DEAR_CUDA(cudaEventRecord(E(slots_[slot].ev_in), current_stream(opt_.device)));
@@ -605,6 +613,38 @@ bool BucketSet::set_pack(int g, const std::vector<int64_t>& src_ptrs, const std:
   if (same && !b.pack_captured) return false;
   b.pack_host = std::move(segs);
   b.ntiles = tiles;
+  if (b.rs_algo == RS_ALGO_PIPE) {
+    // work list of the pipelined kernel: every segment cut at shard and stripe boundaries and into pieces of at
+    // most kPipePackPiece bytes, ordered stripe-major (stripe k of EVERY shard before stripe k+1)
+    const uint64_t SB = static_cast<uint64_t>(b.shard) * es, cs = b.stripe_bytes;
+    std::vector<std::vector<PackSeg>> per_stripe(b.nstripes);
+    for (const PackSeg& sg : b.pack_host) {
+      uint64_t o = sg.dst_off;
+      const uint64_t end = sg.dst_off + sg.nbytes;
+      while (o < end) {
+        const uint64_t in_shard = o % SB;
+        const uint64_t k = in_shard / cs;
+        const uint64_t stripe_end = o - in_shard + std::min<uint64_t>(SB, (k + 1) * cs);
+        const uint64_t n = std::min<uint64_t>({end - o, stripe_end - o, static_cast<uint64_t>(kPipePackPiece)});
+        PackSeg pc = sg;
+        pc.src = sg.src ? reinterpret_cast<const char*>(sg.src) + (o - sg.dst_off) : nullptr;
+        pc.dst_off = o;
+        pc.nbytes = n;
+        pc.tile_begin = static_cast<uint32_t>(k);
+        per_stripe.at(k).push_back(pc);
+        o += n;
+      }
+    }
+    b.pieces_host.clear();
+    for (uint32_t k = 0; k < b.nstripes; ++k) {
+      b.piece_first[k] = static_cast<uint32_t>(b.pieces_host.size());
+      b.pieces_host.insert(b.pieces_host.end(), per_stripe[k].begin(), per_stripe[k].end());
+    }
+    for (uint32_t k = b.nstripes; k < 17; ++k) b.piece_first[k] = static_cast<uint32_t>(b.pieces_host.size());
+    if (comm_->is_cuda())
+      upload(b, true, b.pieces_host.data(), b.pieces_host.size() * sizeof(PackSeg), reinterpret_cast<void**>(&b.pack_dev), &b.pack_cap);
+    return true;
+  }
   if (comm_->is_cuda())
     upload(b, true, b.pack_host.data(), b.pack_host.size() * sizeof(PackSeg), reinterpret_cast<void**>(&b.pack_dev), &b.pack_cap);
   return true;
@@ -669,13 +709,14 @@ void BucketSet::reduce_scatter(int g, bool pack) {
   p.mc_grad = arena_->has_multicast() ? arena_->mc_data() + b.grad_off : nullptr;
   p.out = b.grad_shard.data_ptr<float>();
   p.shard_elems = static_cast<uint64_t>(b.shard);
-  p.scale = 1.0f / static_cast<float>(comm_->size());
+  p.scale = grad_scale_ / static_cast<float>(comm_->size());
   const bool cuda = comm_->is_cuda();
   if (pack && !b.pack_host.empty()) {
     p.segs = cuda ? b.pack_dev : b.pack_host.data();
     p.nseg = static_cast<uint32_t>(b.pack_host.size());
     p.ntiles = b.ntiles;
-    p.direct_out = (comm_->size() == 1 && dtype_ == DT_F32 && !b.pack_inplace) ? 1u : 0u;
+    // one GPU: the pack writes the fp32 shard directly (fp32: copy; bf16 / fp16: widening, CUDA kernel only)
+    p.direct_out = (comm_->size() == 1 && (dtype_ == DT_F32 || cuda) && !b.pack_inplace) ? 1u : 0u;
   }
   p.sig = arena_->sig_table();
   p.ctrl = arena_->ctrl();
@@ -689,11 +730,17 @@ void BucketSet::reduce_scatter(int g, bool pack) {
     DEAR_CUDA(cudaEventRecord(E(b.ev_in), current_stream(comm_->options().device)));
     DEAR_CUDA(cudaStreamWaitEvent(S(stream_), E(b.ev_in), 0));
     // the previous update kernel of this bucket (other stream) must have consumed the reduced shard it overwrites
-    if (ag_stream_ != stream_ && b.ag_pending) DEAR_CUDA(cudaStreamWaitEvent(S(stream_), E(b.ag_done), 0));
+    // (a capturing stream may only wait on events of its own capture, and vice versa; across that boundary the
+    // capture / replay is ordered after the eager work by the stream it is launched on)
+    if (ag_stream_ != stream_ && b.ag_pending && b.ag_done_captured == is_capturing(S(stream_)))
+      DEAR_CUDA(cudaStreamWaitEvent(S(stream_), E(b.ag_done), 0));
     if (b.rs_algo == RS_ALGO_PIPE) {
       p.nstripes = b.nstripes;
       p.stripe_bytes = b.stripe_bytes;
       p.mc_grad = nullptr;
+      p.pieces = (pack && !b.pieces_host.empty()) ? b.pack_dev : nullptr;
+      std::memcpy(p.piece_first, b.piece_first, sizeof(p.piece_first));
+      p.segs = nullptr;
       launch_rs_pipe(p, b.rs_grid, S(stream_));
     } else {
       if (b.rs_algo != RS_ALGO_NVLS) p.mc_grad = nullptr;
@@ -754,6 +801,7 @@ void BucketSet::allgather_update(int g, bool do_update, bool first_step, bool en
     }
     launch_ag(p, grid_for(b.shard * 16, comm_->options().ag_grid), S(ag_stream_));
     DEAR_CUDA(cudaEventRecord(E(b.ag_done), S(ag_stream_)));
+    b.ag_done_captured = is_capturing(S(ag_stream_));
   } else {
     emu_ag(p);
   }

@@ -40,7 +40,7 @@ struct CommOptions {
   // Kernel A variant per bucket: -1 = pick by bucket size (one-shot below `pipe_min_bytes`, stripe-pipelined TMA
   // pull above, NVLS ld_reduce only on request); 0 / 1 / 2 force RS_ALGO_ONESHOT / _PIPE / _NVLS for every bucket.
   int rs_algo = -1;
-  int64_t pipe_min_bytes = 2ll << 20;
+  int64_t pipe_min_bytes = 128ll << 20;
   int64_t stripe_target_bytes = 8ll << 20;   // bucket bytes per stripe the pipelined kernel aims for
   bool separate_ag_stream = true;            // all-gathers on their own stream (reference: three communicators)
 };
@@ -54,7 +54,12 @@ class Communicator : public std::enable_shared_from_this<Communicator> {
   int rank() const { return rank_; }
   int size() const { return world_; }
   bool is_cuda() const { return opt_.device >= 0; }
-  bool has_multicast() const { return general_ && general_->has_multicast(); }
+  bool has_multicast() const { return !arenas_.empty() && arenas_[0]->has_multicast(); }
+  // Grow to at least `n` stream slots (collective: every rank calls it with the same n).  Each slot owns a stream,
+  // two events and its own symmetric staging arena, so operations on different slots never serialise — the
+  // reference's _extendComms (common/comm_core/src/communicator.cpp:85-95) creates one NCCL communicator per slot.
+  void extend_streams(int n);
+  int num_streams() const { return static_cast<int>(slots_.size()); }
   const CommOptions& options() const { return opt_; }
   const c10::intrusive_ptr<c10d::Store>& store() const { return store_; }
   const std::string& name() const { return name_; }
@@ -92,6 +97,7 @@ class Communicator : public std::enable_shared_from_this<Communicator> {
     void* ev_in = nullptr;    // cudaEvent_t
     void* ev_out = nullptr;
   };
+  void add_slot();
   int run_gen(int op, const void* src, void* dst, uint64_t nelems, int dtype, uint32_t elem_bytes,
               int root_or_peer, float scale);
   int next_slot();
@@ -102,7 +108,7 @@ class Communicator : public std::enable_shared_from_this<Communicator> {
   c10::intrusive_ptr<c10d::Store> store_;
   std::string name_;
   CommOptions opt_;
-  std::shared_ptr<SymmArena> general_;   // staging for the general ops
+  std::vector<std::shared_ptr<SymmArena>> arenas_;   // per-slot staging for the general ops
   std::vector<Slot> slots_;
   int cur_slot_ = 0;
   int key_seq_ = 0;
@@ -134,6 +140,8 @@ class BucketSet {
                  const std::vector<int64_t>& opt, const std::vector<double>& beta2, const std::vector<double>& eps);
 
   void reduce_scatter(int g, bool pack);
+  // extra factor folded into the 1/P of Kernel A's epilogue (static loss scaling: 1/S un-scales the gradients)
+  void set_grad_scale(double s) { grad_scale_ = static_cast<float>(s); }
   // (algorithm, stripes, grid) chosen for bucket g at construction time: {"algo": "oneshot|pipe|nvls", ...}
   std::string rs_plan(int g) const;
   void allgather_update(int g, bool do_update, bool first_step, bool entry_barrier, bool zero_grad);
@@ -157,6 +165,9 @@ class BucketSet {
     bool pack_inplace = false;
     PackSeg* pack_dev = nullptr;
     size_t pack_cap = 0;
+    // stripe-pipelined Kernel A: stripe-major list of <= 32 KB copies derived from pack_host (set_pack)
+    std::vector<PackSeg> pieces_host;
+    uint32_t piece_first[17] = {0};
     HyperSeg* hyper_dev = nullptr;
     size_t hyper_cap = 0;
     // Host staging of the two device tables.  Each table kind has its OWN double-buffered pinned area, and an
@@ -179,6 +190,7 @@ class BucketSet {
     void* rs_done = nullptr;
     void* ag_done = nullptr;
     bool ag_pending = false, rs_pending = false;
+    bool ag_done_captured = false;   // ag_done was last recorded inside a CUDA-graph capture
   };
   void upload(Bucket& b, bool is_pack, const void* host, size_t bytes, void** dev, size_t* cap);
   int grid_for(int64_t shard_elems, int max_grid) const;
@@ -192,6 +204,7 @@ class BucketSet {
   void* ag_stream_ = nullptr;   // cudaStream_t: update + all-gather kernels (== stream_ unless separate_ag_stream)
   void* ev_fence_ = nullptr;
   void* ev_fence_ag_ = nullptr;
+  float grad_scale_ = 1.0f;
 };
 
 // device launchers (kernels.cu) and host emulation (emu.cpp)

@@ -183,12 +183,16 @@ struct RSParams {
   uint32_t nstripes;
   uint32_t reserved;
   uint64_t stripe_bytes;
+  // pack work list of the pipelined variant: `pieces` (device) holds <= kPipePackPiece-byte copies in stripe-major
+  // order, stripe k owning entries [piece_first[k], piece_first[k+1])
+  const PackSeg* pieces;
+  uint32_t piece_first[17];
 };
 
 // RS_READY flag encoding shared by both reduce-scatter kernels: (epoch << 8) | stripes_published; the one-shot
 // kernel publishes kAllStripes.  Monotonic, so the wrap-safe ">=" wait works for either producer.
 constexpr uint32_t kAllStripes = 255u;
-constexpr uint32_t kMaxStripes = 64u;
+constexpr uint32_t kMaxStripes = 16u;
 constexpr uint32_t kPipeChunk = 16384;        // bytes per TMA bulk copy of the pull ring
 constexpr uint32_t kPipePackPiece = 32768;    // bytes per pack work item
 

@@ -162,6 +162,7 @@ template <> struct ElemTraits<float> {
                       __float_as_uint(f[3]));
   }
   __device__ static uint4 mc_reduce(const void* mc) { return multimem_ld_reduce_f32(mc); }
+  __device__ static float from_raw16(uint16_t) { return 0.f; }   // (not a 16-bit type)
 };
 template <> struct ElemTraits<__nv_bfloat16> {
   static constexpr int kPerVec = 8;
@@ -183,6 +184,7 @@ template <> struct ElemTraits<__nv_bfloat16> {
     return make_uint4(w[0], w[1], w[2], w[3]);
   }
   __device__ static uint4 mc_reduce(const void* mc) { return multimem_ld_reduce_bf16(mc); }
+  __device__ static float from_raw16(uint16_t r) { return __uint_as_float(uint32_t(r) << 16); }
 };
 template <> struct ElemTraits<__half> {
   static constexpr int kPerVec = 8;
@@ -205,6 +207,7 @@ template <> struct ElemTraits<__half> {
     return make_uint4(w[0], w[1], w[2], w[3]);
   }
   __device__ static uint4 mc_reduce(const void* mc) { return multimem_ld_reduce_f16(mc); }
+  __device__ static float from_raw16(uint16_t r) { return __half2float(__ushort_as_half(r)); }
 };
 
 }  // namespace dear

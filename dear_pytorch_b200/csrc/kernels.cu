@@ -54,9 +54,10 @@ __global__ void __launch_bounds__(kThreads, 1) rs_kernel(const RSParams p) {
   uint32_t* cnt_pack = p.ctrl + kNumChannels + ch_ready;
   uint32_t* cnt_exit = p.ctrl + kNumChannels + ch_done;
   const uint32_t e = *reinterpret_cast<volatile uint32_t*>(epoch_p) + 1;
-  // single-GPU fp32 fast path: the "reduction" of one rank is a copy, so the pack writes the fp32
-  // shard (== the whole bucket) directly and the pull phase disappears.
-  const bool direct = (W == 1) && (sizeof(T) == 4) && p.direct_out;
+  // single-GPU fast path: the "reduction" of one rank is a copy (fp32) or a widening conversion (bf16 / fp16),
+  // so the pack writes the fp32 shard (== the whole bucket) directly and the pull phase disappears.
+  const bool direct = (W == 1) && p.direct_out;
+  const bool direct16 = direct && sizeof(T) == 2;
 
   // (0) my bucket may still be read by a peer's previous reduce-scatter.
   wait_all_peers(sig_local, ch_done, e - 1, world, p.timeout_ns, p.status, ST_TIMEOUT_RS_DONE);
@@ -79,6 +80,34 @@ __global__ void __launch_bounds__(kThreads, 1) rs_kernel(const RSParams p) {
       const uint32_t nb = left < kPackTileBytes ? uint32_t(left) : kPackTileBytes;
       char* d = bucket + sg.dst_off + off;
       const uint32_t nvec = nb >> 4;
+      if (direct16) {
+        // 16-bit gradients, one GPU: widen straight into the fp32 shard (element e of the bucket = out[e])
+        float* o = p.out + ((sg.dst_off + off) >> 1);
+        const bool zero = (sg.flags & SEG_ZERO_FILL) != 0;
+        if (!zero && sg.src == nullptr) continue;
+        const char* s = reinterpret_cast<const char*>(sg.src) + off;
+        uint4 r[kPackVecPerThread];
+#pragma unroll
+        for (int k = 0; k < kPackVecPerThread; ++k) {
+          const uint32_t v = tid + k * kThreads;
+          r[k] = make_uint4(0, 0, 0, 0);
+          if (v < nvec && !zero) r[k] = ld_stream(s + (size_t(v) << 4));
+        }
+#pragma unroll
+        for (int k = 0; k < kPackVecPerThread; ++k) {
+          const uint32_t v = tid + k * kThreads;
+          if (v < nvec) {
+            float f[8];
+            Tr::unpack(r[k], f);
+            float4* o4 = reinterpret_cast<float4*>(o + size_t(v) * 8);
+            o4[0] = make_float4(f[0] * p.scale, f[1] * p.scale, f[2] * p.scale, f[3] * p.scale);
+            o4[1] = make_float4(f[EV - 4] * p.scale, f[EV - 3] * p.scale, f[EV - 2] * p.scale, f[EV - 1] * p.scale);
+          }
+        }
+        for (uint32_t b = (nvec << 4) + tid * 2; b < nb; b += kThreads * 2)
+          o[b >> 1] = zero ? 0.f : Tr::from_raw16(*reinterpret_cast<const uint16_t*>(s + b)) * p.scale;
+        continue;
+      }
       if (sg.flags & SEG_ZERO_FILL) {
         const uint4 z = make_uint4(0, 0, 0, 0);
 #pragma unroll

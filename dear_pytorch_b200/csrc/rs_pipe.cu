@@ -9,12 +9,13 @@
 // idles while HBM copies and vice versa.  Here the shard is cut into stripes; stripe k of every shard is packed
 // and published while stripe k-1 is being pulled, and the pull itself is moved off the LSU:
 //
-//   warps 9-16  PACK      copy this rank's gradients (pack table) into the symmetric bucket, stripe-major; the
-//                         CTA that completes stripe k grid-wide publishes RS_READY = (epoch<<8 | k+1) to all peers
+//   warps 7-18  PACK      copy this rank's gradients into the symmetric bucket, stripe-major, from a host-built work
+//                         list of <= 32 KB copies (BucketSet::set_pack); the CTA that completes stripe k grid-wide
+//                         publishes RS_READY = (epoch<<8 | k+1) to all peers
 //   warp  0     PRODUCER  one lane: wait for every peer's stripe-k flag, then feed a 12 x 16 KB shared-memory
 //                         ring with cp.async.bulk (UBLKCP) copies straight out of the PEERS' buckets over NVLink;
 //                         one ring slot = one 16 KB chunk of my shard from one peer, mbarrier complete_tx
-//   warps 1-8   REDUCE    accumulate the P slots of a chunk in fp32 registers (fixed peer order => run-to-run
+//   warps 1-6   REDUCE    accumulate the P slots of a chunk in fp32 registers (fixed peer order => run-to-run
 //                         deterministic), scale by 1/P, write the fp32 shard
 //
 // Measured basis (tools/p2p_probe.cu, profiles/r2/p2p_probe_2gpu.log): bulk-copy pulls reach the NVLink
@@ -29,11 +30,11 @@
 namespace dear {
 
 constexpr int kPipeStages = 12;                         // 12 x 16 KB = 192 KB ring per CTA
-constexpr int kReduceThreads = 256;
-constexpr int kPackThreads = 256;
-constexpr int kPipeThreads = 32 + kReduceThreads + kPackThreads;
-constexpr int kPackVecs = kPipePackPiece / 16 / kPackThreads;     // 8 x 128-bit per pack thread per piece
-constexpr int kRedVecs = kPipeChunk / 16 / kReduceThreads;        // 4 x 128-bit per reduce thread per chunk
+constexpr int kReduceThreads = 192;
+constexpr int kPackThreads = 384;
+constexpr int kPipeThreads = 32 + kReduceThreads + kPackThreads;  // 608
+constexpr int kPackVecs = (kPipePackPiece / 16 + kPackThreads - 1) / kPackThreads;     // 6 x 128-bit per pack thread per piece
+constexpr int kRedVecs = (kPipeChunk / 16 + kReduceThreads - 1) / kReduceThreads;      // 6 x 128-bit per reduce thread per chunk
 
 // ---- mbarrier / bulk-copy PTX ----------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -76,57 +77,43 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// Lowest segment index whose end lies beyond byte `o` of the bucket (segments are sorted and disjoint).
-__device__ __forceinline__ uint32_t first_seg_ending_after(const PackSeg* segs, uint32_t n, uint64_t o) {
-  uint32_t lo = 0, hi = n;
-  while (lo < hi) {
-    const uint32_t mid = (lo + hi) >> 1;
-    if (segs[mid].dst_off + segs[mid].nbytes > o) hi = mid; else lo = mid + 1;
+// One entry of the host-built work list: copy (or zero-fill) `nbytes` <= kPipePackPiece bytes into the bucket.
+// All loads first (6 x 128 bit in flight per thread, 384 threads => 36 KB in flight per CTA), then the stores.
+__device__ __forceinline__ void pack_piece(const PackSeg& pc, char* bucket, int ptid) {
+  char* d = bucket + pc.dst_off;
+  const uint32_t nb = uint32_t(pc.nbytes);
+  const uint32_t nvec = nb >> 4;
+  if (pc.flags & SEG_ZERO_FILL) {
+    const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int j = 0; j < kPackVecs; ++j) {
+      const uint32_t v = ptid + j * kPackThreads;
+      if (v < nvec) st_stream(d + (size_t(v) << 4), z);
+    }
+    for (uint32_t b = (nvec << 4) + ptid * 2; b < nb; b += kPackThreads * 2) *reinterpret_cast<uint16_t*>(d + b) = 0;
+    return;
   }
-  return lo;
-}
-
-// Copy the part of the pack table that falls into bucket bytes [lo, hi) — one piece of <= 32 KB, done by the
-// 256 pack threads: all loads first (8 x 128 bit in flight per thread), then the stores.
-__device__ __forceinline__ void pack_piece(const PackSeg* segs, uint32_t nseg, char* bucket, uint64_t lo, uint64_t hi,
-                                           int ptid, int lane) {
-  uint32_t s = 0;
-  if (lane == 0) s = first_seg_ending_after(segs, nseg, lo);
-  s = __shfl_sync(0xffffffffu, s, 0);
-  const char* src[kPackVecs];      // nullptr: nothing to do; 0x1: zero-fill
-  uint32_t nb[kPackVecs];          // valid bytes of the vector (16, or the tail of a segment)
+  const char* s = reinterpret_cast<const char*>(pc.src);
   uint4 r[kPackVecs];
 #pragma unroll
   for (int j = 0; j < kPackVecs; ++j) {
-    const uint64_t o = lo + (uint64_t(ptid + j * kPackThreads) << 4);
-    src[j] = nullptr;
-    nb[j] = 0;
-    if (o < hi) {
-      while (s < nseg && segs[s].dst_off + segs[s].nbytes <= o) ++s;
-      if (s < nseg && segs[s].dst_off <= o) {
-        const PackSeg sg = segs[s];
-        const uint64_t left = sg.dst_off + sg.nbytes - o;
-        nb[j] = left < 16 ? uint32_t(left) : 16u;
-        if (sg.flags & SEG_ZERO_FILL) src[j] = reinterpret_cast<const char*>(uintptr_t(1));
-        else if (sg.src != nullptr) src[j] = reinterpret_cast<const char*>(sg.src) + (o - sg.dst_off);
-      }
-    }
+    const uint32_t v = ptid + j * kPackThreads;
+    if (v < nvec) r[j] = ld_stream(s + (size_t(v) << 4));
   }
-#pragma unroll
-  for (int j = 0; j < kPackVecs; ++j)
-    if (nb[j] == 16 && reinterpret_cast<uintptr_t>(src[j]) > 1) r[j] = ld_stream(src[j]);
 #pragma unroll
   for (int j = 0; j < kPackVecs; ++j) {
-    if (src[j] == nullptr) continue;
-    char* d = bucket + lo + (uint64_t(ptid + j * kPackThreads) << 4);
-    const bool zero = reinterpret_cast<uintptr_t>(src[j]) == 1;
-    if (nb[j] == 16) {
-      st_stream(d, zero ? make_uint4(0, 0, 0, 0) : r[j]);
-    } else {
-      for (uint32_t b = 0; b < nb[j]; b += 2)
-        *reinterpret_cast<uint16_t*>(d + b) = zero ? uint16_t(0) : *reinterpret_cast<const uint16_t*>(src[j] + b);
-    }
+    const uint32_t v = ptid + j * kPackThreads;
+    if (v < nvec) st_stream(d + (size_t(v) << 4), r[j]);
   }
+  for (uint32_t b = (nvec << 4) + ptid * 2; b < nb; b += kPackThreads * 2)
+    *reinterpret_cast<uint16_t*>(d + b) = *reinterpret_cast<const uint16_t*>(s + b);
+}
+
+// The chunks of all stripes form one sequence that is dealt round-robin over the CTAs: the first chunk of stripe k
+// that belongs to this CTA (every stripe but the last holds stripe_bytes / kPipeChunk chunks).
+__device__ __forceinline__ uint32_t first_chunk(uint32_t k, uint64_t stripe_bytes) {
+  const uint32_t before = uint32_t((uint64_t(k) * (stripe_bytes / kPipeChunk)) % gridDim.x);
+  return (blockIdx.x + gridDim.x - before) % gridDim.x;
 }
 
 template <typename T>
@@ -134,7 +121,6 @@ __global__ void __launch_bounds__(kPipeThreads, 1) rs_pipe_kernel(const RSParams
   using Tr = ElemTraits<T>;
   constexpr int EV = Tr::kPerVec;
   extern __shared__ __align__(128) unsigned char ring[];          // kPipeStages x kPipeChunk
-  __shared__ PackSeg s_segs[kMaxSmemSegs];
   __shared__ uint64_t s_full[kPipeStages], s_empty[kPipeStages];
   __shared__ uint32_t s_abort, s_last;
 
@@ -153,10 +139,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) rs_pipe_kernel(const RSParams
   // (0) my bucket may still be read by a peer's previous reduce-scatter.
   wait_all_peers(sig_local, ch_done, e - 1, world, p.timeout_ns, p.status, ST_TIMEOUT_RS_DONE);
 
-  const bool packing = p.segs != nullptr && p.nseg > 0;
-  const bool in_smem = p.nseg <= kMaxSmemSegs;
-  if (packing && in_smem)
-    for (uint32_t i = tid; i < p.nseg; i += kPipeThreads) s_segs[i] = p.segs[i];
+  const bool packing = p.pieces != nullptr;
   if (tid == 0) {
     for (int s = 0; s < kPipeStages; ++s) {
       mbar_init(&s_full[s], 1);
@@ -167,7 +150,6 @@ __global__ void __launch_bounds__(kPipeThreads, 1) rs_pipe_kernel(const RSParams
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  const PackSeg* segs = in_smem ? s_segs : p.segs;
   const volatile uint32_t* abort_word = &s_abort;
 
   const uint64_t SB = p.shard_elems * sizeof(T);         // bytes per shard
@@ -180,16 +162,19 @@ __global__ void __launch_bounds__(kPipeThreads, 1) rs_pipe_kernel(const RSParams
     const int ptid = tid - (32 + kReduceThreads);
     char* bucket = reinterpret_cast<char*>(p.grad.ptr[p.rank]);
     for (uint32_t k = 0; k < K; ++k) {
-      const uint64_t s_lo = uint64_t(k) * cs;
-      if (packing && s_lo < SB) {
-        const uint64_t s_hi = (s_lo + cs < SB) ? s_lo + cs : SB;
-        const uint32_t ppr = uint32_t((s_hi - s_lo + kPipePackPiece - 1) / kPipePackPiece);   // pieces per shard
-        const uint32_t total = ppr * uint32_t(world);
-        for (uint32_t i = blockIdx.x; i < total; i += gridDim.x) {
-          const uint32_t r = i / ppr, pc = i - r * ppr;
-          const uint64_t lo = uint64_t(r) * SB + s_lo + uint64_t(pc) * kPipePackPiece;
-          const uint64_t end = uint64_t(r) * SB + s_hi;
-          pack_piece(segs, p.nseg, bucket, lo, (lo + kPipePackPiece < end) ? lo + kPipePackPiece : end, ptid, lane);
+      if (packing) {
+        // stripe k's work items, dealt round-robin over the CTAs (rotated per stripe so nobody is always first)
+        const uint32_t lo = p.piece_first[k], hi = p.piece_first[k + 1];
+        for (uint32_t i = lo + (blockIdx.x + gridDim.x - (lo % gridDim.x)) % gridDim.x; i < hi; i += gridDim.x) {
+          PackSeg pc;
+          const uint4* raw = reinterpret_cast<const uint4*>(p.pieces + i);
+          const uint4 a = __ldg(raw), b2 = __ldg(raw + 1);
+          pc.src = reinterpret_cast<const void*>(uint64_t(a.x) | (uint64_t(a.y) << 32));
+          pc.dst_off = uint64_t(a.z) | (uint64_t(a.w) << 32);
+          pc.nbytes = uint64_t(b2.x) | (uint64_t(b2.y) << 32);
+          pc.tile_begin = b2.z;
+          pc.flags = b2.w;
+          pack_piece(pc, bucket, ptid);
         }
       }
       // stripe k is packed on this CTA; the CTA that completes it grid-wide publishes it to every peer
@@ -222,7 +207,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) rs_pipe_kernel(const RSParams
         asm volatile("fence.proxy.async;" ::: "memory");
         const uint64_t s_hi = (s_lo + cs < SB) ? s_lo + cs : SB;
         const uint32_t nch = uint32_t((s_hi - s_lo + kPipeChunk - 1) / kPipeChunk);
-        for (uint32_t c = blockIdx.x; c < nch && ok; c += gridDim.x) {
+        for (uint32_t c = first_chunk(k, cs); c < nch && ok; c += gridDim.x) {
           const uint64_t off = s_lo + uint64_t(c) * kPipeChunk;
           const uint32_t bytes = (off + kPipeChunk <= s_hi) ? kPipeChunk : uint32_t(s_hi - off);
           for (int j = 0; j < world; ++j) {
@@ -249,7 +234,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) rs_pipe_kernel(const RSParams
       if (s_lo >= SB) break;
       const uint64_t s_hi = (s_lo + cs < SB) ? s_lo + cs : SB;
       const uint32_t nch = uint32_t((s_hi - s_lo + kPipeChunk - 1) / kPipeChunk);
-      for (uint32_t c = blockIdx.x; c < nch && ok; c += gridDim.x) {
+      for (uint32_t c = first_chunk(k, cs); c < nch && ok; c += gridDim.x) {
         const uint64_t off = s_lo + uint64_t(c) * kPipeChunk;
         const uint32_t bytes = (off + kPipeChunk <= s_hi) ? kPipeChunk : uint32_t(s_hi - off);
         const uint32_t nvec = bytes >> 4;

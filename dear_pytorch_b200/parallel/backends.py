@@ -67,6 +67,7 @@ class _BackendBase:
         self.master_shard: List[Optional[torch.Tensor]] = [None] * nb
         self.var_shard: List[Optional[torch.Tensor]] = [None] * nb       # Adam exp_avg_sq
         self.hyper: List[Optional[HyperSpec]] = [None] * nb
+        self.grad_scale = 1.0
 
     # -- shard state ------------------------------------------------------------------
     def _alloc_shards(self):
@@ -103,6 +104,10 @@ class _BackendBase:
 
     def launches(self) -> int:
         return 0
+
+    def set_grad_scale(self, s: float) -> None:
+        """Extra factor applied to the averaged gradient (1/loss_scale for static loss scaling)."""
+        self.grad_scale = float(s)
 
     def stream_key(self, g: int) -> int:
         """Buckets with the same key share one communication stream (ordering domain)."""
@@ -206,6 +211,11 @@ class NativeBackend(_BackendBase):
     def launches(self):
         return self.comm.launches()
 
+    def set_grad_scale(self, s):
+        self.grad_scale = float(s)
+        for bs in self.sets.values():
+            bs.set_grad_scale(float(s))
+
     def stream_key(self, g):
         return id(self.where[g][0])
 
@@ -264,7 +274,7 @@ class TorchBackend(_BackendBase):
                 dist.reduce_scatter_tensor(self._rs_out[g], self._gbuf[g], op=dist.ReduceOp.SUM, group=self.group)
             else:
                 self._rs_out[g].copy_(self._gbuf[g])
-            torch.mul(self._rs_out[g].float(), 1.0 / self.world, out=self.grad_shard[g])
+            torch.mul(self._rs_out[g].float(), self.grad_scale / self.world, out=self.grad_shard[g])
             self._gbuf[g].zero_()
         self._n_launch += 3
 

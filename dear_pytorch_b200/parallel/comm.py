@@ -28,6 +28,10 @@ class Comm:
         self.native = runtime.communicator()
         self.nstreams = max(1, nstreams)
         self._cuda = self.device.type == "cuda"
+        if self.native is not None:
+            # collective, like the reference's _extendComms (communicator.cpp:85-95): the shared native communicator
+            # grows to the largest nstreams any Comm asked for; handles rotate over all of its slots
+            self.native.extendStreams(self.nstreams)
         if self.native is None:
             self.group = runtime.group()
             self._streams = [torch.cuda.Stream(device=self.device) for _ in range(self.nstreams)] if self._cuda else []

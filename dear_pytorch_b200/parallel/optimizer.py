@@ -155,6 +155,7 @@ class DearEngine:
         plan = self.plan
         self.backend = self._make_backend()
         be = self.backend
+        be.set_grad_scale(1.0 / getattr(self, "loss_scale", 1.0))
         self.steal = be.steal_grads
         self._param_view: Dict[nn.Parameter, torch.Tensor] = {}
         self._grad_view: Dict[nn.Parameter, torch.Tensor] = {}
@@ -354,6 +355,16 @@ class DearEngine:
         re-upload the device hyper-parameter tables and order the replay after the upload."""
         self._refresh_hyper()
         self.backend.wait_all()
+
+    def set_loss_scale(self, scale: float):
+        """Static loss scaling (the reference's ImageNet driver runs apex O2 with ``loss_scale=128.0``,
+        dear/imagenet_benchmark.py:116-117,131): back-propagate ``loss * scale`` and the un-scaling is folded into the
+        1/P of the reduce-scatter epilogue — no extra pass over the gradients.  Call it before ``backward()``."""
+        if scale <= 0:
+            raise ValueError("loss scale must be positive")
+        self.loss_scale = float(scale)
+        if self.backend is not None:
+            self.backend.set_grad_scale(1.0 / self.loss_scale)
 
     def params_changed(self):
         """The parameter VALUES were overwritten from outside (``broadcast_parameters``, ``load_state_dict``,
@@ -570,6 +581,16 @@ class _DistributedOptimizer(torch.optim.Optimizer):
 
     flush = synchronize
 
+    def skip_synchronize(self):
+        """Horovod-style context manager used by mixed-precision loops (examples/mnist/pytorch_mnist.py:80 of the
+        reference: ``optimizer.synchronize(); scaler.unscale_(optimizer); with optimizer.skip_synchronize(): ...``).
+        ``step()`` never blocks here, so there is nothing to skip; kept for source compatibility."""
+        import contextlib
+        return contextlib.nullcontext()
+
+    def set_loss_scale(self, scale: float):
+        self._dear.set_loss_scale(scale)
+
     @property
     def engine(self) -> DearEngine:
         return self._dear
@@ -587,7 +608,7 @@ def DistributedOptimizer(optimizer, model, compression=None, is_sparse=False, de
                          layerwise_times=None, norm_clip=None, threshold=None, writer=None, gradient_path=None,
                          fp16=False, mgwfbp=False, rdma=False, multi_job_scheduling=False, exclude_parts="",
                          num_nearby_layers=None, policy=None, verbose=True, bo_tuning=False, bo_kwargs=None,
-                         backward_passes_per_step=1):
+                         backward_passes_per_step=1, loss_scale=None):
     """Wrap ``optimizer`` (``torch.optim.SGD`` / ``Adam`` / ``AdamW``) for DeAR data-parallel training of ``model``.
 
     Signature-compatible with the reference factory (dear/dear_dopt.py:381-398): the Horovod-era
@@ -608,6 +629,8 @@ def DistributedOptimizer(optimizer, model, compression=None, is_sparse=False, de
               num_nearby_layers=num_nearby_layers if num_nearby_layers is not None else NUM_NEARBY_LAYERS,
               exclude_parts=exclude_parts, policy=policy, verbose=verbose,
               backward_passes_per_step=backward_passes_per_step)
+    if loss_scale is not None:
+        opt.set_loss_scale(loss_scale)
     if bo_tuning:
         # dopt_rsag_bo: Bayesian optimisation of the fusion threshold (dear/dopt_rsag_bo.py:100-101)
         from .tuner import attach_tuner

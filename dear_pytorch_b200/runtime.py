@@ -132,19 +132,20 @@ def init(backend: Optional[str] = None, device: Optional[torch.device] = None, *
         o.multicast = bool(multicast) and prov == "vmm"
         o.spin_timeout_s = float(os.environ.get("DEAR_SPIN_TIMEOUT_S", "60"))
         o.rendezvous_timeout_s = float(timeout_s)
-        # CTAs of the fused kernels.  On one GPU nothing ever spins, so the kernels may take most of the
-        # chip for a few microseconds (HBM-bound).  With peers, CTAs spin on cross-GPU flags while they
-        # wait for the slowest rank: keep the footprint small (32 CTAs saturate NVLink: 770 GB/s x ~2 us
-        # latency = 1.5 MB in flight, each CTA keeps >= 64 KB in flight).
-        o.rs_grid = _env_int("DEAR_RS_GRID", 128 if world == 1 else 32)
-        o.ag_grid = _env_int("DEAR_AG_GRID", 128 if world == 1 else 32)
+        # CTAs of the fused kernels (upper bounds; small buckets get fewer, csrc/communicator.cpp: grid_for).  On one GPU
+        # nothing ever spins, so the kernels may take most of the chip for a few microseconds (HBM-bound).  With peers
+        # the pull is NVLink-bound from ~32 CTAs on, but the PACK phase of Kernel A and the push of Kernel B scale with
+        # the CTA count (2 B200s, 392 MB bucket, profiles/r2/kernelA_oneshot_grid_sweep_p2.log: Kernel A 615 / 525 /
+        # 490 / 460 us and Kernel B 508 / 358 / 386 / 343 us at 32 / 48 / 64 / 96 CTAs; NCCL 500 / 495 us).
+        o.rs_grid = _env_int("DEAR_RS_GRID", 128 if world == 1 else 64)
+        o.ag_grid = _env_int("DEAR_AG_GRID", 128 if world == 1 else 48)
         o.gen_grid = _env_int("DEAR_GEN_GRID", 8)
         # Kernel A variant per bucket: by size unless forced (DEAR_RS_ALGO=oneshot|pipe|nvls); csrc/communicator.h
         algo = os.environ.get("DEAR_RS_ALGO", "auto").lower()
         if algo not in ("auto", "oneshot", "pipe", "nvls"):
             raise ValueError("DEAR_RS_ALGO must be auto, oneshot, pipe or nvls")
         o.rs_algo = {"auto": -1, "oneshot": 0, "pipe": 1, "nvls": 2}[algo]
-        o.pipe_min_bytes = int(float(os.environ.get("DEAR_PIPE_MIN_MB", "2")) * (1 << 20))
+        o.pipe_min_bytes = int(float(os.environ.get("DEAR_PIPE_MIN_MB", "128")) * (1 << 20))
         o.stripe_target_bytes = int(float(os.environ.get("DEAR_STRIPE_MB", "8")) * (1 << 20))
         o.separate_ag_stream = os.environ.get("DEAR_AG_STREAM", "1") not in ("0", "false", "False")
         # rendezvous keys must be unique per init(): a re-initialised process group can land on the SAME TCPStore server

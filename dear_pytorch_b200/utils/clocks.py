@@ -13,7 +13,7 @@ _REASONS = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_pow
 
 
 class ClockSampler:
-    def __init__(self, gpu_index: int = 0, period_ms: int = 200):
+    def __init__(self, gpu_index: int = 0, period_ms: int = 50):
         self.gpu_index = gpu_index
         self.period_ms = period_ms
         self.rows = []

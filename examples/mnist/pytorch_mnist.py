@@ -61,6 +61,9 @@ def main(argv=None):
     ap.add_argument("--train-size", type=int, default=6000)
     ap.add_argument("--test-size", type=int, default=1000)
     ap.add_argument("--threshold", type=float, default=0.05, help="fusion threshold in MB (the net has 0.08 MB)")
+    ap.add_argument("--use-mixed-precision", action="store_true", default=False,
+                    help="autocast forward + scaled loss (reference: train_mixed_precision, pytorch_mnist.py:63-83)")
+    ap.add_argument("--loss-scale", type=float, default=128.0, help="static loss scale of the mixed-precision path")
     args = ap.parse_args(argv)
     cuda = not args.no_cuda and torch.cuda.is_available()
 
@@ -93,6 +96,28 @@ def main(argv=None):
                 print("Train Epoch: {} [{}/{} ({:.0f}%)]\tLoss: {:.6f}".format(
                     epoch, batch_idx * len(data), len(train_sampler), 100.0 * batch_idx / len(train_loader), loss.item()))
 
+    def train_mixed_precision(epoch):
+        """The reference's GradScaler loop (examples/mnist/pytorch_mnist.py:63-83): synchronize -> unscale ->
+        ``with optimizer.skip_synchronize(): step``.  Here the gradients never surface as tensors (Kernel A consumes
+        them during back-propagation), so the un-scaling is a factor of the reduce-scatter epilogue
+        (``set_loss_scale``) instead of a pass over the gradients; the call sequence is kept."""
+        model.train()
+        train_sampler.set_epoch(epoch)
+        optimizer.set_loss_scale(args.loss_scale)
+        amp_dtype = torch.bfloat16 if (device.type == "cpu" or torch.cuda.is_bf16_supported()) else torch.float16
+        for batch_idx, (data, target) in enumerate(train_loader):
+            data, target = data.to(device), target.to(device)
+            optimizer.zero_grad()
+            with torch.autocast(device.type, dtype=amp_dtype):
+                loss = F.nll_loss(model(data).float(), target)
+            (loss * args.loss_scale).backward()
+            with optimizer.skip_synchronize():
+                optimizer.step()
+            if batch_idx % args.log_interval == 0 and hvd.rank() == 0:
+                print("Train Epoch: {} [{}/{} ({:.0f}%)]\tLoss: {:.6f}\tLoss Scale: {}".format(
+                    epoch, batch_idx * len(data), len(train_sampler), 100.0 * batch_idx / len(train_loader), loss.item(),
+                    args.loss_scale))
+
     def test():
         model.eval()
         test_loss, test_acc = 0.0, 0.0
@@ -111,7 +136,7 @@ def main(argv=None):
         return test_loss, test_acc
 
     for epoch in range(1, args.epochs + 1):
-        train(epoch)
+        (train_mixed_precision if args.use_mixed_precision else train)(epoch)
     optimizer.synchronize()
     result = test()
     hvd.shutdown()

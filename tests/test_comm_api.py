@@ -205,3 +205,26 @@ def test_broadcast_optimizer_state_to_a_rank_without_state():
         assert torch.equal(a, b) and a.abs().sum() > 0
     for a, b in zip(outs[0][2], outs[1][2]):
         assert torch.equal(a, b)
+
+
+def streams_worker(rank, world):
+    """Comm(nstreams=k) grows the shared native communicator (reference _extendComms, communicator.cpp:85-95)."""
+    import torch
+    import dear_pytorch_b200 as dear
+    from dear_pytorch_b200.parallel.comm import Comm
+    native = dear.communicator()
+    before = native.numStreams()
+    c = Comm(nstreams=3)
+    assert native.numStreams() == max(before, 3)
+    # three operations in flight on three different slots (each has its own staging arena and flags)
+    ts = [torch.full((1000,), float(rank + 1 + i)) for i in range(3)]
+    hs = [c.allReduce(t, 1.0) for t in ts]
+    assert len(set(hs)) == 3
+    for h in hs:
+        c.syncStream(h)
+    return [float(t[0]) for t in ts]
+
+
+def test_comm_nstreams_grows_the_native_communicator():
+    outs = run_ranks(streams_worker, world=2, backend="emu")
+    assert outs[0] == outs[1] == [3.0, 5.0, 7.0]

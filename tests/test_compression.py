@@ -4,7 +4,9 @@ from dear_pytorch_b200.parallel.compression import compressors, SignCompressor
 
 
 def test_registry_matches_reference():
-    assert set(k for k in compressors if k) == {"none", "topk", "eftopk", "gaussian", "signum", "efsignum"}
+    # the reference's registry (wfbp/compression.py:258-267) plus the gTop-k selectors its optimizer keys on by name
+    # (wfbp/dopt.py:725) but never registers
+    assert set(k for k in compressors if k) == {"none", "topk", "eftopk", "gaussian", "signum", "efsignum", "gtopk", "gtopkef"}
 
 
 def test_topk_residual_bookkeeping():

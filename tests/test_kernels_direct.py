@@ -17,7 +17,7 @@ def reference_update(p, g, buf, first, lr, wd, mom, damp, nest):
     return p - lr * g, buf
 
 
-def kernel_worker(rank, world, use_cuda, dtype_name, seed):
+def kernel_worker(rank, world, use_cuda, dtype_name, seed, grad_tol=None):
     import dear_pytorch_b200 as dear
     from dear_pytorch_b200 import ops
     C = ops.require_native()
@@ -88,13 +88,15 @@ def kernel_worker(rank, world, use_cuda, dtype_name, seed):
             ref_p[sl], ref_buf[sl] = reference_update(ref_p[sl], avg[sl], ref_buf[sl], step == 0, lr, wd, m, damp, bool(nest))
             start = end
         got_shard_grad = gs.cpu()
-        torch.testing.assert_close(got_shard_grad, avg[rank * shard:(rank + 1) * shard], rtol=1e-5, atol=1e-6)
+        gt = grad_tol or dict(rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(got_shard_grad, avg[rank * shard:(rank + 1) * shard], **gt)
         got = pbuf.float().cpu()
         if dtype_name == "fp32":
             torch.testing.assert_close(got, ref_p, rtol=1e-5, atol=1e-6)
         else:
-            torch.testing.assert_close(master.cpu(), ref_p[rank * shard:(rank + 1) * shard], rtol=1e-5, atol=1e-6)
-            torch.testing.assert_close(got, ref_p.to(torch.bfloat16).float(), rtol=8e-3, atol=1e-6)   # <= 1 bf16 ulp
+            torch.testing.assert_close(master.cpu(), ref_p[rank * shard:(rank + 1) * shard], **gt)
+            pt = dict(rtol=8e-3, atol=1e-6) if grad_tol is None else dict(rtol=2e-2, atol=1e-2)
+            torch.testing.assert_close(got, ref_p.to(torch.bfloat16).float(), **pt)   # <= 1 bf16 ulp
         results.append(float(got.abs().sum()))
     return results
 
@@ -136,7 +138,7 @@ def plan_worker(rank, world):
     import dear_pytorch_b200 as dear
     from dear_pytorch_b200 import ops
     C = ops.require_native()
-    bs = C.BucketSet(dear.communicator(), [world * 65536, world * 8 * 1024 * 1024], C.DT_F32, True)
+    bs = C.BucketSet(dear.communicator(), [world * 65536, world * 32 * 1024 * 1024], C.DT_F32, True)
     return [bs.rs_plan(0), bs.rs_plan(1)]
 
 
@@ -144,7 +146,7 @@ def plan_worker(rank, world):
 def test_reduce_scatter_algorithm_is_picked_per_bucket_size():
     small, big = run_ranks(plan_worker, world=2, backend="b200", extra_env={"DEAR_SPIN_TIMEOUT_S": "15"}, timeout=300)[0]
     assert small.startswith("oneshot"), small      # 512 KB: latency-bound, fewest flag rounds
-    assert big.startswith("pipe") and "stripes=8" in big, big      # 64 MB: stripe-pipelined TMA pull
+    assert big.startswith("pipe") and "stripes=16" in big, big     # 256 MB: stripe-pipelined TMA pull
 
 
 def nvls_worker(rank, world, dtype_name):
@@ -155,7 +157,10 @@ def nvls_worker(rank, world, dtype_name):
     if not probe.has_multicast():
         return "no-multicast"
     del probe
-    return kernel_worker(rank, world, True, dtype_name, 5)
+    # multimem.ld_reduce on a 16-bit bucket accumulates in fp32 inside the switch but RETURNS the element type:
+    # the reduced gradient carries one bf16 rounding (2^-8 relative) that the P2P kernels do not have
+    tol = dict(rtol=1e-2, atol=1e-2) if dtype_name == "bf16" else None
+    return kernel_worker(rank, world, True, dtype_name, 5, tol)
 
 
 @pytest.mark.gpu
