@@ -42,6 +42,8 @@ def add_common_args(ap):
     ap.add_argument("--rdma", action="store_true", default=False)
     ap.add_argument("--compressor", type=str, default="none")
     ap.add_argument("--density", type=float, default=1.0)
+    ap.add_argument("--momentum-correction", action="store_true", default=False,
+                    help="sparse WFBP: accumulate the velocity before sparsification (wfbp/dopt.py:906-953)")
     ap.add_argument("--exclude-parts", type=str, default="", help="reducescatter, allgather (time breakdown)")
     ap.add_argument("--momentum", type=float, default=0.0)
     ap.add_argument("--optimizer", choices=["sgd", "adam", "adamw"], default="sgd",

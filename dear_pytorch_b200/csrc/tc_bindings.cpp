@@ -30,6 +30,7 @@ long launches() { return g_launches.load(); }
 
 std::vector<at::Tensor> ffn_up_hw(const at::Tensor& x, const at::Tensor& w, const at::Tensor& bias);   // tc_ffn_hw.cu
 at::Tensor ffn_dgelu_hw(const at::Tensor& dy, const at::Tensor& wt, const at::Tensor& z);
+at::Tensor ffn_dgelu_hw_nt(const at::Tensor& dy, const at::Tensor& w, const at::Tensor& z);
 
 }  // namespace dear_tc
 
@@ -68,8 +69,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         {"ffn_up", configs(k_ffn_up)}, {"linear_bias", configs(k_linear_bias)}, {"ffn_dgelu", configs(k_ffn_dgelu)}}; },
     "kernel configurations compiled for each op (index = `variant`)");
   m.def("ffn_up_hw", &dear_tc::ffn_up_hw, py::arg("x"), py::arg("w"), py::arg("bias"),
-        "EXPERIMENTAL hand-written tcgen05 kernel (two-warpgroup epilogue): H, Z = gelu(X W^T + b), X W^T + b");
+        "hand-written tcgen05 kernel (two-warpgroup epilogue, staged coalesced stores): H, Z = gelu(X W^T + b), X W^T + b");
   m.def("ffn_dgelu_hw", &dear_tc::ffn_dgelu_hw, py::arg("dy"), py::arg("wt"), py::arg("z"),
-        "EXPERIMENTAL hand-written tcgen05 kernel: dZ = (dY Wt^T) * gelu'(Z), Wt = transposed down-projection weight [N, K]");
+        "hand-written tcgen05 kernel: dZ = (dY Wt^T) * gelu'(Z), Wt = transposed down-projection weight [N, K]");
+  m.def("ffn_dgelu_hw_nt", &dear_tc::ffn_dgelu_hw_nt, py::arg("dy"), py::arg("w"), py::arg("z"),
+        "hand-written tcgen05 kernel: dZ = (dY W) * gelu'(Z) with W [K, N] as stored (MN-major B operand, no transpose)");
   m.def("launches", &dear_tc::launches);
 }

@@ -17,13 +17,14 @@
 //   warp 1      MMA issuer: one thread issues tcgen05.mma.cta_group::1.kind::f16 (M128 N256 K16) x4 per stage,
 //               tcgen05.commit -> "stage empty" barrier, and -> "accumulator full" barrier after the last K step
 //   warp 2      allocates / frees the 512 TMEM columns (2 accumulator stages x 256 fp32 columns)
-//   warps 4-11  epilogue: tcgen05.ld 32x32b.x32 -> +bias -> erf-GELU -> two 16-byte-vector global stores (H, Z);
-//               arrive on "accumulator empty" so the MMA warp can start tile i+2 while tile i drains
+//   warps 4-11  epilogue: tcgen05.ld 32x32b (64 columns per step) -> +bias -> erf-GELU -> 128B-swizzled staging tile in
+//               shared memory -> coalesced 128-byte-line global stores (H, Z); arrive on "accumulator empty" so the MMA
+//               warp can start tile i+2 while tile i drains
 //
-// STATUS: compiles for sm_100a (ptxas-checked SASS contains UTCHMMA / UTMALDG / LDTM); NOT yet run on hardware
-// (written after the round's GPU budget was spent).  Exported as `_tc.ffn_up_hw` / `_tc.ffn_dgelu_hw`, exercised only by
-// tests/test_tc_gemm.py::test_handwritten_* when DEAR_TEST_UNVALIDATED=1; nothing calls it by default.
-// Every mbarrier wait is bounded and traps instead of spinning forever.
+// STATUS: validated on B200 (tests/test_tc_gemm.py::test_handwritten_*, fp32 oracle).  First hardware run (round 2,
+// profiles/r2/bert_ops_bench_handwritten_tcgen05.json): up+GELU 27.3 us, dgrad x GELU' 27.9 us against 25.4 / 29.3 us for
+// cuBLAS + elementwise kernels — the per-lane 16-byte global stores of that version were the bottleneck, hence the
+// staged, coalesced epilogue above.  Every mbarrier wait is bounded and traps instead of spinning forever.
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/cuda/CUDAGuard.h>
 #include <cuda.h>
@@ -48,7 +49,9 @@ constexpr int kStageBytes = kABytes + kBBytes;          // 48 KB
 constexpr int kNumThreads = 384;                        // 12 warps
 constexpr int kEpilogueWarp0 = 4, kEpilogueWarps = 8;
 constexpr int kTmemCols = kAccStages * kTileN;          // 512
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /* alignment slack */ + 256 /* barriers */;
+constexpr int kEpiChunk = 64;                           // accumulator columns handled per epilogue step
+constexpr int kStageOutBytes = 32 * kEpiChunk * 2;      // 4 KB per epilogue warp: 32 rows x 64 bf16, 128B-swizzled
+constexpr int kSmemBytes = kStages * kStageBytes + kEpilogueWarps * kStageOutBytes + 1024 /* alignment slack */ + 256 /* barriers */;
 
 // ---------------------------------------------------------------------------------------------- PTX
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -151,10 +154,24 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
+// MN-major operand (the matrix is stored with its M/N index contiguous, e.g. B[n][k] = W[k][n] for a row-major W
+// [K, N]), 128-byte swizzle.  Canonical layout in 16-byte units: ((8,n),(8,k)) : ((1,LBO),(8,SBO)) — an atom is 8
+// k-rows of 128 bytes (64 contiguous n); LBO = distance between 64-wide n blocks, SBO = distance between 8-row k groups.
+// Our stage holds kTileN/64 TMA boxes of {64 n, kTileK k} = 8 KB each, so LBO = 8192 B and SBO = 1024 B.
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((kTileK * 128) >> 4) << 16;     // LBO: next 64-wide n block
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;               // SBO: next group of 8 k rows
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
 // Instruction descriptor (cute::UMMA::InstrDescriptor): [4,6) D format = 1 (f32), [7,10) A format = 1 (bf16),
 // [10,13) B format = 1 (bf16), bit 15 / 16 A / B major = 0 (K-major), [17,23) N >> 3, [24,29) M >> 4
 constexpr uint32_t kInstrDesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(kTileN >> 3) << 17) |
                                 (static_cast<uint32_t>(kTileM >> 4) << 24);
+constexpr uint32_t kInstrDescBMN = kInstrDesc | (1u << 16);            // B operand MN-major
 
 // ------------------------------------------------------------------------------------------ GELU
 // Phi(-|x|) by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7), as in tc_gemm.h: 2 MUFU + ~12 FMA per element
@@ -195,14 +212,17 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 // MODE_DGELU: aux = Z [M,N] (read); out0 = dZ = acc * gelu'(Z),  out1 unused
 enum EpilogueMode { MODE_UP = 0, MODE_DGELU = 1 };
 
-template <int MODE>
+// BMN: the B operand is given as a row-major [K, N] matrix (MN-major) instead of [N, K] (K-major): the dgrad GEMM
+// dH = dY W2 reads the nn.Linear weight W2 [hidden, inter] as it is stored — no transposed copy per step.
+template <int MODE, bool BMN>
 __global__ void __launch_bounds__(kNumThreads, 1)
 ffn_hw_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
               const __nv_bfloat16* __restrict__ aux, __nv_bfloat16* __restrict__ out0, __nv_bfloat16* __restrict__ out1,
               int M, int N, int K) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint8_t* stage_out = smem + kStages * kStageBytes;     // [kEpilogueWarps][kStageOutBytes]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_out + kEpilogueWarps * kStageOutBytes);
   uint64_t* full_bar = bars;                             // [kStages]   TMA -> MMA
   uint64_t* empty_bar = bars + kStages;                  // [kStages]   MMA -> TMA
   uint64_t* acc_full_bar = bars + 2 * kStages;           // [kAccStages] MMA -> epilogue
@@ -240,7 +260,14 @@ ffn_hw_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
           mbar_expect_tx(&full_bar[stage], kStageBytes);               // OOB rows/columns are zero-filled AND counted
           uint8_t* a_dst = smem + stage * kStageBytes;
           tma_load_2d(a_dst, &tmap_a, &full_bar[stage], kb * kTileK, m0);
-          tma_load_2d(a_dst + kABytes, &tmap_b, &full_bar[stage], kb * kTileK, n0);
+          if (BMN) {
+            // kTileN/64 boxes of {64 n (contiguous), kTileK k}: 8 KB each, 128B-swizzled by the k row
+#pragma unroll
+            for (int j = 0; j < kTileN / 64; ++j)
+              tma_load_2d(a_dst + kABytes + j * (kTileK * 128), &tmap_b, &full_bar[stage], n0 + j * 64, kb * kTileK);
+          } else {
+            tma_load_2d(a_dst + kABytes, &tmap_b, &full_bar[stage], kb * kTileK, n0);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -261,8 +288,10 @@ ffn_hw_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
           const uint32_t b_addr = a_addr + kABytes;
 #pragma unroll
           for (int k = 0; k < kTileK / kUmmaK; ++k) {
-            // K advance inside the 128-byte swizzle row: +32 bytes per UMMA_K of bf16
-            umma_f16(tmem_d, make_smem_desc(a_addr + k * kUmmaK * 2), make_smem_desc(b_addr + k * kUmmaK * 2), kInstrDesc,
+            // K advance: K-major operands move +32 bytes inside the 128-byte swizzle row per UMMA_K of bf16; the
+            // MN-major operand moves two 8-row k groups (2 x 1024 bytes)
+            const uint64_t bdesc = BMN ? make_smem_desc_mn(b_addr + k * (kUmmaK / 8) * 1024) : make_smem_desc(b_addr + k * kUmmaK * 2);
+            umma_f16(tmem_d, make_smem_desc(a_addr + k * kUmmaK * 2), bdesc, BMN ? kInstrDescBMN : kInstrDesc,
                      (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);                              // frees the smem slot when these MMAs retire
@@ -276,52 +305,94 @@ ffn_hw_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
     // ================================================================== epilogue (8 warps = 2 warpgroups)
     const int quad = warp & 3;                                         // TMEM lanes 32*quad .. 32*quad+31
     const int half = (warp - kEpilogueWarp0) >> 2;                     // which 128 of the 256 accumulator columns
+    // Staging tile of this warp: 32 rows x 128 bytes, 16-byte chunk c of row r stored at chunk (c ^ (r & 7)).
+    //  * register -> smem: lane = row, one STS.128 per chunk; a quarter-warp hits 8 different chunks => no conflicts
+    //  * smem -> global:   8 lanes cover one 128-byte row, 4 rows per instruction => fully coalesced 128-byte lines
+    // (round 1 stored 16 bytes per lane straight to global: 32 different lines per instruction, and the epilogue,
+    //  not the tensor core, set the kernel's pace: 27.3 us against 25.4 us for cuBLAS + a GELU kernel)
+    uint8_t* my_stage = stage_out + (warp - kEpilogueWarp0) * kStageOutBytes;
+    const int srow = lane >> 3, schunk = lane & 7;                     // coalesced phase: row srow + 4*i, chunk schunk
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile % tiles_m) * kTileM, n0 = (tile / tiles_m) * kTileN;
       mbar_wait(&acc_full_bar[acc], acc_phase);
       tc_fence_after();
-      const int row = m0 + quad * 32 + lane;
-      const size_t row_off = static_cast<size_t>(row) * N;
+      const int row0 = m0 + quad * 32;                                 // first global row of this warp's 32 rows
 #pragma unroll 1
-      for (int c = 0; c < (kTileN / 2) / 32; ++c) {
-        const int col0 = half * (kTileN / 2) + c * 32;
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_base + acc * kTileN + col0 + (static_cast<uint32_t>(quad * 32) << 16), v);
-        tmem_ld_wait();
+      for (int c = 0; c < (kTileN / 2) / kEpiChunk; ++c) {
+        const int col0 = half * (kTileN / 2) + c * kEpiChunk;
         const int gcol = n0 + col0;
+        const bool col_ok = gcol + schunk * 8 < N;                     // my 16-byte chunk of the coalesced phases (N % 8 == 0)
+        if (MODE == MODE_DGELU) {
+          // Z chunk: coalesced global -> staging tile (4 rows x 128 B per instruction)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {                                  // 8 columns = one 16-byte vector of bf16
-          const int cj = gcol + j * 8;
-          if (cj < N) {                                                // N % 8 == 0: a vector is all-in or all-out
-            if (MODE == MODE_UP) {
-              const uint4 bv = __ldg(reinterpret_cast<const uint4*>(aux + cj));
-              const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
-              uint32_t zq[4], hq[4];
+          for (int i = 0; i < 8; ++i) {
+            const int r = srow + 4 * i;
+            uint4 zv = make_uint4(0, 0, 0, 0);
+            if (col_ok && row0 + r < M) zv = __ldg(reinterpret_cast<const uint4*>(aux + static_cast<size_t>(row0 + r) * N + gcol) + schunk);
+            *reinterpret_cast<uint4*>(my_stage + r * 128 + ((schunk ^ (r & 7)) << 4)) = zv;
+          }
+          __syncwarp();
+        }
+        uint32_t v[kEpiChunk];
+        {
+          uint32_t lo[32], hi[32];
+          const uint32_t taddr = tmem_base + acc * kTileN + col0 + (static_cast<uint32_t>(quad * 32) << 16);
+          tmem_ld_32x32b_x32(taddr, lo);
+          tmem_ld_32x32b_x32(taddr + 32, hi);
+          tmem_ld_wait();
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float b0 = __uint_as_float(bw[i] << 16), b1 = __uint_as_float(bw[i] & 0xffff0000u);
-                const float z0 = __uint_as_float(v[j * 8 + 2 * i]) + b0, z1 = __uint_as_float(v[j * 8 + 2 * i + 1]) + b1;
-                zq[i] = pack_bf16(z0, z1);
-                hq[i] = pack_bf16(gelu_fast(z0), gelu_fast(z1));
-              }
-              if (row < M) {
-                *reinterpret_cast<uint4*>(out1 + row_off + cj) = make_uint4(zq[0], zq[1], zq[2], zq[3]);
-                *reinterpret_cast<uint4*>(out0 + row_off + cj) = make_uint4(hq[0], hq[1], hq[2], hq[3]);
-              }
-            } else if (row < M) {                                      // (per-lane predicate: no collective below)
-              const uint4 zv = __ldg(reinterpret_cast<const uint4*>(aux + row_off + cj));
-              const uint32_t zw[4] = {zv.x, zv.y, zv.z, zv.w};
-              uint32_t dq[4];
+          for (int j = 0; j < 32; ++j) { v[j] = lo[j]; v[32 + j] = hi[j]; }
+        }
+        uint32_t q0[kEpiChunk / 2];                                    // packed bf16 pairs of out0 (H or dZ)
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float z0 = __uint_as_float(zw[i] << 16), z1 = __uint_as_float(zw[i] & 0xffff0000u);
-                dq[i] = pack_bf16(__uint_as_float(v[j * 8 + 2 * i]) * dgelu_fast(z0),
-                                  __uint_as_float(v[j * 8 + 2 * i + 1]) * dgelu_fast(z1));
-              }
-              *reinterpret_cast<uint4*>(out0 + row_off + cj) = make_uint4(dq[0], dq[1], dq[2], dq[3]);
+        for (int j = 0; j < 8; ++j) {                                  // 8 columns = one 16-byte chunk
+          if (MODE == MODE_UP) {
+            uint4 bv = make_uint4(0, 0, 0, 0);
+            if (gcol + j * 8 < N) bv = __ldg(reinterpret_cast<const uint4*>(aux + gcol) + j);
+            const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+            uint32_t zq[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float b0 = __uint_as_float(bw[i] << 16), b1 = __uint_as_float(bw[i] & 0xffff0000u);
+              const float z0 = __uint_as_float(v[j * 8 + 2 * i]) + b0, z1 = __uint_as_float(v[j * 8 + 2 * i + 1]) + b1;
+              zq[i] = pack_bf16(z0, z1);
+              q0[j * 4 + i] = pack_bf16(gelu_fast(z0), gelu_fast(z1));
+            }
+            // the pre-activation goes to the staging tile right away (it is stored first, below)
+            *reinterpret_cast<uint4*>(my_stage + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_uint4(zq[0], zq[1], zq[2], zq[3]);
+          } else {
+            const uint4 zv = *reinterpret_cast<const uint4*>(my_stage + lane * 128 + ((j ^ (lane & 7)) << 4));
+            const uint32_t zw[4] = {zv.x, zv.y, zv.z, zv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float z0 = __uint_as_float(zw[i] << 16), z1 = __uint_as_float(zw[i] & 0xffff0000u);
+              q0[j * 4 + i] = pack_bf16(__uint_as_float(v[j * 8 + 2 * i]) * dgelu_fast(z0),
+                                        __uint_as_float(v[j * 8 + 2 * i + 1]) * dgelu_fast(z1));
             }
           }
+        }
+        if (MODE == MODE_DGELU) __syncwarp();                          // everyone has read its Z row: the tile is reused
+#pragma unroll
+        for (int pass = 0; pass < (MODE == MODE_UP ? 2 : 1); ++pass) {
+          // MODE_UP: pass 0 stores Z (already staged), pass 1 stages and stores H;  MODE_DGELU: one pass for dZ
+          const bool from_regs = (MODE != MODE_UP) || pass == 1;
+          __nv_bfloat16* outp = (MODE == MODE_UP && pass == 0) ? out1 : out0;
+          if (from_regs) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<uint4*>(my_stage + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                  make_uint4(q0[j * 4], q0[j * 4 + 1], q0[j * 4 + 2], q0[j * 4 + 3]);
+          }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = srow + 4 * i;
+            const uint4 o = *reinterpret_cast<const uint4*>(my_stage + r * 128 + ((schunk ^ (r & 7)) << 4));
+            if (col_ok && row0 + r < M)
+              *(reinterpret_cast<uint4*>(outp + static_cast<size_t>(row0 + r) * N + gcol) + schunk) = o;
+          }
+          __syncwarp();
         }
       }
       tc_fence_before();
@@ -370,6 +441,20 @@ static CUtensorMap make_tmap(const void* base, int64_t rows, int64_t cols, int b
   return m;
 }
 
+// Row-major bf16 matrix [rows = K, cols = N] read as an MN-major operand: box = 64 columns (128 bytes) x kTileK rows
+static CUtensorMap make_tmap_mn(const void* base, int64_t rows, int64_t cols) {
+  CUtensorMap m;
+  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(cols) * 2};
+  const cuuint32_t box[2] = {64u, static_cast<cuuint32_t>(kTileK)};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode_tiled()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TORCH_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (MN-major) failed with code ", static_cast<int>(r));
+  return m;
+}
+
 }  // namespace hw
 
 static void check_bf16(const at::Tensor& t, const char* what) {
@@ -377,20 +462,20 @@ static void check_bf16(const at::Tensor& t, const char* what) {
               reinterpret_cast<uintptr_t>(t.data_ptr()) % 16 == 0, what, ": contiguous 16-byte aligned CUDA bf16 tensor expected");
 }
 
-template <int MODE>
+template <int MODE, bool BMN = false>
 static void launch_hw(const at::Tensor& a, const at::Tensor& b, const __nv_bfloat16* aux, at::Tensor& out0, at::Tensor* out1,
                       int M, int N, int K) {
   const CUtensorMap ta = hw::make_tmap(a.data_ptr(), M, K, hw::kTileM);
-  const CUtensorMap tb = hw::make_tmap(b.data_ptr(), N, K, hw::kTileN);
+  const CUtensorMap tb = BMN ? hw::make_tmap_mn(b.data_ptr(), K, N) : hw::make_tmap(b.data_ptr(), N, K, hw::kTileN);
   static std::once_flag attr_once;
   std::call_once(attr_once, [] {
-    C10_CUDA_CHECK(cudaFuncSetAttribute(hw::ffn_hw_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, hw::kSmemBytes));
+    C10_CUDA_CHECK(cudaFuncSetAttribute(hw::ffn_hw_kernel<MODE, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, hw::kSmemBytes));
   });
   const int tiles = ((M + hw::kTileM - 1) / hw::kTileM) * ((N + hw::kTileN - 1) / hw::kTileN);
   const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
   const int grid = std::min(tiles, sms);
   auto stream = at::cuda::getCurrentCUDAStream().stream();
-  hw::ffn_hw_kernel<MODE><<<grid, hw::kNumThreads, hw::kSmemBytes, stream>>>(
+  hw::ffn_hw_kernel<MODE, BMN><<<grid, hw::kNumThreads, hw::kSmemBytes, stream>>>(
       ta, tb, aux, reinterpret_cast<__nv_bfloat16*>(out0.data_ptr()),
       out1 != nullptr ? reinterpret_cast<__nv_bfloat16*>(out1->data_ptr()) : nullptr, M, N, K);
   C10_CUDA_KERNEL_LAUNCH_CHECK();
@@ -423,6 +508,21 @@ at::Tensor ffn_dgelu_hw(const at::Tensor& dy, const at::Tensor& wt, const at::Te
   auto dz = at::empty({M, N}, dy.options());
   if (M == 0) return dz;
   launch_hw<hw::MODE_DGELU>(dy, wt, reinterpret_cast<const __nv_bfloat16*>(z.data_ptr()), dz, nullptr, M, N, K);
+  return dz;
+}
+
+// dZ = (dY W) * gelu'(Z)   with the nn.Linear weight W [K, N] = [hidden, inter] exactly as it is stored (MN-major B
+// operand): the dgrad of the down projection fused with the GELU backward, no transposed copy of W.
+at::Tensor ffn_dgelu_hw_nt(const at::Tensor& dy, const at::Tensor& w, const at::Tensor& z) {
+  check_bf16(dy, "ffn_dgelu_hw_nt dy"); check_bf16(w, "ffn_dgelu_hw_nt w"); check_bf16(z, "ffn_dgelu_hw_nt z");
+  TORCH_CHECK(dy.dim() == 2 && w.dim() == 2 && z.dim() == 2 && dy.size(1) == w.size(0) && z.size(0) == dy.size(0) &&
+              z.size(1) == w.size(1), "ffn_dgelu_hw_nt: shape mismatch (dy [M,K], w [K,N], z [M,N])");
+  const int M = dy.size(0), K = dy.size(1), N = w.size(1);
+  TORCH_CHECK(K % 8 == 0 && N % 8 == 0, "ffn_dgelu_hw_nt: K and N must be multiples of 8");
+  c10::cuda::CUDAGuard guard(dy.device());
+  auto dz = at::empty({M, N}, dy.options());
+  if (M == 0) return dz;
+  launch_hw<hw::MODE_DGELU, true>(dy, w, reinterpret_cast<const __nv_bfloat16*>(z.data_ptr()), dz, nullptr, M, N, K);
   return dz;
 }
 

@@ -86,8 +86,8 @@ class _FusedFFN(torch.autograd.Function):
         dy2 = dy.reshape(-1, dy.shape[-1])
         if not dy2.is_contiguous():
             dy2 = dy2.contiguous()
-        if HANDWRITTEN:     # K-major operands only: one 8 MB transpose of W2 per layer and step (~3 us)
-            dz = tc.ffn_dgelu_hw(dy2, w2.t().contiguous(), z)
+        if HANDWRITTEN:     # W2 [hidden, inter] is read as it is stored (MN-major B operand): no transposed copy
+            dz = tc.ffn_dgelu_hw_nt(dy2, w2, z)
         else:
             dz = tc.ffn_dgelu(dy2, w2, z, VARIANT["ffn_dgelu"])              # (dy W2) * gelu'(z), one kernel
         dw2 = dy2.t().mm(h) if ctx.needs_input_grad[3] else None

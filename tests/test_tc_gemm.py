@@ -97,6 +97,22 @@ def test_handwritten_ffn_dgelu(M, K, N):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("M,K,N", [(128, 64, 256), (2048, 1024, 4096), (300, 72, 264), (5, 8, 16)])
+def test_handwritten_ffn_dgelu_mn_major_weight(M, K, N):
+    """Same op with the weight [K, N] as nn.Linear stores it: the B operand is MN-major (TMA boxes of 64 contiguous n,
+    UMMA descriptor with LBO/SBO of the MN-major canonical layout) — no transposed copy."""
+    tc = require_tc()
+    dev = torch.device("cuda:0")
+    torch.manual_seed(2)
+    dy, w, z = _rand((M, K), dev), _rand((K, N), dev, K ** -0.5), _rand((M, N), dev)
+    dz = tc.ffn_dgelu_hw_nt(dy, w, z)
+    torch.cuda.synchronize()
+    z32 = z.float().requires_grad_(True)
+    F.gelu(z32).backward(dy.float() @ w.float())
+    torch.testing.assert_close(dz.float(), z32.grad, rtol=1.5e-2, atol=1.5e-2)
+
+
+@pytest.mark.gpu
 def test_fused_ffn_autograd_matches_eager_bf16():
     dev = torch.device("cuda:0")
     torch.manual_seed(3)

@@ -63,7 +63,7 @@ def _gemm_section(r, tc, x, w1, b1, w2, b2, h, z, dy):
     for v, cfg in enumerate(tc.variants()["ffn_up"]):
         r["up_gelu_tcgen05_v%d" % v] = graph_time(lambda: tc.ffn_up(x, w1, b1, v))
     r["up_gelu_tcgen05"] = min(r["up_gelu_tcgen05_v%d" % v] for v in range(len(tc.variants()["ffn_up"])))
-    if os.environ.get("DEAR_TC_EXPERIMENTAL"):     # hand-written kernel with the two-warpgroup epilogue (csrc/tc_ffn_hw.cu)
+    if hasattr(tc, "ffn_up_hw"):     # hand-written kernel with the two-warpgroup epilogue (csrc/tc_ffn_hw.cu)
         r["up_gelu_tcgen05_handwritten"] = graph_time(lambda: tc.ffn_up_hw(x, w1, b1))
     for v, cfg in enumerate(tc.variants()["linear_bias"]):
         r["up_bias_only_tcgen05_v%d" % v] = graph_time(lambda: tc.linear_bias(x, w1, b1, v))
@@ -81,10 +81,10 @@ def _gemm_section(r, tc, x, w1, b1, w2, b2, h, z, dy):
     for v, cfg in enumerate(tc.variants()["ffn_dgelu"]):
         r["dgrad_dgelu_tcgen05_v%d" % v] = graph_time(lambda: tc.ffn_dgelu(dy, w2, z, v))
     r["dgrad_dgelu_tcgen05"] = min(r["dgrad_dgelu_tcgen05_v%d" % v] for v in range(len(tc.variants()["ffn_dgelu"])))
-    if os.environ.get("DEAR_TC_EXPERIMENTAL"):
+    if hasattr(tc, "ffn_dgelu_hw_nt"):
         w2t = w2.t().contiguous()
-        r["dgrad_dgelu_tcgen05_handwritten"] = graph_time(lambda: tc.ffn_dgelu_hw(dy, w2t, z))
-        r["weight_transpose_for_handwritten_dgrad"] = graph_time(lambda: w2.t().contiguous())
+        r["dgrad_dgelu_tcgen05_handwritten_kmajor_needs_transpose"] = graph_time(lambda: tc.ffn_dgelu_hw(dy, w2t, z))
+        r["dgrad_dgelu_tcgen05_handwritten"] = graph_time(lambda: tc.ffn_dgelu_hw_nt(dy, w2, z))
     r["dgrad_gemm_only_cublas"] = graph_time(lambda: dy.mm(w2))
 
 
