@@ -65,6 +65,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def_readwrite("gen_grid", &CommOptions::gen_grid)
       .def_readwrite("rs_algo", &CommOptions::rs_algo)
       .def_readwrite("pipe_min_bytes", &CommOptions::pipe_min_bytes)
+      .def_readwrite("rs_grid_big", &CommOptions::rs_grid_big)
+      .def_readwrite("big_bucket_bytes", &CommOptions::big_bucket_bytes)
       .def_readwrite("stripe_target_bytes", &CommOptions::stripe_target_bytes)
       .def_readwrite("separate_ag_stream", &CommOptions::separate_ag_stream);
 

@@ -421,7 +421,7 @@ BucketSet::BucketSet(std::shared_ptr<Communicator> comm, std::vector<int64_t> pa
     } else {
       b.nstripes = 1;
       b.stripe_bytes = static_cast<uint64_t>(shard_bytes);
-      b.rs_grid = grid_for(bytes, o.rs_grid);
+      b.rs_grid = grid_for(bytes, (world > 1 && bytes >= o.big_bucket_bytes) ? std::max(o.rs_grid, o.rs_grid_big) : o.rs_grid);
     }
   }
   if (comm_->is_cuda()) {
@@ -451,12 +451,13 @@ BucketSet::~BucketSet() {
         for (void* e : st->ev) if (e) cudaEventDestroy(E(e));
         for (void* p : st->pinned) if (p) cudaFreeHost(p);
       }
-      for (void* p : b.captured_pinned) cudaFreeHost(p);
+      for (void* p : b.captured_tables) cudaFree(p);
       if (b.pack_dev) cudaFree(b.pack_dev);
       if (b.hyper_dev) cudaFree(b.hyper_dev);
     }
     if (ev_fence_) cudaEventDestroy(E(ev_fence_));
     if (ev_fence_ag_) cudaEventDestroy(E(ev_fence_ag_));
+    if (upload_stream_) cudaStreamDestroy(S(upload_stream_));
     if (ag_stream_ && ag_stream_ != stream_) {
       cudaStreamSynchronize(S(ag_stream_));
       cudaStreamDestroy(S(ag_stream_));
@@ -520,8 +521,45 @@ void BucketSet::upload(Bucket& b, bool is_pack, const void* host, size_t bytes, 
   const cudaStream_t cur = current_stream(comm_->options().device);
   // a capture may be in progress on the compute stream before the comm stream has joined it
   const bool capturing = is_capturing(S(stream_)) || is_capturing(cur);
+  if (capturing) {
+    //  * hyper-parameters must never be frozen into a graph (an LR scheduler could not change them any more):
+    //    TrainStep uploads them before the capture starts and after every change, outside the graph;
+    //  * a pack table holds the gradient addresses of THIS capture.  It gets a device buffer of its own that only the
+    //    captured kernels ever read (the pointer is baked into their launch parameters), filled right now on a private
+    //    stream outside the capture.  A replay therefore needs no H2D copy node — round 2 first used memcpy nodes, and
+    //    in the end-to-end benchmark they queued behind the 38 MB batch upload on the same copy engine — and eager
+    //    steps between replays keep using (and overwriting) the bucket's ordinary table without disturbing the graph.
+    DEAR_CHECK(is_pack, "optimizer hyper-parameters changed during CUDA-graph capture; upload them before capturing "
+                        "(DearEngine.refresh_hyper_outside_graph)");
+    void* dtab = nullptr;
+    void* pin = nullptr;
+    cudaError_t err = cudaSuccess;
+    {
+      // allocation / synchronisation calls are "potentially unsafe" under a thread-local capture: relax the mode
+      cudaStreamCaptureMode mode = cudaStreamCaptureModeRelaxed;
+      DEAR_CUDA(cudaThreadExchangeStreamCaptureMode(&mode));
+      if (upload_stream_ == nullptr) {
+        cudaStream_t us;
+        err = cudaStreamCreateWithFlags(&us, cudaStreamNonBlocking);
+        if (err == cudaSuccess) upload_stream_ = us;
+      }
+      if (err == cudaSuccess) err = cudaMalloc(&dtab, bytes);
+      if (err == cudaSuccess) err = cudaHostAlloc(&pin, bytes, cudaHostAllocDefault);
+      if (err == cudaSuccess) {
+        std::memcpy(pin, host, bytes);
+        err = cudaMemcpyAsync(dtab, pin, bytes, cudaMemcpyHostToDevice, S(upload_stream_));
+      }
+      if (err == cudaSuccess) err = cudaStreamSynchronize(S(upload_stream_));
+      if (pin) cudaFreeHost(pin);
+      cudaThreadExchangeStreamCaptureMode(&mode);
+    }
+    DEAR_CUDA(err);
+    b.captured_tables.push_back(dtab);
+    b.capture_table = dtab;
+    b.eager_table_stale = true;      // pack_host now mirrors the capture's table, not what pack_dev holds
+    return;
+  }
   if (*cap < bytes) {
-    DEAR_CHECK(!capturing, "device table would have to grow during CUDA-graph capture; run a few eager steps first");
     // the old table may still be read by an in-flight kernel on the comm streams
     DEAR_CUDA(cudaStreamSynchronize(S(stream_)));
     if (ag_stream_ != stream_) DEAR_CUDA(cudaStreamSynchronize(S(ag_stream_)));
@@ -530,31 +568,7 @@ void BucketSet::upload(Bucket& b, bool is_pack, const void* host, size_t bytes, 
     DEAR_CUDA(cudaMalloc(dev, ncap));
     *cap = ncap;
   }
-  if (capturing) {
-    // The copy becomes a memcpy NODE that re-reads its host source on every replay.
-    //  * hyper-parameters must never be frozen into a graph (an LR scheduler could not change them any more):
-    //    TrainStep uploads them before the capture starts and after every change, outside the graph;
-    //  * a pack table (the gradient addresses of THIS capture) gets a dedicated pinned buffer that nobody
-    //    writes again, and the copy is forced INTO the graph (the comm stream joins the capture first), so a
-    //    replay always restores the table its kernels were captured with — whatever eager steps ran in between.
-    DEAR_CHECK(is_pack, "optimizer hyper-parameters changed during CUDA-graph capture; upload them before capturing "
-                        "(DearEngine.refresh_hyper_outside_graph)");
-    if (!is_capturing(S(stream_))) fence_current_to_comm();
-    void* pin = nullptr;
-    {
-      // allocation calls are "potentially unsafe" under a thread-local capture: relax the mode around this one
-      cudaStreamCaptureMode mode = cudaStreamCaptureModeRelaxed;
-      DEAR_CUDA(cudaThreadExchangeStreamCaptureMode(&mode));
-      cudaError_t err = cudaHostAlloc(&pin, bytes, cudaHostAllocDefault);
-      cudaThreadExchangeStreamCaptureMode(&mode);
-      DEAR_CUDA(err);
-    }
-    b.captured_pinned.push_back(pin);
-    std::memcpy(pin, host, bytes);
-    DEAR_CUDA(cudaMemcpyAsync(*dev, pin, bytes, cudaMemcpyHostToDevice, S(stream_)));
-    b.pack_captured = true;
-    return;
-  }
+  if (is_pack) b.eager_table_stale = false;
   if (!is_pack && ag_stream_ != stream_) {
     // the hyper table is read by update kernels on the all-gather stream: overwrite it only after they finished
     DEAR_CUDA(cudaEventRecord(E(ev_fence_ag_), S(ag_stream_)));
@@ -609,8 +623,9 @@ bool BucketSet::set_pack(int g, const std::vector<int64_t>& src_ptrs, const std:
   const bool same = segs.size() == b.pack_host.size() &&
                     (segs.empty() || std::memcmp(segs.data(), b.pack_host.data(), segs.size() * sizeof(PackSeg)) == 0);
   b.pack_inplace = inplace;
-  // once a graph owns a memcpy node for this table, the device copy is whatever the last replay restored
-  if (same && !b.pack_captured) return false;
+  // (a capture always builds its own table; an eager call after a capture must refresh the bucket's table)
+  const bool capturing_now = comm_->is_cuda() && (is_capturing(S(stream_)) || is_capturing(current_stream(comm_->options().device)));
+  if (same && !b.eager_table_stale && !capturing_now) return false;
   b.pack_host = std::move(segs);
   b.ntiles = tiles;
   if (b.rs_algo == RS_ALGO_PIPE) {
@@ -711,8 +726,11 @@ void BucketSet::reduce_scatter(int g, bool pack) {
   p.shard_elems = static_cast<uint64_t>(b.shard);
   p.scale = grad_scale_ / static_cast<float>(comm_->size());
   const bool cuda = comm_->is_cuda();
+  // a capturing launch reads the capture's private table (set by set_pack during this capture)
+  const bool cap_now = cuda && is_capturing(current_stream(comm_->options().device));
+  PackSeg* table_dev = (cap_now && b.capture_table != nullptr) ? static_cast<PackSeg*>(b.capture_table) : b.pack_dev;
   if (pack && !b.pack_host.empty()) {
-    p.segs = cuda ? b.pack_dev : b.pack_host.data();
+    p.segs = cuda ? table_dev : b.pack_host.data();
     p.nseg = static_cast<uint32_t>(b.pack_host.size());
     p.ntiles = b.ntiles;
     // one GPU: the pack writes the fp32 shard directly (fp32: copy; bf16 / fp16: widening, CUDA kernel only)
@@ -738,7 +756,7 @@ void BucketSet::reduce_scatter(int g, bool pack) {
       p.nstripes = b.nstripes;
       p.stripe_bytes = b.stripe_bytes;
       p.mc_grad = nullptr;
-      p.pieces = (pack && !b.pieces_host.empty()) ? b.pack_dev : nullptr;
+      p.pieces = (pack && !b.pieces_host.empty()) ? table_dev : nullptr;
       std::memcpy(p.piece_first, b.piece_first, sizeof(p.piece_first));
       p.segs = nullptr;
       launch_rs_pipe(p, b.rs_grid, S(stream_));

@@ -40,7 +40,11 @@ struct CommOptions {
   // Kernel A variant per bucket: -1 = pick by bucket size (one-shot below `pipe_min_bytes`, stripe-pipelined TMA
   // pull above, NVLS ld_reduce only on request); 0 / 1 / 2 force RS_ALGO_ONESHOT / _PIPE / _NVLS for every bucket.
   int rs_algo = -1;
-  int64_t pipe_min_bytes = 128ll << 20;
+  int64_t pipe_min_bytes = int64_t(1) << 60;   // auto never picks the pipelined variant unless this is lowered:
+                                               // at 8 GPUs the one-shot kernel on a wide grid is faster at every
+                                               // size (profiles/r2/session_8gpu_a.log)
+  int rs_grid_big = 128;                       // CTA bound for buckets >= big_bucket_bytes (their pack phase scales
+  int64_t big_bucket_bytes = 128ll << 20;      // with the CTA count: 846 / 711 us at 32 / 96 CTAs for 392 MB, P=8)
   int64_t stripe_target_bytes = 8ll << 20;   // bucket bytes per stripe the pipelined kernel aims for
   bool separate_ag_stream = true;            // all-gathers on their own stream (reference: three communicators)
 };
@@ -171,8 +175,7 @@ class BucketSet {
     HyperSeg* hyper_dev = nullptr;
     size_t hyper_cap = 0;
     // Host staging of the two device tables.  Each table kind has its OWN double-buffered pinned area, and an
-    // upload that is captured into a CUDA graph gets a dedicated buffer that is never written again (the graph's
-    // memcpy node re-reads it on every replay).
+    // upload requested during a CUDA-graph capture fills a device table of its own (BucketSet::upload).
     struct Staging {
       void* pinned[2] = {nullptr, nullptr};
       size_t cap[2] = {0, 0};
@@ -180,8 +183,9 @@ class BucketSet {
       int next = 0;
     };
     Staging stage_pack, stage_hyper;
-    std::vector<void*> captured_pinned;   // owned by captured memcpy nodes; freed with the BucketSet
-    bool pack_captured = false;           // a graph restores pack_dev on replay: eager uploads can never be skipped
+    std::vector<void*> captured_tables;   // device tables owned by CUDA-graph captures; freed with the BucketSet
+    void* capture_table = nullptr;        // table of the capture in progress (launch parameter of its kernels)
+    bool eager_table_stale = false;       // pack_host mirrors a capture's table: the next eager set_pack must upload
     int rs_algo = RS_ALGO_ONESHOT;
     uint32_t nstripes = 1;
     uint64_t stripe_bytes = 0;
@@ -204,6 +208,7 @@ class BucketSet {
   void* ag_stream_ = nullptr;   // cudaStream_t: update + all-gather kernels (== stream_ unless separate_ag_stream)
   void* ev_fence_ = nullptr;
   void* ev_fence_ag_ = nullptr;
+  void* upload_stream_ = nullptr;   // private non-capturing stream for tables built during a capture
   float grad_scale_ = 1.0f;
 };
 

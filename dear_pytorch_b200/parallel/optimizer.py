@@ -97,6 +97,12 @@ class DearEngine:
             for p in grp["params"]:
                 self.group_of[p] = gi
 
+        # true grad-as-bucket-view for GEMM-produced gradients (fused backends, one backward pass per step)
+        from ..ops import direct_wgrad
+        self._direct_wgrad = (self.backend_name in ("b200", "emu") and self.passes_per_step == 1 and direct_wgrad.enabled()
+                              and not self.exclude_reducescatter)
+        if self._direct_wgrad:
+            direct_wgrad.install(model)
         self.plan = BucketPlan(model, self.world)
         for s in self.plan.slots:
             if s.param not in self.group_of:
@@ -159,6 +165,7 @@ class DearEngine:
         self.steal = be.steal_grads
         self._param_view: Dict[nn.Parameter, torch.Tensor] = {}
         self._grad_view: Dict[nn.Parameter, torch.Tensor] = {}
+        self._direct_params: List[nn.Parameter] = []
         for b in plan.buckets:
             pbuf, gbuf = be.param_buffer(b.index), be.grad_buffer(b.index)
             for s in b.slots:
@@ -175,6 +182,13 @@ class DearEngine:
                     p.grad = None
                 else:
                     p.grad = gv
+                # Linear weights: the wgrad GEMM writes its slice of the gradient bucket directly (ops/direct_wgrad.py)
+                if self._direct_wgrad and p.dim() == 2 and gv.is_contiguous():
+                    p._dear_grad_view = gv
+                    p._dear_grad_written = False
+                    self._direct_params.append(p)
+                elif hasattr(p, "_dear_grad_view"):
+                    del p._dear_grad_view
         be.init_master_shards()
         if carry is not None:
             self._restore_state(carry)
@@ -263,6 +277,11 @@ class DearEngine:
 
     def _hand_over(self, g, i, p, grad):
         """Steal mode: point the pack table of bucket g at this gradient (or stage it in the bucket view)."""
+        if grad.data_ptr() == self._grad_view[p].data_ptr():
+            # already in the bucket: the layer's wgrad GEMM wrote it there (ops/direct_wgrad.py)
+            self._src[g][i] = 0
+            self._flags[g][i] = 0
+            return
         if (grad.dtype == p.dtype and grad.stride() == p.stride() and grad.data_ptr() % 16 == 0
                 and not grad.is_sparse):
             self._src[g][i] = grad.data_ptr()
@@ -405,6 +424,8 @@ class DearEngine:
             for s in self.plan.slots:
                 s.param.grad = None
         self._passes_seen.clear()
+        for p in self._direct_params:
+            p._dear_grad_written = False
         # reset the per-iteration state machine
         for g in range(nb):
             if self._n_arrived[g]:
@@ -531,6 +552,8 @@ class DearEngine:
             for s in self.plan.slots:
                 s.param.data = s.param.data.clone(memory_format=torch.preserve_format)
                 s.param.grad = None
+                if hasattr(s.param, "_dear_grad_view"):
+                    del s.param._dear_grad_view
         self._inflight.clear()
         self._grad_view = {}
         self.backend = None

@@ -145,7 +145,9 @@ def init(backend: Optional[str] = None, device: Optional[torch.device] = None, *
         if algo not in ("auto", "oneshot", "pipe", "nvls"):
             raise ValueError("DEAR_RS_ALGO must be auto, oneshot, pipe or nvls")
         o.rs_algo = {"auto": -1, "oneshot": 0, "pipe": 1, "nvls": 2}[algo]
-        o.pipe_min_bytes = int(float(os.environ.get("DEAR_PIPE_MIN_MB", "128")) * (1 << 20))
+        if "DEAR_PIPE_MIN_MB" in os.environ:      # auto mode: buckets at least this large use the pipelined variant
+            o.pipe_min_bytes = int(float(os.environ["DEAR_PIPE_MIN_MB"]) * (1 << 20))
+        o.rs_grid_big = _env_int("DEAR_RS_GRID_BIG", 128)
         o.stripe_target_bytes = int(float(os.environ.get("DEAR_STRIPE_MB", "8")) * (1 << 20))
         o.separate_ag_stream = os.environ.get("DEAR_AG_STREAM", "1") not in ("0", "false", "False")
         # rendezvous keys must be unique per init(): a re-initialised process group can land on the SAME TCPStore server

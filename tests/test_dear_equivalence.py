@@ -96,3 +96,34 @@ def test_world_of_three_emu():
     for params, nb in outs:
         for a, b in zip(params, ref):
             torch.testing.assert_close(a, b, rtol=2e-5, atol=2e-6)
+
+
+def _direct_wgrad_worker(rank, world):
+    import dear_pytorch_b200 as dear
+    torch.manual_seed(0)
+    model = nn.Sequential(nn.Linear(16, 32), nn.ReLU(), nn.Linear(32, 4))
+    opt = dear.DistributedOptimizer(torch.optim.SGD(model.parameters(), lr=0.1), model, threshold=0.0001, verbose=False)
+    eng = opt.engine
+    x = torch.randn(8, 16)
+    model(x).pow(2).mean().backward()
+    in_bucket = {}
+    for s in eng.plan.slots:
+        p = s.param
+        in_bucket[s.name] = (p.grad is not None and p.grad.data_ptr() == eng._grad_view[p].data_ptr(),
+                             eng._src[s.bucket][s.index_in_bucket])
+    opt.step()
+    opt.synchronize()
+    return in_bucket
+
+
+def test_linear_weight_gradients_are_written_into_the_bucket_by_the_gemm():
+    """True grad-as-bucket-view for GEMM-produced gradients (ops/direct_wgrad.py): after backward the Linear weights'
+    ``p.grad`` aliases the gradient bucket and the pack table skips them (source pointer 0 = already in place);
+    biases still travel through the pack."""
+    from _mp import run_ranks
+    out = run_ranks(_direct_wgrad_worker, world=2, backend="emu")[0]
+    for name, (aliased, src) in out.items():
+        if name.endswith("weight"):
+            assert aliased and src == 0, (name, aliased, src)
+        else:
+            assert not aliased and src != 0, (name, aliased, src)

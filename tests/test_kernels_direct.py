@@ -144,9 +144,12 @@ def plan_worker(rank, world):
 
 @pytest.mark.gpu
 def test_reduce_scatter_algorithm_is_picked_per_bucket_size():
-    small, big = run_ranks(plan_worker, world=2, backend="b200", extra_env={"DEAR_SPIN_TIMEOUT_S": "15"}, timeout=300)[0]
-    assert small.startswith("oneshot"), small      # 512 KB: latency-bound, fewest flag rounds
-    assert big.startswith("pipe") and "stripes=16" in big, big     # 256 MB: stripe-pipelined TMA pull
+    env = {"DEAR_SPIN_TIMEOUT_S": "15"}
+    small, big = run_ranks(plan_worker, world=2, backend="b200", extra_env=env, timeout=300)[0]
+    assert small.startswith("oneshot:grid=8:"), small       # 512 KB: latency-bound, few CTAs
+    assert big.startswith("oneshot:grid=128:"), big         # 256 MB: the pack phase wants the wide grid
+    small, big = run_ranks(plan_worker, world=2, backend="b200", extra_env=dict(env, DEAR_PIPE_MIN_MB="128"), timeout=300)[0]
+    assert small.startswith("oneshot") and big.startswith("pipe") and "stripes=16" in big, (small, big)
 
 
 def nvls_worker(rank, world, dtype_name):

@@ -125,6 +125,8 @@ def main():
                 out.div_(world)
             row["nccl_copy_rs_div_us"] = round(nccl_timed(ref_path), 2)
             row["rs_vs_nccl"] = round(t_rs / row["nccl_rs_us"], 3)
+            # gradients that a GEMM wrote straight into the bucket (ops/direct_wgrad.py: Linear layers) skip the pack
+            row["rs_nopack_vs_nccl"] = round(t_rs_nopack / row["nccl_rs_us"], 3)
             row["rs_vs_nccl_copy_rs_div"] = round(t_rs / row["nccl_copy_rs_div_us"], 3)
             del src
         results.append(row)
