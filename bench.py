@@ -49,7 +49,8 @@ def parse_args(argv=None):
     ap.add_argument("--fused-ln", type=int, default=int(os.environ.get("DEAR_BENCH_FUSED_LN", "1")),
                     help="BERT: dropout + add + LayerNorm in one kernel (csrc/ln_fused.cu)")
     ap.add_argument("--tc-ffn", type=int, default=int(os.environ.get("DEAR_BENCH_TC_FFN", "0")),
-                    help="BERT bf16: feed-forward block on the tcgen05 GEMMs with fused GELU epilogues (csrc/tc_gemm*.cu)")
+                    help="BERT bf16: feed-forward block on the hand-written tcgen05 GEMMs with fused GELU epilogues (csrc/tc_ffn_hw.cu); "
+                         "off by default: cuBLAS + the fused bias/GELU kernels are faster (profiles/README.md R2.5)")
     ap.add_argument("--threshold", type=float, default=25.0)
     ap.add_argument("--momentum", type=float, default=0.0)
     ap.add_argument("--optimizer", choices=["sgd", "adam", "adamw"], default="sgd",

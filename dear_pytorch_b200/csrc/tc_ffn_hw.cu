@@ -17,14 +17,15 @@
 //   warp 1      MMA issuer: one thread issues tcgen05.mma.cta_group::1.kind::f16 (M128 N256 K16) x4 per stage,
 //               tcgen05.commit -> "stage empty" barrier, and -> "accumulator full" barrier after the last K step
 //   warp 2      allocates / frees the 512 TMEM columns (2 accumulator stages x 256 fp32 columns)
-//   warps 4-11  epilogue: tcgen05.ld 32x32b (64 columns per step) -> +bias -> erf-GELU -> 128B-swizzled staging tile in
-//               shared memory -> coalesced 128-byte-line global stores (H, Z); arrive on "accumulator empty" so the MMA
-//               warp can start tile i+2 while tile i drains
+//   warps 4-11  epilogue: tcgen05.ld 32x32b.x32 -> +bias -> erf-GELU -> 16-byte-vector global stores (H, Z); arrive on
+//               "accumulator empty" so the MMA warp can start tile i+2 while tile i drains
 //
-// STATUS: validated on B200 (tests/test_tc_gemm.py::test_handwritten_*, fp32 oracle).  First hardware run (round 2,
-// profiles/r2/bert_ops_bench_handwritten_tcgen05.json): up+GELU 27.3 us, dgrad x GELU' 27.9 us against 25.4 / 29.3 us for
-// cuBLAS + elementwise kernels — the per-lane 16-byte global stores of that version were the bottleneck, hence the
-// staged, coalesced epilogue above.  Every mbarrier wait is bounded and traps instead of spinning forever.
+// STATUS: validated on B200 (tests/test_tc_gemm.py::test_handwritten_*, fp32 oracle; 1/2/4-CTA multicast clusters, K-major
+// and MN-major B).  Measured (profiles/r2/): up+GELU 27.3 us and dgrad x GELU' 27.9 us (on the weight as stored) against
+// 25.4 / 29.3 us for cuBLAS + elementwise kernels; multicast clusters buy ~9 %.  ncu (prof_tc_ffn_hw_cl1_summary.md): tensor
+// pipe 29 % active — two serialized ~10 us epilogues per CTA (256 tiles on 148 SMs), not the mainloop, set the pace.  The
+// kernel is opt-in (DEAR_TC_FFN_IMPL=hw); the default FFN stays cuBLAS + the fused bias/GELU kernels of ln_fused.cu.
+// Every mbarrier wait is bounded and traps instead of spinning forever.
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/cuda/CUDAGuard.h>
 #include <cuda.h>
@@ -49,9 +50,7 @@ constexpr int kStageBytes = kABytes + kBBytes;          // 48 KB
 constexpr int kNumThreads = 384;                        // 12 warps
 constexpr int kEpilogueWarp0 = 4, kEpilogueWarps = 8;
 constexpr int kTmemCols = kAccStages * kTileN;          // 512
-constexpr int kEpiChunk = 64;                           // accumulator columns handled per epilogue step
-constexpr int kStageOutBytes = 32 * kEpiChunk * 2;      // 4 KB per epilogue warp: 32 rows x 64 bf16, 128B-swizzled
-constexpr int kSmemBytes = kStages * kStageBytes + kEpilogueWarps * kStageOutBytes + 1024 /* alignment slack */ + 256 /* barriers */;
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /* alignment slack */ + 256 /* barriers */;
 
 // ---------------------------------------------------------------------------------------------- PTX
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -100,6 +99,22 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// the same box delivered into the shared memory (same CTA-relative offset) of every CTA in `mask`; each destination's
+// mbarrier (same offset) receives the complete_tx
+__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -124,6 +139,13 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
 // all previously issued tcgen05.mma of this thread arrive on the mbarrier when they complete
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ... and on the barrier at the same offset in every CTA of `mask` (a stage that a peer's multicast load will overwrite)
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(mask)
+               : "memory");
 }
 
 __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -214,15 +236,19 @@ enum EpilogueMode { MODE_UP = 0, MODE_DGELU = 1 };
 
 // BMN: the B operand is given as a row-major [K, N] matrix (MN-major) instead of [N, K] (K-major): the dgrad GEMM
 // dH = dY W2 reads the nn.Linear weight W2 [hidden, inter] as it is stored — no transposed copy per step.
-template <int MODE, bool BMN>
+// CL: CTAs per cluster (1, 2 or 4).  The CTAs of a cluster work on vertically adjacent output tiles (same n range); each
+// loads 1/CL of the B tile and MULTICASTS it to all of them, so per K step a CTA makes L2 serve 16 + 32/CL KB instead of
+// 48 KB.  Why: ncu on the CL = 1 kernel (profiles/r2/prof_tc_ffn_hw_cl1_summary.md) shows the tensor pipe 29 % active
+// and 201 MB of L2->SM traffic in 30 us = 6.7 TB/s, which IS the chip's L2 throughput cap (~6300 B/clk, B300_MICROARCH.md):
+// a 128x256 tile per CTA re-reads B 16 times and A 16 times.  Multicast is the B200 answer: one L2 read, CL deliveries.
+template <int MODE, bool BMN, int CL>
 __global__ void __launch_bounds__(kNumThreads, 1)
 ffn_hw_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
               const __nv_bfloat16* __restrict__ aux, __nv_bfloat16* __restrict__ out0, __nv_bfloat16* __restrict__ out1,
               int M, int N, int K) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint8_t* stage_out = smem + kStages * kStageBytes;     // [kEpilogueWarps][kStageOutBytes]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_out + kEpilogueWarps * kStageOutBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
   uint64_t* full_bar = bars;                             // [kStages]   TMA -> MMA
   uint64_t* empty_bar = bars + kStages;                  // [kStages]   MMA -> TMA
   uint64_t* acc_full_bar = bars + 2 * kStages;           // [kAccStages] MMA -> epilogue
@@ -231,21 +257,27 @@ ffn_hw_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_m = (M + kTileM - 1) / kTileM, tiles_n = (N + kTileN - 1) / kTileN;
-  const int num_tiles = tiles_m * tiles_n;
   const int num_kb = (K + kTileK - 1) / kTileK;
+  // cluster-tile schedule: cluster c takes every (gridDim/CL)-th group of CL vertically adjacent tiles
+  const int crank = (CL > 1) ? static_cast<int>(cluster_ctarank()) : 0;
+  const int cid = blockIdx.x / CL, ncl = gridDim.x / CL;
+  const int tiles_mc = tiles_m / CL;                     // the host guarantees tiles_m % CL == 0
+  const int num_ct = tiles_mc * tiles_n;
+  constexpr uint16_t kAllCtas = static_cast<uint16_t>((1u << CL) - 1);
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CL); }
     for (int a = 0; a < kAccStages; ++a) { mbar_init(&acc_full_bar[a], 1); mbar_init(&acc_empty_bar[a], kEpilogueWarps); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_base_slot, kTmemCols);
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();                        // the peer's barriers exist before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
 
@@ -253,18 +285,27 @@ ffn_hw_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
     // ===================================================================== TMA producer (one lane)
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile % tiles_m) * kTileM, n0 = (tile / tiles_m) * kTileN;
+      for (int ct = cid; ct < num_ct; ct += ncl) {
+        const int m0 = ((ct % tiles_mc) * CL + crank) * kTileM, n0 = (ct / tiles_mc) * kTileN;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);                     // slot free (passes at once the first round)
+          mbar_wait(&empty_bar[stage], phase ^ 1);                     // slot free in EVERY CTA of the cluster
           mbar_expect_tx(&full_bar[stage], kStageBytes);               // OOB rows/columns are zero-filled AND counted
           uint8_t* a_dst = smem + stage * kStageBytes;
           tma_load_2d(a_dst, &tmap_a, &full_bar[stage], kb * kTileK, m0);
           if (BMN) {
-            // kTileN/64 boxes of {64 n (contiguous), kTileK k}: 8 KB each, 128B-swizzled by the k row
+            // kTileN/64 boxes of {64 n (contiguous), kTileK k}: 8 KB each, 128B-swizzled by the k row; with CL = 2
+            // this CTA fetches its half of the boxes and multicasts them
 #pragma unroll
-            for (int j = 0; j < kTileN / 64; ++j)
-              tma_load_2d(a_dst + kABytes + j * (kTileK * 128), &tmap_b, &full_bar[stage], n0 + j * 64, kb * kTileK);
+            for (int j = 0; j < kTileN / 64 / CL; ++j) {
+              const int jj = crank * (kTileN / 64 / CL) + j;
+              uint8_t* dst = a_dst + kABytes + jj * (kTileK * 128);
+              if (CL > 1) tma_load_2d_mc(dst, &tmap_b, &full_bar[stage], n0 + jj * 64, kb * kTileK, kAllCtas);
+              else tma_load_2d(dst, &tmap_b, &full_bar[stage], n0 + jj * 64, kb * kTileK);
+            }
+          } else if (CL > 1) {
+            // rows [n0 + crank*kTileN/CL, +kTileN/CL) of B, delivered to every CTA (the map's box has kTileN / CL rows)
+            tma_load_2d_mc(a_dst + kABytes + crank * (kBBytes / CL), &tmap_b, &full_bar[stage], kb * kTileK,
+                           n0 + crank * (kTileN / CL), kAllCtas);
           } else {
             tma_load_2d(a_dst + kABytes, &tmap_b, &full_bar[stage], kb * kTileK, n0);
           }
@@ -277,7 +318,7 @@ ffn_hw_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int ct = cid; ct < num_ct; ct += ncl) {
         mbar_wait(&acc_empty_bar[acc], acc_phase ^ 1);                 // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * kTileN;
@@ -294,7 +335,8 @@ ffn_hw_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
             umma_f16(tmem_d, make_smem_desc(a_addr + k * kUmmaK * 2), bdesc, BMN ? kInstrDescBMN : kInstrDesc,
                      (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);                              // frees the smem slot when these MMAs retire
+          // frees the smem slot when these MMAs retire — in every CTA whose multicast load refills it
+          if (CL > 1) umma_commit_mc(&empty_bar[stage], kAllCtas); else umma_commit(&empty_bar[stage]);
           if (kb == num_kb - 1) umma_commit(&acc_full_bar[acc]);       // accumulator complete -> epilogue
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -305,94 +347,57 @@ ffn_hw_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
     // ================================================================== epilogue (8 warps = 2 warpgroups)
     const int quad = warp & 3;                                         // TMEM lanes 32*quad .. 32*quad+31
     const int half = (warp - kEpilogueWarp0) >> 2;                     // which 128 of the 256 accumulator columns
-    // Staging tile of this warp: 32 rows x 128 bytes, 16-byte chunk c of row r stored at chunk (c ^ (r & 7)).
-    //  * register -> smem: lane = row, one STS.128 per chunk; a quarter-warp hits 8 different chunks => no conflicts
-    //  * smem -> global:   8 lanes cover one 128-byte row, 4 rows per instruction => fully coalesced 128-byte lines
-    // (round 1 stored 16 bytes per lane straight to global: 32 different lines per instruction, and the epilogue,
-    //  not the tensor core, set the kernel's pace: 27.3 us against 25.4 us for cuBLAS + a GELU kernel)
-    uint8_t* my_stage = stage_out + (warp - kEpilogueWarp0) * kStageOutBytes;
-    const int srow = lane >> 3, schunk = lane & 7;                     // coalesced phase: row srow + 4*i, chunk schunk
+    // Each lane owns one output row and stores 16-byte vectors straight to global memory.  A staged variant (128B-
+    // swizzled shared-memory tile per warp, 4 full 128-byte lines per store instruction) was measured on B200 and was
+    // SLOWER: 29.95 vs 27.25 us for up+GELU (profiles/r2/bert_ops_bench_staged_epilogue.json vs
+    // bert_ops_bench_handwritten_tcgen05.json) — the epilogue is bound by its instruction count (~37 per element with two
+    // outputs and an erf GELU, 2 warps per scheduler), not by store wavefronts, and the staging added instructions.
     int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile % tiles_m) * kTileM, n0 = (tile / tiles_m) * kTileN;
+    for (int ct = cid; ct < num_ct; ct += ncl) {
+      const int m0 = ((ct % tiles_mc) * CL + crank) * kTileM, n0 = (ct / tiles_mc) * kTileN;
       mbar_wait(&acc_full_bar[acc], acc_phase);
       tc_fence_after();
-      const int row0 = m0 + quad * 32;                                 // first global row of this warp's 32 rows
+      const int row = m0 + quad * 32 + lane;
+      const size_t row_off = static_cast<size_t>(row) * N;
 #pragma unroll 1
-      for (int c = 0; c < (kTileN / 2) / kEpiChunk; ++c) {
-        const int col0 = half * (kTileN / 2) + c * kEpiChunk;
+      for (int c = 0; c < (kTileN / 2) / 32; ++c) {
+        const int col0 = half * (kTileN / 2) + c * 32;
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + acc * kTileN + col0 + (static_cast<uint32_t>(quad * 32) << 16), v);
+        tmem_ld_wait();
         const int gcol = n0 + col0;
-        const bool col_ok = gcol + schunk * 8 < N;                     // my 16-byte chunk of the coalesced phases (N % 8 == 0)
-        if (MODE == MODE_DGELU) {
-          // Z chunk: coalesced global -> staging tile (4 rows x 128 B per instruction)
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = srow + 4 * i;
-            uint4 zv = make_uint4(0, 0, 0, 0);
-            if (col_ok && row0 + r < M) zv = __ldg(reinterpret_cast<const uint4*>(aux + static_cast<size_t>(row0 + r) * N + gcol) + schunk);
-            *reinterpret_cast<uint4*>(my_stage + r * 128 + ((schunk ^ (r & 7)) << 4)) = zv;
-          }
-          __syncwarp();
-        }
-        uint32_t v[kEpiChunk];
-        {
-          uint32_t lo[32], hi[32];
-          const uint32_t taddr = tmem_base + acc * kTileN + col0 + (static_cast<uint32_t>(quad * 32) << 16);
-          tmem_ld_32x32b_x32(taddr, lo);
-          tmem_ld_32x32b_x32(taddr + 32, hi);
-          tmem_ld_wait();
+        for (int j = 0; j < 4; ++j) {                                  // 8 columns = one 16-byte vector of bf16
+          const int cj = gcol + j * 8;
+          if (cj < N) {                                                // N % 8 == 0: a vector is all-in or all-out
+            if (MODE == MODE_UP) {
+              const uint4 bv = __ldg(reinterpret_cast<const uint4*>(aux + cj));
+              const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+              uint32_t zq[4], hq[4];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) { v[j] = lo[j]; v[32 + j] = hi[j]; }
-        }
-        uint32_t q0[kEpiChunk / 2];                                    // packed bf16 pairs of out0 (H or dZ)
+              for (int i = 0; i < 4; ++i) {
+                const float b0 = __uint_as_float(bw[i] << 16), b1 = __uint_as_float(bw[i] & 0xffff0000u);
+                const float z0 = __uint_as_float(v[j * 8 + 2 * i]) + b0, z1 = __uint_as_float(v[j * 8 + 2 * i + 1]) + b1;
+                zq[i] = pack_bf16(z0, z1);
+                hq[i] = pack_bf16(gelu_fast(z0), gelu_fast(z1));
+              }
+              if (row < M) {
+                *reinterpret_cast<uint4*>(out1 + row_off + cj) = make_uint4(zq[0], zq[1], zq[2], zq[3]);
+                *reinterpret_cast<uint4*>(out0 + row_off + cj) = make_uint4(hq[0], hq[1], hq[2], hq[3]);
+              }
+            } else if (row < M) {                                      // (per-lane predicate: no collective below)
+              const uint4 zv = __ldg(reinterpret_cast<const uint4*>(aux + row_off + cj));
+              const uint32_t zw[4] = {zv.x, zv.y, zv.z, zv.w};
+              uint32_t dq[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {                                  // 8 columns = one 16-byte chunk
-          if (MODE == MODE_UP) {
-            uint4 bv = make_uint4(0, 0, 0, 0);
-            if (gcol + j * 8 < N) bv = __ldg(reinterpret_cast<const uint4*>(aux + gcol) + j);
-            const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
-            uint32_t zq[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float b0 = __uint_as_float(bw[i] << 16), b1 = __uint_as_float(bw[i] & 0xffff0000u);
-              const float z0 = __uint_as_float(v[j * 8 + 2 * i]) + b0, z1 = __uint_as_float(v[j * 8 + 2 * i + 1]) + b1;
-              zq[i] = pack_bf16(z0, z1);
-              q0[j * 4 + i] = pack_bf16(gelu_fast(z0), gelu_fast(z1));
-            }
-            // the pre-activation goes to the staging tile right away (it is stored first, below)
-            *reinterpret_cast<uint4*>(my_stage + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_uint4(zq[0], zq[1], zq[2], zq[3]);
-          } else {
-            const uint4 zv = *reinterpret_cast<const uint4*>(my_stage + lane * 128 + ((j ^ (lane & 7)) << 4));
-            const uint32_t zw[4] = {zv.x, zv.y, zv.z, zv.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float z0 = __uint_as_float(zw[i] << 16), z1 = __uint_as_float(zw[i] & 0xffff0000u);
-              q0[j * 4 + i] = pack_bf16(__uint_as_float(v[j * 8 + 2 * i]) * dgelu_fast(z0),
-                                        __uint_as_float(v[j * 8 + 2 * i + 1]) * dgelu_fast(z1));
+              for (int i = 0; i < 4; ++i) {
+                const float z0 = __uint_as_float(zw[i] << 16), z1 = __uint_as_float(zw[i] & 0xffff0000u);
+                dq[i] = pack_bf16(__uint_as_float(v[j * 8 + 2 * i]) * dgelu_fast(z0),
+                                  __uint_as_float(v[j * 8 + 2 * i + 1]) * dgelu_fast(z1));
+              }
+              *reinterpret_cast<uint4*>(out0 + row_off + cj) = make_uint4(dq[0], dq[1], dq[2], dq[3]);
             }
           }
-        }
-        if (MODE == MODE_DGELU) __syncwarp();                          // everyone has read its Z row: the tile is reused
-#pragma unroll
-        for (int pass = 0; pass < (MODE == MODE_UP ? 2 : 1); ++pass) {
-          // MODE_UP: pass 0 stores Z (already staged), pass 1 stages and stores H;  MODE_DGELU: one pass for dZ
-          const bool from_regs = (MODE != MODE_UP) || pass == 1;
-          __nv_bfloat16* outp = (MODE == MODE_UP && pass == 0) ? out1 : out0;
-          if (from_regs) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              *reinterpret_cast<uint4*>(my_stage + lane * 128 + ((j ^ (lane & 7)) << 4)) =
-                  make_uint4(q0[j * 4], q0[j * 4 + 1], q0[j * 4 + 2], q0[j * 4 + 3]);
-          }
-          __syncwarp();
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = srow + 4 * i;
-            const uint4 o = *reinterpret_cast<const uint4*>(my_stage + r * 128 + ((schunk ^ (r & 7)) << 4));
-            if (col_ok && row0 + r < M)
-              *(reinterpret_cast<uint4*>(outp + static_cast<size_t>(row0 + r) * N + gcol) + schunk) = o;
-          }
-          __syncwarp();
         }
       }
       tc_fence_before();
@@ -405,6 +410,7 @@ ffn_hw_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
   // ------------------------------------------------------------------------------------- teardown
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();                        // no multicast / remote arrive may target a CTA that has exited
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
@@ -462,24 +468,62 @@ static void check_bf16(const at::Tensor& t, const char* what) {
               reinterpret_cast<uintptr_t>(t.data_ptr()) % 16 == 0, what, ": contiguous 16-byte aligned CUDA bf16 tensor expected");
 }
 
-template <int MODE, bool BMN = false>
-static void launch_hw(const at::Tensor& a, const at::Tensor& b, const __nv_bfloat16* aux, at::Tensor& out0, at::Tensor* out1,
-                      int M, int N, int K) {
+template <int MODE, bool BMN, int CL>
+static void launch_hw_cl(const at::Tensor& a, const at::Tensor& b, const __nv_bfloat16* aux, at::Tensor& out0, at::Tensor* out1,
+                         int M, int N, int K) {
   const CUtensorMap ta = hw::make_tmap(a.data_ptr(), M, K, hw::kTileM);
-  const CUtensorMap tb = BMN ? hw::make_tmap_mn(b.data_ptr(), K, N) : hw::make_tmap(b.data_ptr(), N, K, hw::kTileN);
+  const CUtensorMap tb = BMN ? hw::make_tmap_mn(b.data_ptr(), K, N) : hw::make_tmap(b.data_ptr(), N, K, hw::kTileN / CL);
   static std::once_flag attr_once;
   std::call_once(attr_once, [] {
-    C10_CUDA_CHECK(cudaFuncSetAttribute(hw::ffn_hw_kernel<MODE, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, hw::kSmemBytes));
+    C10_CUDA_CHECK(cudaFuncSetAttribute(hw::ffn_hw_kernel<MODE, BMN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, hw::kSmemBytes));
   });
   const int tiles = ((M + hw::kTileM - 1) / hw::kTileM) * ((N + hw::kTileN - 1) / hw::kTileN);
   const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
-  const int grid = std::min(tiles, sms);
   auto stream = at::cuda::getCurrentCUDAStream().stream();
-  hw::ffn_hw_kernel<MODE, BMN><<<grid, hw::kNumThreads, hw::kSmemBytes, stream>>>(
-      ta, tb, aux, reinterpret_cast<__nv_bfloat16*>(out0.data_ptr()),
-      out1 != nullptr ? reinterpret_cast<__nv_bfloat16*>(out1->data_ptr()) : nullptr, M, N, K);
-  C10_CUDA_KERNEL_LAUNCH_CHECK();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(std::max(CL, sms / CL * CL));
+  cfg.blockDim = dim3(hw::kNumThreads);
+  cfg.dynamicSmemBytes = hw::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  // persistent kernel: one resident cluster per slot the hardware can co-schedule (GPC boundaries strand a few SMs
+  // for clusters of 4), never more than there are cluster-tiles
+  static int max_clusters = 0;
+  if (max_clusters == 0) {
+    int n = 0;
+    if (CL == 1 || cudaOccupancyMaxActiveClusters(&n, hw::ffn_hw_kernel<MODE, BMN, CL>, &cfg) != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      n = sms / CL;
+    }
+    max_clusters = n;
+  }
+  const int grid = std::max(1, std::min(tiles / CL, max_clusters)) * CL;
+  cfg.gridDim = dim3(grid);
+  C10_CUDA_CHECK(cudaLaunchKernelEx(&cfg, hw::ffn_hw_kernel<MODE, BMN, CL>, ta, tb, aux,
+                                    reinterpret_cast<__nv_bfloat16*>(out0.data_ptr()),
+                                    out1 != nullptr ? reinterpret_cast<__nv_bfloat16*>(out1->data_ptr()) : nullptr, M, N, K));
   count_launch();
+}
+
+static int g_force_cluster = -1;       // -1: pick by shape; 1 / 2 / 4: forced (benchmarks, tests)
+void set_ffn_hw_cluster(int cl) { g_force_cluster = cl; }
+
+template <int MODE, bool BMN = false>
+static void launch_hw(const at::Tensor& a, const at::Tensor& b, const __nv_bfloat16* aux, at::Tensor& out0, at::Tensor* out1,
+                      int M, int N, int K) {
+  const int tiles_m = (M + hw::kTileM - 1) / hw::kTileM;
+  // the CTAs of a cluster take vertically adjacent tiles: the cluster size must divide the number of tile rows
+  int cl = g_force_cluster > 0 ? g_force_cluster : 4;
+  while (cl > 1 && tiles_m % cl != 0) cl >>= 1;
+  if (cl >= 4) launch_hw_cl<MODE, BMN, 4>(a, b, aux, out0, out1, M, N, K);
+  else if (cl == 2) launch_hw_cl<MODE, BMN, 2>(a, b, aux, out0, out1, M, N, K);
+  else launch_hw_cl<MODE, BMN, 1>(a, b, aux, out0, out1, M, N, K);
 }
 
 // H, Z = gelu(X W^T + b), X W^T + b      (experimental: see the header of this file)

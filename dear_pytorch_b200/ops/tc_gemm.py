@@ -1,4 +1,4 @@
-"""Transformer feed-forward block on the tcgen05 GEMMs of ``csrc/tc_gemm*.cu``.
+"""Transformer feed-forward block on the hand-written tcgen05 GEMMs of ``csrc/tc_ffn_hw.cu`` (opt-in: ``--tc-ffn 1``).
 
 ``fused_ffn(x, w1, b1, w2, b2)`` = ``linear(gelu(linear(x, w1, b1)), w2, b2)`` with
 
@@ -49,11 +49,6 @@ def tc_launches() -> int:
     return int(mod.launches()) if mod is not None else 0
 
 
-# kernel configuration per op (index into ``_tc.variants()[op]``); chosen from tools/bert_ops_bench.py on a B200
-VARIANT = {"ffn_up": int(os.environ.get("DEAR_TC_UP_VARIANT", "0")),
-           "linear_bias": int(os.environ.get("DEAR_TC_DOWN_VARIANT", "0")),
-           "ffn_dgelu": int(os.environ.get("DEAR_TC_DGELU_VARIANT", "0"))}
-
 
 def _eligible(x: torch.Tensor, *ws: torch.Tensor) -> bool:
     if not (x.is_cuda and x.dtype == torch.bfloat16):
@@ -61,20 +56,15 @@ def _eligible(x: torch.Tensor, *ws: torch.Tensor) -> bool:
     return all(w.dtype == torch.bfloat16 and w.shape[-1] % 8 == 0 and w.shape[0] % 8 == 0 for w in ws if w.dim() == 2)
 
 
-# DEAR_TC_FFN_IMPL=hw routes the two fused GEMMs of `fused_ffn` to the hand-written kernels of csrc/tc_ffn_hw.cu
-# (two-warpgroup epilogue; experimental until they have run on hardware).  Default: the CUTLASS-collective variants.
-HANDWRITTEN = os.environ.get("DEAR_TC_FFN_IMPL", "").lower() == "hw"
-
-
 class _FusedFFN(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, w1, b1, w2, b2, tc_down):
+    def forward(ctx, x, w1, b1, w2, b2):
         tc = require_tc()
         x2 = x.reshape(-1, x.shape[-1])
         if not x2.is_contiguous():
             x2 = x2.contiguous()
-        h, z = tc.ffn_up_hw(x2, w1, b1) if HANDWRITTEN else tc.ffn_up(x2, w1, b1, VARIANT["ffn_up"])
-        y = tc.linear_bias(h, w2, b2, VARIANT["linear_bias"]) if tc_down else torch.addmm(b2, h, w2.t())
+        h, z = tc.ffn_up_hw(x2, w1, b1)                  # GEMM + bias + GELU; activation and pre-activation in one pass
+        y = torch.addmm(b2, h, w2.t())                   # plain GEMM: cuBLAS
         ctx.save_for_backward(x2, w1, w2, h, z)
         ctx.x_shape = x.shape
         return y.view(*x.shape[:-1], w2.shape[0])
@@ -86,30 +76,18 @@ class _FusedFFN(torch.autograd.Function):
         dy2 = dy.reshape(-1, dy.shape[-1])
         if not dy2.is_contiguous():
             dy2 = dy2.contiguous()
-        if HANDWRITTEN:     # W2 [hidden, inter] is read as it is stored (MN-major B operand): no transposed copy
-            dz = tc.ffn_dgelu_hw_nt(dy2, w2, z)
-        else:
-            dz = tc.ffn_dgelu(dy2, w2, z, VARIANT["ffn_dgelu"])              # (dy W2) * gelu'(z), one kernel
+        # (dy W2) * gelu'(z) in one kernel; W2 [hidden, inter] is read as it is stored (MN-major B operand)
+        dz = tc.ffn_dgelu_hw_nt(dy2, w2, z)
         dw2 = dy2.t().mm(h) if ctx.needs_input_grad[3] else None
         db2 = dy2.sum(0) if ctx.needs_input_grad[4] else None
         dw1 = dz.t().mm(x2) if ctx.needs_input_grad[1] else None
         db1 = dz.sum(0) if ctx.needs_input_grad[2] else None
         dx = dz.mm(w1).view(ctx.x_shape) if ctx.needs_input_grad[0] else None
-        return dx, dw1, db1, dw2, db2, None
+        return dx, dw1, db1, dw2, db2
 
 
-def fused_ffn(x, w1, b1, w2, b2, tc_down: bool = None):
+def fused_ffn(x, w1, b1, w2, b2):
     """``linear(gelu(linear(x, w1, b1)), w2, b2)``; tcgen05 kernels on CUDA bf16."""
     if _eligible(x, w1, w2):
-        if tc_down is None:
-            tc_down = os.environ.get("DEAR_TC_DOWN", "1") != "0"
-        return _FusedFFN.apply(x, w1, b1, w2, b2, bool(tc_down))
+        return _FusedFFN.apply(x, w1, b1, w2, b2)
     return F.linear(F.gelu(F.linear(x, w1, b1)), w2, b2)
-
-
-def linear_bias(x, w, b):
-    """``F.linear(x, w, b)`` on the tcgen05 mainloop (forward only; used by benchmarks/tests)."""
-    if _eligible(x, w):
-        x2 = x.reshape(-1, x.shape[-1]).contiguous()
-        return require_tc().linear_bias(x2, w, b, VARIANT["linear_bias"]).view(*x.shape[:-1], w.shape[0])
-    return F.linear(x, w, b)

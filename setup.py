@@ -1,7 +1,7 @@
 """Build the native runtime in-tree:  python setup.py build_ext --inplace
 
-Produces dear_pytorch_b200/_C.*.so (runtime, collectives, fused BN) and dear_pytorch_b200/_tc.*.so
-(tcgen05 GEMMs with fused epilogues) -- sm_100a only; no other architecture is built.
+Produces dear_pytorch_b200/_C.*.so (runtime, collectives, fused BN / LN kernels) and dear_pytorch_b200/_tc.*.so
+(hand-written tcgen05 GEMMs with fused epilogues) -- sm_100a only; no other architecture is built.
 The reference's counterpart is common/comm_core/setup.py:16-44 (NCCL+MPI); this
 extension links neither.
 """
@@ -33,28 +33,12 @@ ext = CUDAExtension(
 
 
 
-def cutlass_root():
-    """CuTe/CUTLASS header tree vendored in the image (flashinfer ships CUTLASS 4.x); DEAR_CUTLASS_DIR overrides."""
-    cand = [os.environ.get("DEAR_CUTLASS_DIR")]
-    import importlib.util
-    for pkg, sub in (("flashinfer", "data/cutlass"), ("tilelang", "3rdparty/cutlass")):
-        spec = importlib.util.find_spec(pkg)
-        if spec is not None and spec.submodule_search_locations:
-            cand.append(os.path.join(list(spec.submodule_search_locations)[0], sub))
-    for c in cand:
-        if c and os.path.isfile(os.path.join(c, "include", "cutlass", "gemm", "collective", "builders", "sm100_umma_builder.inl")):
-            return c
-    raise RuntimeError("no CUTLASS header tree with sm_100 collectives found (set DEAR_CUTLASS_DIR)")
-
-
-CUTLASS = cutlass_root()
 tc_ext = CUDAExtension(
     name="dear_pytorch_b200._tc",
-    # one translation unit per (operation, tile configuration): they compile in parallel
-    sources=[os.path.join(CSRC, "tc_bindings.cpp"), os.path.join(CSRC, "tc_ffn_hw.cu")] + sorted(
-        os.path.relpath(f, ROOT) for f in glob.glob(os.path.join(ROOT, CSRC, "tc_gemm_*.cu"))),
-    include_dirs=[os.path.join(ROOT, CSRC), os.path.join(CUTLASS, "include"), os.path.join(CUTLASS, "tools", "util", "include")],
-    extra_compile_args={"cxx": CXX_FLAGS, "nvcc": NVCC_FLAGS + ["--expt-extended-lambda", "-diag-suppress", "20012"]},
+    # hand-written tcgen05 / TMEM / TMA kernels (raw PTX; no CUTLASS headers needed)
+    sources=[os.path.join(CSRC, "tc_bindings.cpp"), os.path.join(CSRC, "tc_ffn_hw.cu")],
+    include_dirs=[os.path.join(ROOT, CSRC)],
+    extra_compile_args={"cxx": CXX_FLAGS, "nvcc": NVCC_FLAGS},
 )
 
 setup(

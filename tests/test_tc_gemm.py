@@ -1,9 +1,9 @@
-"""tcgen05 GEMMs with fused epilogues (csrc/tc_gemm*.cu) against plain PyTorch fp32 references."""
+"""Hand-written tcgen05 GEMMs with fused epilogues (csrc/tc_ffn_hw.cu) against plain PyTorch fp32 references."""
 import pytest
 import torch
 import torch.nn.functional as F
 
-from dear_pytorch_b200.ops.tc_gemm import fused_ffn, linear_bias, require_tc, tc_launches
+from dear_pytorch_b200.ops.tc_gemm import fused_ffn, require_tc, tc_launches
 
 
 def test_cpu_fallback_is_the_plain_formula():
@@ -11,11 +11,10 @@ def test_cpu_fallback_is_the_plain_formula():
     x = torch.randn(5, 7, 16, requires_grad=True)
     w1, b1, w2, b2 = torch.randn(32, 16), torch.randn(32), torch.randn(16, 32), torch.randn(16)
     torch.testing.assert_close(fused_ffn(x, w1, b1, w2, b2), F.linear(F.gelu(F.linear(x, w1, b1)), w2, b2))
-    torch.testing.assert_close(linear_bias(x, w1, b1), F.linear(x, w1, b1))
 
 
 def test_fast_gelu_math_matches_erf():
-    """The epilogue's Abramowitz-Stegun normal tail (csrc/tc_gemm.h: normal_tail) against erf, in fp32 on the host."""
+    """The epilogue's Abramowitz-Stegun normal tail (csrc/tc_ffn_hw.cu: gelu_fast / dgelu_fast) against erf, in fp32 on the host."""
     import math
     x = torch.linspace(-9.0, 9.0, 20001, dtype=torch.float64)
     ax = x.abs()
@@ -33,39 +32,6 @@ def test_fast_gelu_math_matches_erf():
 
 def _rand(shape, dev, scale=1.0):
     return (scale * torch.randn(shape, device=dev)).to(torch.bfloat16)
-
-
-@pytest.mark.gpu
-@pytest.mark.parametrize("M,K,N", [(2048, 1024, 4096), (256, 64, 128), (300, 72, 136), (1, 8, 8), (777, 1024, 1032)])
-def test_ffn_up_and_linear_bias(M, K, N):
-    tc = require_tc()
-    dev = torch.device("cuda:0")
-    torch.manual_seed(1)
-    x, w, b = _rand((M, K), dev), _rand((N, K), dev, K ** -0.5), _rand((N,), dev)
-    z_ref = x.float() @ w.float().t() + b.float()
-    n0 = tc_launches()
-    for v in range(len(tc.variants()["ffn_up"])):          # every compiled tile configuration
-        h, z = tc.ffn_up(x, w, b, v)
-        torch.testing.assert_close(z.float(), z_ref, rtol=1e-2, atol=1e-2, msg=lambda s: "ffn_up variant %d: %s" % (v, s))
-        torch.testing.assert_close(h.float(), F.gelu(z_ref), rtol=1e-2, atol=1e-2, msg=lambda s: "gelu variant %d: %s" % (v, s))
-    for v in range(len(tc.variants()["linear_bias"])):
-        y = tc.linear_bias(x, w, b, v)
-        torch.testing.assert_close(y.float(), z_ref, rtol=1e-2, atol=1e-2, msg=lambda s: "linear_bias variant %d: %s" % (v, s))
-    assert tc_launches() == n0 + len(tc.variants()["ffn_up"]) + len(tc.variants()["linear_bias"])
-
-
-@pytest.mark.gpu
-@pytest.mark.parametrize("M,K,N", [(2048, 1024, 4096), (256, 64, 128), (300, 72, 136), (5, 8, 16)])
-def test_ffn_dgelu(M, K, N):
-    tc = require_tc()
-    dev = torch.device("cuda:0")
-    torch.manual_seed(2)
-    dy, w, z = _rand((M, K), dev), _rand((K, N), dev, K ** -0.5), _rand((M, N), dev)
-    z32 = z.float().requires_grad_(True)
-    F.gelu(z32).backward(dy.float() @ w.float())
-    for v in range(len(tc.variants()["ffn_dgelu"])):
-        dz = tc.ffn_dgelu(dy, w, z, v)
-        torch.testing.assert_close(dz.float(), z32.grad, rtol=1.5e-2, atol=1.5e-2, msg=lambda s: "variant %d: %s" % (v, s))
 
 
 @pytest.mark.gpu
@@ -113,6 +79,32 @@ def test_handwritten_ffn_dgelu_mn_major_weight(M, K, N):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("cl", [1, 2, 4])
+@pytest.mark.parametrize("M,K,N", [(2048, 1024, 4096), (512, 192, 512), (1024, 64, 264)])
+def test_handwritten_kernels_with_multicast_clusters(M, K, N, cl):
+    """CL CTAs per cluster share the B tile: each loads 1/CL of it and multicasts (cp.async.bulk.tensor ...
+    .multicast::cluster), the MMA warp releases a stage in every CTA (tcgen05.commit ... multicast::cluster)."""
+    tc = require_tc()
+    dev = torch.device("cuda:0")
+    torch.manual_seed(4)
+    tc.set_ffn_hw_cluster(cl)
+    try:
+        x, w, b = _rand((M, K), dev), _rand((N, K), dev, K ** -0.5), _rand((N,), dev)
+        h, z = tc.ffn_up_hw(x, w, b)
+        z_ref = x.float() @ w.float().t() + b.float()
+        torch.testing.assert_close(z.float(), z_ref, rtol=1e-2, atol=1e-2)
+        torch.testing.assert_close(h.float(), F.gelu(z_ref), rtol=1e-2, atol=1e-2)
+        dy, w2, zz = _rand((M, K), dev), _rand((K, N), dev, K ** -0.5), _rand((M, N), dev)
+        dz = tc.ffn_dgelu_hw_nt(dy, w2, zz)
+        torch.cuda.synchronize()
+        z32 = zz.float().requires_grad_(True)
+        F.gelu(z32).backward(dy.float() @ w2.float())
+        torch.testing.assert_close(dz.float(), z32.grad, rtol=1.5e-2, atol=1.5e-2)
+    finally:
+        tc.set_ffn_hw_cluster(-1)
+
+
+@pytest.mark.gpu
 def test_fused_ffn_autograd_matches_eager_bf16():
     dev = torch.device("cuda:0")
     torch.manual_seed(3)
@@ -121,8 +113,8 @@ def test_fused_ffn_autograd_matches_eager_bf16():
     w1, b1 = _rand((I, H), dev, H ** -0.5).requires_grad_(True), _rand((I,), dev, 0.1).requires_grad_(True)
     w2, b2 = _rand((H, I), dev, I ** -0.5).requires_grad_(True), _rand((H,), dev, 0.1).requires_grad_(True)
     dy = _rand((4, M // 4, H), dev)
-    for down in (True, False):
-        y = fused_ffn(x, w1, b1, w2, b2, tc_down=down)
+    for _ in range(1):
+        y = fused_ffn(x, w1, b1, w2, b2)
         grads = torch.autograd.grad(y, (x, w1, b1, w2, b2), dy)
         ps = [t.detach().float().requires_grad_(True) for t in (x, w1, b1, w2, b2)]
         y_ref = F.linear(F.gelu(F.linear(ps[0], ps[1], ps[2])), ps[3], ps[4])
@@ -138,11 +130,11 @@ def test_tc_ffn_inside_cuda_graph():
     dev = torch.device("cuda:0")
     tc = require_tc()
     x, w, b = _rand((512, 256), dev), _rand((1024, 256), dev, 1 / 16), _rand((1024,), dev)
-    tc.ffn_up(x, w, b)
+    tc.ffn_up_hw(x, w, b)
     torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
-        h, z = tc.ffn_up(x, w, b)
+        h, z = tc.ffn_up_hw(x, w, b)
     x.copy_(_rand((512, 256), dev))
     g.replay(); torch.cuda.synchronize()
     torch.testing.assert_close(z.float(), x.float() @ w.float().t() + b.float(), rtol=1e-2, atol=1e-2)

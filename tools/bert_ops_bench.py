@@ -58,35 +58,31 @@ def _graph_time(fn, iters):
 
 
 def _gemm_section(r, tc, x, w1, b1, w2, b2, h, z, dy):
-    # 1. up projection + GELU (forward)
+    """The FFN's two fusable GEMMs: library path (cuBLAS + elementwise kernels) vs the hand-written tcgen05 kernels
+    (csrc/tc_ffn_hw.cu) with 1 / 2 / 4 CTAs per cluster sharing the B tile through TMA multicast."""
+    # 1. up projection + bias + GELU (forward)
     r["up_gelu_eager"] = graph_time(lambda: F.gelu(F.linear(x, w1, b1)))
-    for v, cfg in enumerate(tc.variants()["ffn_up"]):
-        r["up_gelu_tcgen05_v%d" % v] = graph_time(lambda: tc.ffn_up(x, w1, b1, v))
-    r["up_gelu_tcgen05"] = min(r["up_gelu_tcgen05_v%d" % v] for v in range(len(tc.variants()["ffn_up"])))
-    if hasattr(tc, "ffn_up_hw"):     # hand-written kernel with the two-warpgroup epilogue (csrc/tc_ffn_hw.cu)
-        r["up_gelu_tcgen05_handwritten"] = graph_time(lambda: tc.ffn_up_hw(x, w1, b1))
-    for v, cfg in enumerate(tc.variants()["linear_bias"]):
-        r["up_bias_only_tcgen05_v%d" % v] = graph_time(lambda: tc.linear_bias(x, w1, b1, v))
     r["up_gemm_only_cublas"] = graph_time(lambda: F.linear(x, w1, b1))
-    # 2. down projection (forward)
+    for cl in (1, 2, 4):
+        tc.set_ffn_hw_cluster(cl)
+        r["up_gelu_tcgen05_handwritten_cl%d" % cl] = graph_time(lambda: tc.ffn_up_hw(x, w1, b1))
+    tc.set_ffn_hw_cluster(-1)
+    r["up_gelu_tcgen05_handwritten"] = graph_time(lambda: tc.ffn_up_hw(x, w1, b1))
+    # 2. down projection (forward): plain GEMM, cuBLAS in both paths
     r["down_eager"] = graph_time(lambda: F.linear(h, w2, b2))
-    for v, cfg in enumerate(tc.variants()["linear_bias"]):
-        r["down_tcgen05_v%d" % v] = graph_time(lambda: tc.linear_bias(h, w2, b2, v))
-    r["down_tcgen05"] = min(r["down_tcgen05_v%d" % v] for v in range(len(tc.variants()["linear_bias"])))
     # 3. dgrad of the down projection + GELU backward
     def eager_dgelu():
         dh = dy.mm(w2)
         return torch.ops.aten.gelu_backward(dh, z)
     r["dgrad_dgelu_eager"] = graph_time(eager_dgelu)
-    for v, cfg in enumerate(tc.variants()["ffn_dgelu"]):
-        r["dgrad_dgelu_tcgen05_v%d" % v] = graph_time(lambda: tc.ffn_dgelu(dy, w2, z, v))
-    r["dgrad_dgelu_tcgen05"] = min(r["dgrad_dgelu_tcgen05_v%d" % v] for v in range(len(tc.variants()["ffn_dgelu"])))
-    if hasattr(tc, "ffn_dgelu_hw_nt"):
-        w2t = w2.t().contiguous()
-        r["dgrad_dgelu_tcgen05_handwritten_kmajor_needs_transpose"] = graph_time(lambda: tc.ffn_dgelu_hw(dy, w2t, z))
-        r["dgrad_dgelu_tcgen05_handwritten"] = graph_time(lambda: tc.ffn_dgelu_hw_nt(dy, w2, z))
     r["dgrad_gemm_only_cublas"] = graph_time(lambda: dy.mm(w2))
-
+    for cl in (1, 2, 4):
+        tc.set_ffn_hw_cluster(cl)
+        r["dgrad_dgelu_tcgen05_handwritten_cl%d" % cl] = graph_time(lambda: tc.ffn_dgelu_hw_nt(dy, w2, z))
+    tc.set_ffn_hw_cluster(-1)
+    r["dgrad_dgelu_tcgen05_handwritten"] = graph_time(lambda: tc.ffn_dgelu_hw_nt(dy, w2, z))
+    w2t = w2.t().contiguous()
+    r["dgrad_dgelu_tcgen05_handwritten_kmajor_needs_transpose"] = graph_time(lambda: tc.ffn_dgelu_hw(dy, w2t, z))
 
 
 def main():
@@ -115,7 +111,7 @@ def main():
     gamma = torch.ones(H, device=dev, dtype=bf)
     beta = torch.zeros(H, device=dev, dtype=bf)
     flops_up = 2.0 * M * H * I
-    out = {"shape": {"tokens": M, "hidden": H, "inter": I}, "variants": tc.variants(), "us": {}}
+    out = {"shape": {"tokens": M, "hidden": H, "inter": I}, "us": {}}
     r = out["us"]
 
     if "gemm" in sections:
@@ -128,13 +124,12 @@ def main():
         y = F.linear(F.gelu(F.linear(xs, ps[0], ps[1])), ps[2], ps[3])
         return torch.autograd.grad(y, [xs] + ps, dy)
 
-    def ffn_fused(down):
-        y = fused_ffn(xs, ps[0], ps[1], ps[2], ps[3], tc_down=down)
+    def ffn_fused():
+        y = fused_ffn(xs, ps[0], ps[1], ps[2], ps[3])
         return torch.autograd.grad(y, [xs] + ps, dy)
     if "ffn" in sections:
         r["ffn_fwd_bwd_eager"] = graph_time(ffn_eager)
-        r["ffn_fwd_bwd_tcgen05"] = graph_time(lambda: ffn_fused(True))
-        r["ffn_fwd_bwd_tcgen05_cublas_down"] = graph_time(lambda: ffn_fused(False))
+        r["ffn_fwd_bwd_tcgen05_handwritten"] = graph_time(ffn_fused)
 
     # 5. dropout + add + LayerNorm, forward + backward
     av = x.clone().requires_grad_(True)

@@ -8,7 +8,7 @@ echo "=== FFN op micro-benchmark"; timeout 300 python tools/bert_ops_bench.py --
 B="timeout 300 python bench.py --no-e2e"
 echo "=== bert 1 GPU default / hand-written FFN"
 $B --model bert --steps 30 --warmup 8 2>&1 | grep -E '"metric"|rror' | cut -c1-200
-DEAR_TC_FFN_IMPL=hw DEAR_TC_DOWN=0 $B --model bert --steps 30 --warmup 8 --tc-ffn 1 2>&1 | grep -E '"metric"|rror' | cut -c1-200
+$B --model bert --steps 30 --warmup 8 --tc-ffn 1 2>&1 | grep -E '"metric"|rror' | cut -c1-200
 echo "=== bert 1 GPU without direct wgrad"
 DEAR_DIRECT_WGRAD=0 $B --model bert --steps 30 --warmup 8 2>&1 | grep -E '"metric"|rror' | cut -c1-200
 echo "=== vgg16 1 GPU graph"

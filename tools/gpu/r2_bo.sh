@@ -3,7 +3,7 @@
 #   gpurun --gpus N -- 'bash tools/gpu/r2_bo.sh N'
 N=${1:-2}
 mkdir -p gpurun_out
-exec > >(tee gpurun_out/bo_tuner_bert_base_p$N.log) 2>&1
+exec > >(tee -a gpurun_out/bo_tuner_bert_base_p$N.log) 2>&1
 export DEAR_TIMEOUT_S=180
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 ARGS="benchmarks/bert_benchmark.py --model bert_base --batch-size 64 --sentence-len 64 --dtype bf16"
