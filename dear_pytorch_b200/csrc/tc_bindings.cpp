@@ -30,6 +30,6 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("ffn_dgelu_hw_nt", &dear_tc::ffn_dgelu_hw_nt, py::arg("dy"), py::arg("w"), py::arg("z"),
         "dZ = (dY W) * gelu'(Z) with W [K, N] as nn.Linear stores it (MN-major B operand, no transposed copy)");
   m.def("set_ffn_hw_cluster", &dear_tc::set_ffn_hw_cluster, py::arg("cl"),
-        "CTAs per cluster sharing the B tile through TMA multicast: -1 = largest of 4/2/1 dividing the tile rows, or forced");
+        "CTAs per cluster sharing the B tile through TMA multicast: -1 = default (1); 1 / 2 / 4 forced (must divide the tile rows)");
   m.def("launches", &dear_tc::launches);
 }

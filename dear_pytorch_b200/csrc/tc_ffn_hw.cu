@@ -21,8 +21,9 @@
 //               "accumulator empty" so the MMA warp can start tile i+2 while tile i drains
 //
 // STATUS: validated on B200 (tests/test_tc_gemm.py::test_handwritten_*, fp32 oracle; 1/2/4-CTA multicast clusters, K-major
-// and MN-major B).  Measured (profiles/r2/): up+GELU 27.3 us and dgrad x GELU' 27.9 us (on the weight as stored) against
-// 25.4 / 29.3 us for cuBLAS + elementwise kernels; multicast clusters buy ~9 %.  ncu (prof_tc_ffn_hw_cl1_summary.md): tensor
+// and MN-major B).  Measured (profiles/r2/bert_ops_bench_r2_final.json): up+GELU 27.6 us and dgrad x GELU' 28.5 us (on the
+// weight as stored) against 25.3 / 29.5 us for cuBLAS + elementwise kernels; multicast clusters of 2 / 4 change nothing
+// (27.8 / 28.4 us): the operand traffic is not the limiter.  ncu (prof_tc_ffn_hw_cl1_summary.md): tensor
 // pipe 29 % active — two serialized ~10 us epilogues per CTA (256 tiles on 148 SMs), not the mainloop, set the pace.  The
 // kernel is opt-in (DEAR_TC_FFN_IMPL=hw); the default FFN stays cuBLAS + the fused bias/GELU kernels of ln_fused.cu.
 // Every mbarrier wait is bounded and traps instead of spinning forever.
@@ -511,7 +512,7 @@ static void launch_hw_cl(const at::Tensor& a, const at::Tensor& b, const __nv_bf
   count_launch();
 }
 
-static int g_force_cluster = -1;       // -1: pick by shape; 1 / 2 / 4: forced (benchmarks, tests)
+static int g_force_cluster = -1;       // -1: default (1 CTA per cluster); 1 / 2 / 4: forced (benchmarks, tests)
 void set_ffn_hw_cluster(int cl) { g_force_cluster = cl; }
 
 template <int MODE, bool BMN = false>
@@ -519,7 +520,9 @@ static void launch_hw(const at::Tensor& a, const at::Tensor& b, const __nv_bfloa
                       int M, int N, int K) {
   const int tiles_m = (M + hw::kTileM - 1) / hw::kTileM;
   // the CTAs of a cluster take vertically adjacent tiles: the cluster size must divide the number of tile rows
-  int cl = g_force_cluster > 0 ? g_force_cluster : 4;
+  // default 1: measured on B200 the epilogue, not the operand traffic, bounds the kernel, and clusters of 2 / 4 are within
+  // noise of / slightly behind single CTAs (27.6 / 27.8 / 28.4 us, profiles/r2/bert_ops_bench_r2_final.json)
+  int cl = g_force_cluster > 0 ? g_force_cluster : 1;
   while (cl > 1 && tiles_m % cl != 0) cl >>= 1;
   if (cl >= 4) launch_hw_cl<MODE, BMN, 4>(a, b, aux, out0, out1, M, N, K);
   else if (cl == 2) launch_hw_cl<MODE, BMN, 2>(a, b, aux, out0, out1, M, N, K);

@@ -208,9 +208,9 @@ def main():
     for k in list(r):
         r[k] = round(r[k], 2)
     if "gemm" in sections:
-        out["tflops"] = {"up_gelu_tcgen05": round(flops_up / r["up_gelu_tcgen05"] / 1e6, 1),
+        out["tflops"] = {"up_gelu_tcgen05_handwritten": round(flops_up / r["up_gelu_tcgen05_handwritten"] / 1e6, 1),
                          "up_gemm_only_cublas": round(flops_up / r["up_gemm_only_cublas"] / 1e6, 1),
-                         "dgrad_dgelu_tcgen05": round(flops_up / r["dgrad_dgelu_tcgen05"] / 1e6, 1),
+                         "dgrad_dgelu_tcgen05_handwritten": round(flops_up / r["dgrad_dgelu_tcgen05_handwritten"] / 1e6, 1),
                          "dgrad_gemm_only_cublas": round(flops_up / r["dgrad_gemm_only_cublas"] / 1e6, 1)}
     print(json.dumps(out, indent=1))
     if a.json:
