@@ -121,8 +121,7 @@ PIPE_ENV = {"DEAR_SPIN_TIMEOUT_S": "15", "DEAR_RS_ALGO": "pipe", "DEAR_PIPE_MIN_
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("dtype_name", ["fp32", "bf16"])
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world,dtype_name", [(2, "fp32"), (2, "bf16"), (4, "fp32")])
 def test_cuda_pipelined_reduce_scatter_matches_reference(world, dtype_name):
     """Kernel A, stripe-pipelined variant (csrc/rs_pipe.cu: pack warps + TMA bulk-copy pull ring + shared-memory
     reduce) forced onto the small test bucket with 64 KB stripes, so several stripes, partial chunks, segment tails,
@@ -138,18 +137,17 @@ def plan_worker(rank, world):
     import dear_pytorch_b200 as dear
     from dear_pytorch_b200 import ops
     C = ops.require_native()
-    bs = C.BucketSet(dear.communicator(), [world * 65536, world * 32 * 1024 * 1024], C.DT_F32, True)
-    return [bs.rs_plan(0), bs.rs_plan(1)]
+    bs = C.BucketSet(dear.communicator(), [world * 65536, world * 16 * 1024 * 1024, world * 32 * 1024 * 1024], C.DT_F32, True)
+    return [bs.rs_plan(0), bs.rs_plan(1), bs.rs_plan(2)]
 
 
 @pytest.mark.gpu
 def test_reduce_scatter_algorithm_is_picked_per_bucket_size():
-    env = {"DEAR_SPIN_TIMEOUT_S": "15"}
-    small, big = run_ranks(plan_worker, world=2, backend="b200", extra_env=env, timeout=300)[0]
+    env = {"DEAR_SPIN_TIMEOUT_S": "15", "DEAR_PIPE_MIN_MB": "200"}
+    small, mid, big = run_ranks(plan_worker, world=2, backend="b200", extra_env=env, timeout=300)[0]
     assert small.startswith("oneshot:grid=8:"), small       # 512 KB: latency-bound, few CTAs
-    assert big.startswith("oneshot:grid=128:"), big         # 256 MB: the pack phase wants the wide grid
-    small, big = run_ranks(plan_worker, world=2, backend="b200", extra_env=dict(env, DEAR_PIPE_MIN_MB="128"), timeout=300)[0]
-    assert small.startswith("oneshot") and big.startswith("pipe") and "stripes=16" in big, (small, big)
+    assert mid.startswith("oneshot:grid=128:"), mid         # 128 MB: the pack phase wants the wide grid
+    assert big.startswith("pipe") and "stripes=16" in big, big      # 256 MB >= DEAR_PIPE_MIN_MB: stripe-pipelined TMA pull
 
 
 def nvls_worker(rank, world, dtype_name):
