@@ -147,8 +147,15 @@ def mgs_groups(sizes: Sequence[int], tb: Sequence[float], world: int, density: f
 class _DistributedOptimizer(torch.optim.Optimizer):
     def __init__(self, params, named_parameters, compression=None, is_sparse=False, density=0.001,
                  seq_layernames=None, layerwise_times=None, norm_clip=None, threshold=0, fp16=False, mgwfbp=False,
-                 asc=False, mgs=False, rdma=False, alpha=None, beta=None, verbose=True, momentum_correction=False):
+                 asc=False, mgs=False, rdma=False, alpha=None, beta=None, verbose=True, momentum_correction=False,
+                 profiling=False):
         super(self.__class__, self).__init__(params)
+        # in-optimizer timers of the reference (wfbp/dopt.py:198-200,883-903; dead code there: the printer is a no-op):
+        # host-side seconds per group for compression, collective launch and gradient write-back
+        self._profiling = bool(profiling)
+        self._compression_timers: Dict[str, list] = {}
+        self._allreduce_timers: Dict[str, list] = {}
+        self._update_times: Dict[str, list] = {}
         if not runtime.is_initialized():
             runtime.init()
         self._rank, self._world, self._device = runtime.rank(), runtime.size(), runtime.device()
@@ -246,7 +253,22 @@ class _DistributedOptimizer(torch.optim.Optimizer):
                 return g.get("momentum", 0.0)
         return 0.0
 
+    def _tick(self, table, gi, t0):
+        if self._profiling:
+            import time
+            if self._cuda:
+                torch.cuda.synchronize(self._device)      # the reference's timers synchronise too (profiling mode only)
+            table.setdefault("group-%d" % gi, []).append(time.perf_counter() - t0)
+
+    def profiling_summary(self):
+        """Mean seconds per group: {"compression": {...}, "allreduce": {...}, "update": {...}} (profiling=True)."""
+        mean = lambda d: {k: sum(v) / len(v) for k, v in d.items() if v}
+        return {"compression": mean(self._compression_timers), "allreduce": mean(self._allreduce_timers),
+                "update": mean(self._update_times)}
+
     def _launch(self, gi):
+        import time
+        t_launch = time.perf_counter()
         buf = self._buffers[gi]
         ctx = torch.cuda.stream(self._stream) if self._cuda else None
         if self._cuda:
@@ -257,6 +279,7 @@ class _DistributedOptimizer(torch.optim.Optimizer):
                 name = "group-%d" % gi
                 _, idx, vals = self._compression.compress(buf, name, ratio=self._density)
                 k = idx.numel()
+                self._tick(self._compression_timers, gi, t_launch)
                 if self._gtopk:
                     # global top-k of the SUM in log2(P) pairwise rounds; every rank ends with the same k entries
                     from ..comm import Comm
@@ -279,6 +302,7 @@ class _DistributedOptimizer(torch.optim.Optimizer):
             else:
                 dist.all_reduce(buf, group=self._group)
                 self._launched[gi] = True
+            self._tick(self._allreduce_timers, gi, t_launch)
         finally:
             if self._cuda:
                 ctx.__exit__(None, None, None)
@@ -291,7 +315,9 @@ class _DistributedOptimizer(torch.optim.Optimizer):
                 self._launch(gi)
         if self._cuda:
             torch.cuda.current_stream(self._device).wait_stream(self._stream)
+        import time
         for gi, g in enumerate(self._groups):
+            t_up = time.perf_counter()
             buf = self._buffers[gi]
             res = self._launched.pop(gi)
             if self._sparse and res[0] == "gtopk":
@@ -311,6 +337,7 @@ class _DistributedOptimizer(torch.optim.Optimizer):
             if not self._sparse:
                 buf.zero_()          # a parameter that misses its gradient next iteration must contribute zeros
             self._arrived[gi] = 0
+            self._tick(self._update_times, gi, t_up)
         if self._norm_clip is not None:
             torch.nn.utils.clip_grad_norm_(self._params, self._norm_clip)
 
@@ -354,7 +381,7 @@ def DistributedOptimizer(optimizer, named_parameters=None, model: Optional[nn.Mo
                          is_sparse=False, density=0.001, seq_layernames=None, layerwise_times=None, norm_clip=None,
                          threshold=0, writer=None, gradient_path=None, fp16=False, mgwfbp=False, asc=False, mgs=False,
                          rdma=False, multi_job_scheduling=False, alpha=None, beta=None, verbose=True,
-                         momentum_correction=False, **ignored):
+                         momentum_correction=False, profiling=False, **ignored):
     """WFBP (``threshold=0``), threshold fusion, MG-WFBP (``mgwfbp=True``) or ASC (``asc=True``)."""
     if named_parameters is None:
         if model is None:
@@ -366,4 +393,4 @@ def DistributedOptimizer(optimizer, named_parameters=None, model: Optional[nn.Mo
     return cls(optimizer.param_groups, list(named_parameters), compression=compression, is_sparse=is_sparse,
                density=density, seq_layernames=seq_layernames, layerwise_times=layerwise_times, norm_clip=norm_clip,
                threshold=threshold, fp16=fp16, mgwfbp=mgwfbp, asc=asc, mgs=mgs, rdma=rdma, alpha=alpha, beta=beta,
-               verbose=verbose, momentum_correction=momentum_correction)
+               verbose=verbose, momentum_correction=momentum_correction, profiling=profiling)

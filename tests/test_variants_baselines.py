@@ -82,6 +82,25 @@ def test_variant_matches_sgd(kind):
             assert max(n for _, _, n in log) <= partition and any(i > 0 for _, i, _ in log)   # tensors were partitioned
 
 
+def test_wfbp_in_optimizer_timers():
+    def w(rank, world):
+        import dear_pytorch_b200 as dear
+        from dear_pytorch_b200.parallel.baselines import WFBPDistributedOptimizer
+        model = make_model()
+        opt = WFBPDistributedOptimizer(torch.optim.SGD(model.parameters(), lr=0.05), model=model, compression="topk",
+                                       is_sparse=True, density=0.25, threshold=600, profiling=True, verbose=False)
+        dear.broadcast_parameters(model.state_dict(), 0)
+        for t in range(2):
+            x, y = data(t, 8)
+            opt.zero_grad()
+            nn.functional.cross_entropy(model(x[rank * 4:(rank + 1) * 4]), y[rank * 4:(rank + 1) * 4]).backward()
+            opt.step()
+        return opt.profiling_summary()
+    out = run_ranks(w, world=2, backend="gloo")[0]
+    assert out["compression"] and set(out["compression"]) == set(out["allreduce"]) == set(out["update"])
+    assert all(v > 0 for v in out["allreduce"].values())
+
+
 def test_horovod_cycle_grouping():
     from dear_pytorch_b200.parallel.baselines import cycle_groups
     t = [0.0, 1.0, 4.9, 5.1, 6.0, 20.0]                    # ms since the first gradient
