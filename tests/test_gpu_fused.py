@@ -334,7 +334,7 @@ def test_broadcast_after_wrapping_updates_the_fp32_masters():
             assert torch.equal(a, b), "an lr=0 step moved the parameters: stale master shards were pushed"
 
 
-@pytest.mark.parametrize("dtype_name", ["fp32", "bf16"])
+@pytest.mark.parametrize("dtype_name", ["fp32"])     # (bf16 through the pipelined kernel: tests/test_kernels_direct.py)
 def test_engine_on_the_pipelined_reduce_scatter(dtype_name):
     """Whole engine (hooks, steal-mode pack tables, sharded update) with every bucket forced onto the stripe-pipelined
     Kernel A (csrc/rs_pipe.cu) and the all-gathers on their own stream."""
