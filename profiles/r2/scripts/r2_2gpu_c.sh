@@ -10,5 +10,5 @@ MASTER_PORT=29961 timeout 500 bash tools/ncu_multi_gpu.sh 2 rs_kernel gpurun_out
 MASTER_PORT=29962 timeout 500 bash tools/ncu_multi_gpu.sh 2 ag_kernel gpurun_out/prof_ag_kernel_p2 --sizes-mb 64
 ncu --query-metrics 2>/dev/null | grep -i -E "^nvl|nvlrx|nvltx" | head -40 > gpurun_out/nvlink_metric_names.txt
 echo "=== BO tuner, BERT-base, 2 GPUs"
-bash tools/gpu/r2_bo.sh 2 2>&1 | grep -E "===|optimal|Total|rror"
+bash profiles/r2/scripts/r2_bo.sh 2 2>&1 | grep -E "===|optimal|Total|rror"
 echo "=== done"

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Bayesian buffer-size tuner (dopt_rsag_bo) on BERT-base at N GPUs: 3 tuned runs + 3 runs at the 25 MB default.
-#   gpurun --gpus N -- 'bash tools/gpu/r2_bo.sh N'
+#   gpurun --gpus N -- 'bash profiles/r2/scripts/r2_bo.sh N'
 N=${1:-2}
 mkdir -p gpurun_out
 exec > >(tee -a gpurun_out/bo_tuner_bert_base_p$N.log) 2>&1
