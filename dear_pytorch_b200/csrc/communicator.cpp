@@ -841,12 +841,19 @@ void BucketSet::wait_rs(int g) {
 
 void BucketSet::wait_all() {
   if (!comm_->is_cuda()) return;
-  // each comm stream is ordered, so one fresh event per stream covers all buckets
-  DEAR_CUDA(cudaEventRecord(E(ev_fence_), S(stream_)));
-  DEAR_CUDA(cudaStreamWaitEvent(current_stream(comm_->options().device), E(ev_fence_), 0));
-  if (ag_stream_ != stream_) {
+  // each comm stream is ordered, so one fresh event per stream covers all buckets.  A capturing stream may only wait
+  // on streams of the same capture (and an eager one only on eager streams): a comm stream on the other side of that
+  // boundary has nothing this wait could be about — eager work precedes the capture, which TrainStep starts only
+  // after a full synchronisation.
+  const cudaStream_t cur = current_stream(comm_->options().device);
+  const bool cc = is_capturing(cur);
+  if (is_capturing(S(stream_)) == cc) {
+    DEAR_CUDA(cudaEventRecord(E(ev_fence_), S(stream_)));
+    DEAR_CUDA(cudaStreamWaitEvent(cur, E(ev_fence_), 0));
+  }
+  if (ag_stream_ != stream_ && is_capturing(S(ag_stream_)) == cc) {
     DEAR_CUDA(cudaEventRecord(E(ev_fence_ag_), S(ag_stream_)));
-    DEAR_CUDA(cudaStreamWaitEvent(current_stream(comm_->options().device), E(ev_fence_ag_), 0));
+    DEAR_CUDA(cudaStreamWaitEvent(cur, E(ev_fence_ag_), 0));
   }
 }
 
