@@ -117,6 +117,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def("reduce_scatter", &BucketSet::reduce_scatter, py::arg("bucket"), py::arg("pack") = true)
       .def("rs_plan", &BucketSet::rs_plan, py::arg("bucket"))
       .def("set_grad_scale", &BucketSet::set_grad_scale, py::arg("scale"))
+      .def("pack_pieces", &BucketSet::pack_pieces, py::arg("bucket"))
       .def("allgather_update", &BucketSet::allgather_update, py::arg("bucket"), py::arg("do_update") = true,
            py::arg("first_step") = false, py::arg("entry_barrier") = true, py::arg("zero_grad") = false)
       .def("fence_current_to_comm", &BucketSet::fence_current_to_comm)

@@ -406,7 +406,9 @@ BucketSet::BucketSet(std::shared_ptr<Communicator> comm, std::vector<int64_t> pa
     const int64_t shard_bytes = b.shard * static_cast<int64_t>(es);
     int algo = o.rs_algo;
     if (algo < 0) algo = (world > 1 && bytes >= o.pipe_min_bytes) ? RS_ALGO_PIPE : RS_ALGO_ONESHOT;
-    if (world == 1 || !comm_->is_cuda()) algo = RS_ALGO_ONESHOT;
+    // (the host emulation runs one algorithm; a FORCED pipe plan is still built there so that the stripe-major work
+    // list of set_pack can be tested without a GPU)
+    if (world == 1 || (!comm_->is_cuda() && o.rs_algo != RS_ALGO_PIPE)) algo = RS_ALGO_ONESHOT;
     if (algo == RS_ALGO_NVLS && !arena_->has_multicast()) algo = RS_ALGO_ONESHOT;
     b.rs_algo = algo;
     if (algo == RS_ALGO_PIPE) {
@@ -855,6 +857,15 @@ void BucketSet::wait_all() {
     DEAR_CUDA(cudaEventRecord(E(ev_fence_ag_), S(ag_stream_)));
     DEAR_CUDA(cudaStreamWaitEvent(cur, E(ev_fence_ag_), 0));
   }
+}
+
+std::vector<std::vector<int64_t>> BucketSet::pack_pieces(int g) const {
+  const auto& b = buckets_.at(g);
+  std::vector<std::vector<int64_t>> out;
+  for (const PackSeg& pc : b.pieces_host)
+    out.push_back({static_cast<int64_t>(reinterpret_cast<uintptr_t>(pc.src)), static_cast<int64_t>(pc.dst_off),
+                   static_cast<int64_t>(pc.nbytes), static_cast<int64_t>(pc.tile_begin), static_cast<int64_t>(pc.flags)});
+  return out;
 }
 
 std::string BucketSet::rs_plan(int g) const {

@@ -148,6 +148,8 @@ class BucketSet {
   void set_grad_scale(double s) { grad_scale_ = static_cast<float>(s); }
   // (algorithm, stripes, grid) chosen for bucket g at construction time: {"algo": "oneshot|pipe|nvls", ...}
   std::string rs_plan(int g) const;
+  // the pipelined kernel's work list of bucket g as rows (src, dst_off, nbytes, stripe, flags) — for tests / debugging
+  std::vector<std::vector<int64_t>> pack_pieces(int g) const;
   void allgather_update(int g, bool do_update, bool first_step, bool entry_barrier, bool zero_grad);
   void fence_current_to_comm();
   void wait_bucket(int g);

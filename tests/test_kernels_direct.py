@@ -256,3 +256,61 @@ def test_cuda_adam_kernel(world, dtype_name):
     outs = run_ranks(adam_worker, world=world, backend="b200", args=(True, dtype_name, 9),
                      extra_env={"DEAR_SPIN_TIMEOUT_S": "15"}, timeout=300)
     assert all(o == outs[0] for o in outs)
+
+
+def pieces_worker(rank, world):
+    """Host-side work list of the stripe-pipelined Kernel A (BucketSet::set_pack): forced onto the emulation backend."""
+    import dear_pytorch_b200 as dear
+    from dear_pytorch_b200 import ops
+    C = ops.require_native()
+    es, padded = 4, world * 160 * 1024           # 640 KB per shard at fp32
+    bs = C.BucketSet(dear.communicator(), [padded], C.DT_F32, True)
+    gs = torch.zeros(padded // world)
+    bs.set_shards(0, gs, None, None)
+    # segments with odd sizes, a gap, a zero-fill and an "already in place" one; the last one crosses several stripes
+    numels = [1000, 37, 50001, 8, 200000]
+    starts, off = [], 0
+    for n in numels:
+        off = (off + 63) // 64 * 64
+        starts.append(off)
+        off += n
+    assert off <= padded
+    srcs = [torch.randn(n) for n in numels]
+    ptrs = [t.data_ptr() for t in srcs]
+    ptrs[3] = 0                                   # in place: dropped from the list
+    flags = [0, C.SEG_ZERO_FILL, 0, 0, 0]
+    ptrs[1] = 0
+    bs.set_pack(0, ptrs, [s * es for s in starts], [n * es for n in numels], flags)
+    return bs.rs_plan(0), bs.pack_pieces(0), [s * es for s in starts], [n * es for n in numels], ptrs
+
+
+def test_pipelined_work_list_covers_the_pack_table_stripe_major():
+    env = {"DEAR_RS_ALGO": "pipe", "DEAR_STRIPE_MB": "0.25"}
+    plan, pieces, starts, nbytes, ptrs = run_ranks(pieces_worker, world=2, backend="emu", extra_env=env)[0]
+    assert plan.startswith("pipe"), plan
+    fields = dict(kv.split("=") for kv in plan.split(":")[1:])
+    nstripes, cs = int(fields["stripes"]), int(fields["stripe_bytes"])
+    SB = 160 * 1024 * 4
+    assert nstripes > 1 and cs % 32768 == 0 and nstripes * cs >= SB
+    # stripe-major order, bounded piece size, no piece crosses a stripe or shard boundary
+    assert [p[3] for p in pieces] == sorted(p[3] for p in pieces)
+    for src, dst, n, k, fl in pieces:
+        assert 0 < n <= 32768
+        in_shard = dst % SB
+        assert in_shard // cs == k and (in_shard + n - 1) // cs == k and (dst + n - 1) // SB == dst // SB
+    # exact cover of every listed segment (the in-place one is absent), with matching source offsets
+    covered = {}
+    for src, dst, n, k, fl in pieces:
+        for i, (s0, nb) in enumerate(zip(starts, nbytes)):
+            if s0 <= dst < s0 + nb:
+                assert dst + n <= s0 + nb
+                covered.setdefault(i, []).append((dst, n))
+                if fl & 1:
+                    assert i == 1
+                else:
+                    assert src == ptrs[i] + (dst - s0)
+    assert sorted(covered) == [0, 1, 2, 4]
+    for i, spans in covered.items():
+        spans.sort()
+        assert spans[0][0] == starts[i] and sum(n for _, n in spans) == nbytes[i]
+        assert all(a[0] + a[1] == b[0] for a, b in zip(spans, spans[1:]))
