@@ -746,6 +746,18 @@ void BucketSet::reduce_scatter(int g, bool pack) {
   p.dtype = dtype_;
   p.status = cuda ? status_word_device() : status_word_host();
   p.timeout_ns = comm_->timeout_ns();
+  if (b.rs_algo == RS_ALGO_PIPE) {
+    // stripe-pipelined variant: stripe-major work list instead of the segment table (device kernel and host emulation)
+    p.nstripes = b.nstripes;
+    p.stripe_bytes = b.stripe_bytes;
+    p.mc_grad = nullptr;
+    p.pieces = (pack && !b.pieces_host.empty()) ? (cuda ? table_dev : b.pieces_host.data()) : nullptr;
+    std::memcpy(p.piece_first, b.piece_first, sizeof(p.piece_first));
+    p.segs = nullptr;
+    p.nseg = 0;
+    p.ntiles = 0;
+    p.direct_out = 0;
+  }
   if (cuda) {
     DEAR_CUDA(cudaEventRecord(E(b.ev_in), current_stream(comm_->options().device)));
     DEAR_CUDA(cudaStreamWaitEvent(S(stream_), E(b.ev_in), 0));
@@ -755,12 +767,6 @@ void BucketSet::reduce_scatter(int g, bool pack) {
     if (ag_stream_ != stream_ && b.ag_pending && b.ag_done_captured == is_capturing(S(stream_)))
       DEAR_CUDA(cudaStreamWaitEvent(S(stream_), E(b.ag_done), 0));
     if (b.rs_algo == RS_ALGO_PIPE) {
-      p.nstripes = b.nstripes;
-      p.stripe_bytes = b.stripe_bytes;
-      p.mc_grad = nullptr;
-      p.pieces = (pack && !b.pieces_host.empty()) ? table_dev : nullptr;
-      std::memcpy(p.piece_first, b.piece_first, sizeof(p.piece_first));
-      p.segs = nullptr;
       launch_rs_pipe(p, b.rs_grid, S(stream_));
     } else {
       if (b.rs_algo != RS_ALGO_NVLS) p.mc_grad = nullptr;

@@ -9,6 +9,7 @@
 #include <c10/util/BFloat16.h>
 #include <c10/util/Half.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstring>
@@ -64,7 +65,38 @@ void rs_impl(const RSParams& p) {
   const uint32_t ch_done = bucket_channel(p.bucket, RS_DONE);
   uint32_t* epoch_p = p.ctrl + ch_ready;
   const uint32_t e = *epoch_p + 1;
+  const uint32_t e8 = e << 8;                    // RS_READY = (epoch << 8) | stripes published, like the device kernels
   wait_all(sig_local, ch_done, e - 1, p.world, p.timeout_ns, p.status, ST_TIMEOUT_RS_DONE);
+  const uint64_t off = uint64_t(p.rank) * p.shard_elems;
+  if (p.nstripes >= 1 && p.stripe_bytes > 0 && (p.pieces != nullptr || p.nstripes > 1)) {
+    // stripe-pipelined variant (rs_pipe.cu): stripe k of every shard is packed from the stripe-major work list and
+    // published; stripe k of my shard is reduced once every peer has published it
+    char* bucket = reinterpret_cast<char*>(p.grad.ptr[p.rank]);
+    for (uint32_t k = 0; k < p.nstripes; ++k) {
+      if (p.pieces != nullptr) {
+        for (uint32_t i = p.piece_first[k]; i < p.piece_first[k + 1]; ++i) {
+          const PackSeg& pc = p.pieces[i];
+          if (pc.flags & SEG_ZERO_FILL) std::memset(bucket + pc.dst_off, 0, pc.nbytes);
+          else if (pc.src != nullptr) std::memcpy(bucket + pc.dst_off, pc.src, pc.nbytes);
+        }
+      }
+      signal_all(p.sig, ch_ready, p.rank, p.world, e8 | (k + 1));
+    }
+    const uint64_t stripe_elems = p.stripe_bytes / sizeof(T);
+    for (uint32_t k = 0; k < p.nstripes; ++k) {
+      wait_all(sig_local, ch_ready, e8 | (k + 1), p.world, p.timeout_ns, p.status, ST_TIMEOUT_RS_READY);
+      const uint64_t lo = uint64_t(k) * stripe_elems;
+      const uint64_t hi = std::min<uint64_t>(p.shard_elems, lo + stripe_elems);
+      for (uint64_t i = lo; i < hi; ++i) {
+        float acc = 0.f;
+        for (int q = 0; q < p.world; ++q) acc += ld<T>(p.grad.ptr[q], off + i);   // fixed order
+        p.out[i] = acc * p.scale;
+      }
+    }
+    signal_all(p.sig, ch_done, p.rank, p.world, e);
+    *epoch_p = e;
+    return;
+  }
   const bool direct = p.world == 1 && sizeof(T) == 4 && p.direct_out;
   // pack (tile by tile, exactly like the device kernel)
   if (p.segs != nullptr) {
@@ -72,16 +104,15 @@ void rs_impl(const RSParams& p) {
     for (uint32_t tile = 0; tile < p.ntiles; ++tile) {
       const uint32_t si = find_pack_seg(p.segs, p.nseg, tile);
       const PackSeg& sg = p.segs[si];
-      const uint64_t off = uint64_t(tile - sg.tile_begin) * kPackTileBytes;
-      const uint64_t left = sg.nbytes - off;
+      const uint64_t off2 = uint64_t(tile - sg.tile_begin) * kPackTileBytes;
+      const uint64_t left = sg.nbytes - off2;
       const uint32_t nb = left < kPackTileBytes ? uint32_t(left) : kPackTileBytes;
-      if (sg.flags & SEG_ZERO_FILL) std::memset(bucket + sg.dst_off + off, 0, nb);
-      else if (sg.src != nullptr) std::memcpy(bucket + sg.dst_off + off, reinterpret_cast<const char*>(sg.src) + off, nb);
+      if (sg.flags & SEG_ZERO_FILL) std::memset(bucket + sg.dst_off + off2, 0, nb);
+      else if (sg.src != nullptr) std::memcpy(bucket + sg.dst_off + off2, reinterpret_cast<const char*>(sg.src) + off2, nb);
     }
   }
-  signal_all(p.sig, ch_ready, p.rank, p.world, e);
-  wait_all(sig_local, ch_ready, e, p.world, p.timeout_ns, p.status, ST_TIMEOUT_RS_READY);
-  const uint64_t off = uint64_t(p.rank) * p.shard_elems;
+  signal_all(p.sig, ch_ready, p.rank, p.world, e8 | kAllStripes);
+  wait_all(sig_local, ch_ready, e8 | kAllStripes, p.world, p.timeout_ns, p.status, ST_TIMEOUT_RS_READY);
   for (uint64_t i = 0; i < p.shard_elems && !direct; ++i) {
     float acc = 0.f;
     for (int q = 0; q < p.world; ++q) acc += ld<T>(p.grad.ptr[q], off + i);   // fixed order

@@ -98,6 +98,18 @@ def test_world_of_three_emu():
             torch.testing.assert_close(a, b, rtol=2e-5, atol=2e-6)
 
 
+def test_engine_on_the_emulated_pipelined_reduce_scatter():
+    """The whole engine with every bucket on the stripe-pipelined Kernel A variant (host emulation), 3 ranks."""
+    case = CASES[2]
+    ref = reference_run(case, 4, 3, 2)
+    env = {"DEAR_RS_ALGO": "pipe", "DEAR_STRIPE_MB": "0.03125"}
+    from _mp import run_ranks
+    for params, nb in run_ranks(dear_worker, world=3, backend="emu", args=(case, 4, 2, 0.001, None), extra_env=env):
+        assert nb > 1
+        for a, b in zip(params, ref):
+            torch.testing.assert_close(a, b, rtol=2e-5, atol=2e-6)
+
+
 def _direct_wgrad_worker(rank, world):
     import dear_pytorch_b200 as dear
     torch.manual_seed(0)

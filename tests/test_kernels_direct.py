@@ -108,6 +108,16 @@ def test_emulated_kernels_match_reference(world, dtype_name):
     assert all(o == outs[0] for o in outs)
 
 
+@pytest.mark.parametrize("dtype_name", ["fp32", "bf16"])
+@pytest.mark.parametrize("world", [2, 3])
+def test_emulated_pipelined_reduce_scatter_matches_reference(world, dtype_name):
+    """Host emulation of the stripe-pipelined Kernel A (emu.cpp mirrors rs_pipe.cu: stripe-major work list, one
+    RS_READY flag value per stripe): several stripes, segment tails, zero-fill and in-place segments."""
+    env = {"DEAR_RS_ALGO": "pipe", "DEAR_STRIPE_MB": "0.0625"}
+    outs = run_ranks(kernel_worker, world=world, backend="emu", args=(False, dtype_name, 5), extra_env=env)
+    assert all(o == outs[0] for o in outs)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("dtype_name", ["fp32", "bf16"])
 @pytest.mark.parametrize("world", [1, 2])
