@@ -1,11 +1,11 @@
 #!/usr/bin/env python
 """Launch the BERT-layer kernels of this repo a few times at the benchmark's shapes, for an ncu capture:
 
-    ncu --set full --clock-control none --import-source on -k regex:'device_kernel|ln_fwd_kernel|ln_bwd_kernel|bias_gelu_bwd' \
-        --launch-skip 12 --launch-count 6 -o gpurun_out/prof_bert_ops python tools/ncu_bert_ops.py
+    ncu --set full --clock-control none --import-source on -k regex:'ffn_hw_kernel|ln_fwd_kernel|ln_bwd_kernel|bias_gelu_bwd' \
+        --launch-skip 10 --launch-count 5 -o gpurun_out/prof_bert_ops python tools/ncu_bert_ops.py
 
-Per iteration, in order: tcgen05 GEMM+bias, GEMM+bias+GELU, dgrad GEMM x GELU', fused dropout+add+LN forward,
-its backward, bias+GELU backward (6 kernels matching the regex above)."""
+Per iteration, in order: hand-written tcgen05 GEMM+bias+GELU, dgrad GEMM x GELU' (MN-major weight), fused dropout+add+LN
+forward, its backward, bias+GELU backward (5 kernels matching the regex above)."""
 import os
 import sys
 
@@ -29,11 +29,9 @@ def main():
     dy = torch.randn(M, H, device=dev).to(bf)
     dh = torch.randn(M, I, device=dev).to(bf)
     g, b = torch.ones(H, device=dev, dtype=bf), torch.zeros(H, device=dev, dtype=bf)
-    up_v = int(os.environ.get("DEAR_TC_UP_VARIANT", "4"))
     for _ in range(3):
-        tc.linear_bias(x, w1, b1, 0)
-        tc.ffn_up(x, w1, b1, up_v)
-        tc.ffn_dgelu(dy, w2, z, 0)
+        tc.ffn_up_hw(x, w1, b1)
+        tc.ffn_dgelu_hw_nt(dy, w2, z)
         y, s, mean, rstd, mask = C.ln_forward(x, dy, g, b, 0.1, True, 1e-12, g)
         C.ln_backward(dy, s, mean, rstd, g, mask, 0.1, True)
         C.bias_gelu_backward(dh, z, b1)
