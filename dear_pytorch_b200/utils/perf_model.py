@@ -125,15 +125,21 @@ def fit_alpha_beta(rows, key: str):
 
 def fused_kernel_model(path: str = None) -> dict:
     """alpha-beta of Kernel A / Kernel B and of NCCL's reduce-scatter / all-gather on this machine, from the committed
-    8-GPU sweep (``profiles/kernel_bench_p8_ipc.json``) — the counterpart of the reference's hard-coded per-cluster
+    8-GPU sweep (``profiles/r2/kernel_bench_p8_r2_auto.json``, else ``profiles/kernel_bench_p8_ipc.json``) — the counterpart of the reference's hard-coded per-cluster
     tables (``dear/utils.py:62-104``), which MG-WFBP style planners (baselines/wfbp.py: mgwfbp_groups) consume."""
     root = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    path = path or os.path.join(root, "profiles", "kernel_bench_p8_ipc.json")
+    if path is None:
+        # newest committed 8-GPU sweep first (round 2: one-shot kernel on the per-size grid plan), round-1 sweep as fallback
+        for cand in (("profiles", "r2", "kernel_bench_p8_r2_auto.json"), ("profiles", "kernel_bench_p8_ipc.json")):
+            path = os.path.join(root, *cand)
+            if os.path.isfile(path):
+                break
     with open(path) as f:
         rows = json.load(f)["rows"]
     out = {"world": rows[0].get("world"), "source": os.path.basename(path)}
-    for name, key in (("reduce_scatter", "rs_us"), ("allgather_update", "ag_sgd_us"), ("nccl_reduce_scatter", "nccl_rs_us"),
-                      ("nccl_all_gather", "nccl_ag_us")):
+    for name, key in (("reduce_scatter", "rs_us"), ("reduce_scatter_in_place", "rs_nopack_us"), ("allgather_update", "ag_sgd_us"),
+                      ("nccl_reduce_scatter", "nccl_rs_us"), ("nccl_all_gather", "nccl_ag_us"),
+                      ("nccl_copy_reduce_scatter_div", "nccl_copy_rs_div_us")):
         try:
             out[name] = fit_alpha_beta(rows, key)
         except (ValueError, ZeroDivisionError):
