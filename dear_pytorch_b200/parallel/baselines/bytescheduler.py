@@ -191,6 +191,13 @@ class _ByteSchedulerOptimizer(torch.optim.Optimizer):
 
     def _finish(self, p):
         """Wait for p's chunks (stream-wise on GPU), average, and — lazy mode — apply p's update."""
+        if not self._launched_all[p].is_set() and self._thread is None:
+            # a forward pass between backward() and step() (no scheduler thread yet): schedule what is queued now,
+            # in the same deterministic priority / credit order the thread would use
+            self._drain()
+            if self._thread_error is not None:
+                err, self._thread_error = self._thread_error, None
+                raise err
         self._launched_all[p].wait()
         if self._thread_error is not None:
             self._join()
