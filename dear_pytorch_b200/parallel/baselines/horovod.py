@@ -31,6 +31,13 @@ import torch.nn as nn
 from ... import runtime
 
 
+def _flat_dense(t: torch.Tensor) -> torch.Tensor:
+    """1-D alias of a dense tensor's storage (channels-last gradients are dense but not contiguous)."""
+    if t.is_contiguous():
+        return t.view(-1)
+    return torch.as_strided(t, (t.numel(),), (1,), t.storage_offset())
+
+
 def cycle_groups(arrival_ms: List[float], nbytes: List[int], cycle_time_ms: float, fusion_threshold_bytes: int) -> List[List[int]]:
     """Group tensor indices (given in readiness order with their ready times) the way Horovod's cycle does:
     a new group starts at every cycle boundary and whenever the fusion buffer would overflow.  A tensor larger
@@ -110,7 +117,7 @@ class _HorovodOptimizer(torch.optim.Optimizer):
             if self._t_first is None:
                 self._t_first = now
             self._arrival.append((n, (now - self._t_first) * 1e3))
-            self._allreduce(p.grad)
+            self._allreduce(_flat_dense(p.grad))
             self._launched[n] = True
             return
         gi = self._group_of[n]
@@ -165,7 +172,7 @@ class _HorovodOptimizer(torch.optim.Optimizer):
         if self.groups is None:
             for p in self._params:                              # gradients that never arrived this step
                 if self._names[p] not in self._launched and p.grad is not None:
-                    self._allreduce(p.grad)
+                    self._allreduce(_flat_dense(p.grad))
             if self._cuda:
                 torch.cuda.current_stream(self._device).wait_stream(self._stream)
             for p in self._params:
