@@ -57,6 +57,10 @@ def parse_args(argv=None):
                     help="sgd = the reference's benchmark optimizer; adam/adamw use the sharded Adam epilogue of Kernel B")
     ap.add_argument("--backend", default=None)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--upload-delay-us", type=float, default=None,
+                    help="end-to-end run: spin this long on the copy stream before each prefetch upload so the PCIe DMA does "
+                         "not start at the step boundary, where the rotated step runs the update + all-gather kernels "
+                         "(utils/data.py). Default: 1500 with --overlap-update 1, else 0")
     args = ap.parse_args(argv)
     is_bert = args.model in BERT_MODELS
     if args.batch_size is None:
@@ -250,7 +254,8 @@ def run_dear(args):
             while True:
                 yield wl.host_batches[i % len(wl.host_batches)]
                 i += 1
-        feed = PinnedPrefetcher(endless(), device)
+        delay_us = args.upload_delay_us if args.upload_delay_us is not None else (1500.0 if (cuda and step.overlap_update) else 0.0)
+        feed = PinnedPrefetcher(endless(), device, upload_delay_us=delay_us)
         loss_host = torch.zeros(args.steps + args.warmup + 4, dtype=torch.float32)
         if cuda:
             loss_host = loss_host.pin_memory()
@@ -268,7 +273,7 @@ def run_dear(args):
         ms_e2e = _max_over_ranks(ms_e2e, world)
         e2e = {"value": round(B * world * args.steps / (ms_e2e / 1e3), 2), "unit": wl.unit,
                "h2d_bytes_per_step": int(wl.h2d_bytes), "d2h_bytes_per_step": 4,
-               "ms_per_step": round(ms_e2e / args.steps, 4)}
+               "ms_per_step": round(ms_e2e / args.steps, 4), "upload_delay_us": delay_us}
     clocks = None
     if sampler is not None:
         sampler.stop()

@@ -11,6 +11,14 @@ goes through.
 
 Contract: a batch returned by ``next()`` stays valid until the work enqueued before the *next*
 ``next()`` call has consumed it (the usual "one batch per training step" loop).
+
+``upload_delay_us``: a ring slot frees when the previous step's work retires, so every upload starts exactly at a
+step boundary.  With the rotated training step (``TrainStep(overlap_update=True)``) the first thing a step runs is
+Kernel B — the sharded update + all-gather, whose flag traffic uses system-scope release/acquire — and the PCIe DMA
+landing at the same moment measurably stretches it (end-to-end minus device-resident step time: 0.01 ms with the
+natural body, 0.18 ms with the rotated one at 1 GPU; profiles/bench_default_1gpu*.json).  A short spin on the COPY
+stream in front of each upload moves the DMA into the forward pass, where the natural body already shows it is
+free.  The copy still completes one and a half steps before its batch is consumed.
 """
 from __future__ import annotations
 
@@ -47,7 +55,8 @@ class SyntheticImages:
 class PinnedPrefetcher:
     """Wrap an iterable of pinned host batches; yields device batches, ``depth`` copies ahead."""
 
-    def __init__(self, host_batches: Iterable[Sequence[torch.Tensor]], device: torch.device, depth: int = 2):
+    def __init__(self, host_batches: Iterable[Sequence[torch.Tensor]], device: torch.device, depth: int = 2,
+                 upload_delay_us: float = 0.0):
         self.it = iter(host_batches)
         self.device = torch.device(device)
         self.cuda = self.device.type == "cuda"
@@ -58,8 +67,12 @@ class PinnedPrefetcher:
         self.free_ev = [None] * self.nslots       # compute-stream event: slot may be overwritten
         self._slot = 0
         self._last = None
+        self._delay_cycles = 0
         if self.cuda:
             self.stream = torch.cuda.Stream(device=self.device)
+            if upload_delay_us > 0 and hasattr(torch.cuda, "_sleep"):
+                khz = getattr(torch.cuda.get_device_properties(self.device), "clock_rate", 0) or 1_900_000
+                self._delay_cycles = int(upload_delay_us * khz / 1e3)
         for _ in range(self.depth):
             self._enqueue()
 
@@ -85,6 +98,8 @@ class PinnedPrefetcher:
         with torch.cuda.stream(self.stream):
             if self.free_ev[slot] is not None:
                 self.stream.wait_event(self.free_ev[slot])      # the consumer is done with this slot
+                if self._delay_cycles:
+                    torch.cuda._sleep(self._delay_cycles)       # one spinning thread on the copy stream
             for b, h in zip(bufs, host):
                 b.copy_(h, non_blocking=True)
             ev = torch.cuda.Event()

@@ -1,5 +1,6 @@
 """Small utilities: clock-sample summary (bench.py's `clocks` field), the input prefetcher on a CPU device, the ncu
 launch-list aggregator."""
+import pytest
 import os
 import subprocess
 import sys
@@ -55,3 +56,28 @@ def test_ncu_launch_list_aggregation():
         os.unlink(path)
     assert "total 30.0 us over 3 launches" in out
     assert "dear::rs_kernel" in out and "n=   2" in out and "80.0%" in out
+
+
+def test_prefetcher_upload_delay_is_a_noop_on_cpu():
+    from dear_pytorch_b200.utils.data import PinnedPrefetcher, SyntheticImages
+    src = SyntheticImages(2, image_size=8, num_classes=5, n_buffers=2)
+    feed = PinnedPrefetcher(iter(src), torch.device("cpu"), upload_delay_us=1500.0)
+    assert feed._delay_cycles == 0
+    x, y = next(feed)
+    assert torch.equal(x, src.batches[0][0])
+
+
+@pytest.mark.gpu
+def test_prefetcher_with_delayed_uploads_delivers_every_batch_intact():
+    """The copy-stream spin in front of each upload (bench.py's end-to-end run with the rotated step) must not change
+    what arrives: 12 batches through a 3-slot ring, each checked against its host original after a consumer kernel."""
+    from dear_pytorch_b200.utils.data import PinnedPrefetcher
+    dev = torch.device("cuda:0")
+    host = [torch.full((1 << 20,), float(i)).pin_memory() for i in range(12)]
+    feed = PinnedPrefetcher(iter([(h,) for h in host]), dev, upload_delay_us=300.0)
+    assert feed._delay_cycles > 0
+    sums = []
+    for (x,) in feed:
+        sums.append(x.double().sum())              # consumer work on the current stream
+    torch.cuda.synchronize()
+    assert [float(s) for s in sums] == [float(i) * (1 << 20) for i in range(12)]
