@@ -60,7 +60,7 @@ def parse_args(argv=None):
     ap.add_argument("--upload-delay-us", type=float, default=None,
                     help="end-to-end run: spin this long on the copy stream before each prefetch upload so the PCIe DMA does "
                          "not start at the step boundary, where the rotated step runs the update + all-gather kernels "
-                         "(utils/data.py). Default: 1500 with --overlap-update 1, else 0")
+                         "(utils/data.py). Default: 2000 with --overlap-update 1, else 0")
     args = ap.parse_args(argv)
     is_bert = args.model in BERT_MODELS
     if args.batch_size is None:
@@ -254,7 +254,7 @@ def run_dear(args):
             while True:
                 yield wl.host_batches[i % len(wl.host_batches)]
                 i += 1
-        delay_us = args.upload_delay_us if args.upload_delay_us is not None else (1500.0 if (cuda and step.overlap_update) else 0.0)
+        delay_us = args.upload_delay_us if args.upload_delay_us is not None else (2000.0 if (cuda and step.overlap_update) else 0.0)
         feed = PinnedPrefetcher(endless(), device, upload_delay_us=delay_us)
         loss_host = torch.zeros(args.steps + args.warmup + 4, dtype=torch.float32)
         if cuda:
