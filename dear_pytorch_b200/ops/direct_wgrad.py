@@ -29,19 +29,33 @@ import torch.nn.functional as F
 class _LinearDirectWgrad(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias):
-        ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
-        return F.linear(x, weight, bias)
+        ctx.grad_dtypes = (x.dtype, weight.dtype, bias.dtype if bias is not None else None)
+        dev = x.device.type
+        if torch.is_autocast_enabled(dev) and x.is_floating_point():
+            # autocast is off inside backward: keep the operands in the dtype the forward GEMM actually used, and
+            # hand gradients back in the dtype of the tensors autograd knows (fp32 master weights under bf16 autocast)
+            dt = torch.get_autocast_dtype(dev)
+            x, weight = x.to(dt), weight.to(dt)
+            bias = bias.to(dt) if bias is not None else None
+            with torch.autocast(dev, enabled=False):
+                y = F.linear(x, weight, bias)
+        else:
+            y = F.linear(x, weight, bias)
+        ctx.save_for_backward(x, weight)
+        return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, weight = ctx.saved_tensors
+        x, weight = ctx.saved_tensors            # as the GEMM saw them (cast copies under autocast)
+        xdt, wdt, bdt = ctx.grad_dtypes
         dy2 = dy.reshape(-1, dy.shape[-1])
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = dy2.mm(weight).view(x.shape)
+            dx = dy2.mm(weight).view(x.shape).to(xdt)
         if ctx.needs_input_grad[1]:
             x2 = x.reshape(-1, x.shape[-1])
+            # under autocast `weight` is a temporary copy without the engine's attributes: ordinary gradient there
             view = getattr(weight, "_dear_grad_view", None)
             if (view is not None and not getattr(weight, "_dear_grad_written", False) and view.dtype == dy2.dtype
                     and x2.dtype == dy2.dtype and view.is_contiguous() and view.device == dy2.device):
@@ -51,9 +65,9 @@ class _LinearDirectWgrad(torch.autograd.Function):
                 # ordinary tensors that autograd sums into it.  The engine clears the mark at step().
                 weight._dear_grad_written = True
             else:
-                dw = dy2.t().mm(x2)
+                dw = dy2.t().mm(x2).to(wdt)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = dy2.sum(0)
+            db = dy2.sum(0).to(bdt)
         return dx, dw, db
 
 

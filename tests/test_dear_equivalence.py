@@ -139,3 +139,50 @@ def test_linear_weight_gradients_are_written_into_the_bucket_by_the_gemm():
             assert aliased and src == 0, (name, aliased, src)
         else:
             assert not aliased and src != 0, (name, aliased, src)
+
+
+def test_direct_wgrad_linear_under_autocast_matches_the_stock_module():
+    """autocast is off inside backward: the patched Linear must keep the operands the forward GEMM used and return
+    gradients in the dtype of the fp32 masters (it used to fail with a bf16 x fp32 matmul)."""
+    import copy
+    from dear_pytorch_b200.ops import direct_wgrad
+    torch.manual_seed(0)
+    m = nn.Sequential(nn.Linear(8, 16), nn.ReLU(), nn.Linear(16, 4, bias=False))
+    r = copy.deepcopy(m)
+    assert direct_wgrad.install(m) == 2
+    x = torch.randn(5, 3, 8, requires_grad=True)
+    xr = x.detach().clone().requires_grad_(True)
+    for mod, inp in ((m, x), (r, xr)):
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            y = mod(inp)
+        assert y.dtype == torch.bfloat16
+        y.float().pow(2).sum().backward()
+    for a, b in zip(m.parameters(), r.parameters()):
+        assert a.grad.dtype == torch.float32
+        torch.testing.assert_close(a.grad, b.grad, rtol=0, atol=0)
+    torch.testing.assert_close(x.grad, xr.grad, rtol=0, atol=0)
+
+
+def _autocast_engine_worker(rank, world):
+    import dear_pytorch_b200 as dear
+    torch.manual_seed(0)
+    model = nn.Sequential(nn.Linear(16, 32), nn.ReLU(), nn.Linear(32, 4))
+    opt = dear.DistributedOptimizer(torch.optim.SGD(model.parameters(), lr=0.1), model, threshold=0.0001, verbose=False)
+    g = torch.Generator().manual_seed(5)
+    for _ in range(3):
+        x = torch.randn(8, 16, generator=g)
+        opt.zero_grad()
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            loss = model(x).float().pow(2).mean()
+        loss.backward()
+        opt.step()
+    opt.synchronize()
+    return [p.detach().clone() for p in model.parameters()]
+
+
+def test_engine_with_autocast_forward_direct_wgrad_on_and_off():
+    from _mp import run_ranks
+    on = run_ranks(_autocast_engine_worker, world=2, backend="emu")[0]
+    off = run_ranks(_autocast_engine_worker, world=2, backend="emu", extra_env={"DEAR_DIRECT_WGRAD": "0"})[0]
+    for a, b in zip(on, off):
+        torch.testing.assert_close(a, b, rtol=0, atol=0)
