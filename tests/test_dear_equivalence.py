@@ -186,3 +186,20 @@ def test_engine_with_autocast_forward_direct_wgrad_on_and_off():
     off = run_ranks(_autocast_engine_worker, world=2, backend="emu", extra_env={"DEAR_DIRECT_WGRAD": "0"})[0]
     for a, b in zip(on, off):
         torch.testing.assert_close(a, b, rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("algo", ["oneshot", "pipe"])
+def test_world_of_eight_emu(algo):
+    """The headline world size on the host emulation of the kernels (same flag protocol, same tables), both
+    reduce-scatter variants: 8 ranks x 1 sample == one process on the 8-sample batch."""
+    case = CASES[2]
+    ref = reference_run(case, 3, 8, 1)
+    env = {"DEAR_RS_ALGO": algo, "DEAR_STRIPE_MB": "0.0078125"} if algo == "pipe" else None
+    outs = run_ranks(dear_worker, world=8, backend="emu", args=(case, 3, 1, 0.001, None), timeout=300, extra_env=env)
+    for params, nb in outs:
+        assert nb > 1
+        for a, b in zip(params, ref):
+            torch.testing.assert_close(a, b, rtol=2e-5, atol=2e-6)
+    for other in outs[1:]:
+        for a, b in zip(outs[0][0], other[0]):
+            assert torch.equal(a, b)
