@@ -71,8 +71,13 @@ class PinnedPrefetcher:
         if self.cuda:
             self.stream = torch.cuda.Stream(device=self.device)
             if upload_delay_us > 0 and hasattr(torch.cuda, "_sleep"):
-                khz = getattr(torch.cuda.get_device_properties(self.device), "clock_rate", 0) or 1_900_000
-                self._delay_cycles = int(upload_delay_us * khz / 1e3)
+                try:
+                    khz = getattr(torch.cuda.get_device_properties(self.device), "clock_rate", 0) or 1_900_000
+                    with torch.cuda.stream(self.stream):
+                        torch.cuda._sleep(1)                    # private torch API: probe it once, fall back to no delay
+                    self._delay_cycles = int(upload_delay_us * khz / 1e3)
+                except Exception:                               # pragma: no cover
+                    self._delay_cycles = 0
         for _ in range(self.depth):
             self._enqueue()
 
