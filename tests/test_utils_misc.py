@@ -75,7 +75,8 @@ def test_prefetcher_with_delayed_uploads_delivers_every_batch_intact():
     dev = torch.device("cuda:0")
     host = [torch.full((1 << 20,), float(i)).pin_memory() for i in range(12)]
     feed = PinnedPrefetcher(iter([(h,) for h in host]), dev, upload_delay_us=300.0)
-    assert feed._delay_cycles > 0
+    if feed._delay_cycles == 0:
+        pytest.skip("torch.cuda._sleep is not usable in this build: the prefetcher runs without the delay")
     sums = []
     for (x,) in feed:
         sums.append(x.double().sum())              # consumer work on the current stream
