@@ -73,7 +73,7 @@ def parse_args(argv=None):
         # Rotated body wherever it measured faster: with peers (it hides the all-gather tail: ResNet-50 13.51 -> 13.38 ms
         # at 8 GPUs) and for BERT even on one GPU (+3.5 %).  A CNN on ONE GPU has no communication to hide and the
         # natural body is faster there (ResNet-50 13.25 vs 13.27 ms resident, 13.26 vs 13.44 ms end to end; VGG-16
-        # 21.12 vs 21.45 ms), so that case keeps it.
+        # 21.12 (round-1 eager loop, natural order) vs 21.45 ms), so that case keeps it.
         args.overlap_update = 1 if (is_bert or int(os.environ.get("WORLD_SIZE", "1")) > 1) else 0
     return args
 
