@@ -65,8 +65,8 @@ def main(argv=None):
     def sync(host=True):
         if hasattr(optimizer, "_dear"):
             optimizer._dear.synchronize(host=host)
-        elif method == "dear-rb":
-            optimizer.synchronize()
+        elif method in ("dear-rb", "bytescheduler") and hasattr(optimizer, "synchronize"):
+            optimizer.synchronize()            # bytescheduler: deferred per-layer updates + its scheduler thread
         if cuda and host:
             torch.cuda.synchronize()
 

@@ -22,6 +22,7 @@ def main(argv=None):
                                  formatter_class=argparse.ArgumentDefaultsHelpFormatter)
     ap.add_argument("--model", type=str, default="resnet50")
     ap.add_argument("--channels-last", type=int, default=1)
+    ap.add_argument("--image-size", type=int, default=None, help="default: the model's native resolution (224; 299 for inception)")
     ap.add_argument("--fused-bn", type=int, default=1, help="fused BatchNorm(+add)+ReLU kernels (resnet*/densenet*)")
     common.add_common_args(ap)
     args = ap.parse_args(argv)
@@ -38,7 +39,7 @@ def main(argv=None):
         for m in model.modules():
             if isinstance(m, torch.nn.modules.batchnorm._BatchNorm):
                 m.float()
-    size = input_size(args.model)
+    size = args.image_size or input_size(args.model)
     data = torch.randn(args.batch_size, 3, size, size, device=device)
     if dtype == "bf16":
         data = data.to(torch.bfloat16)
@@ -62,8 +63,8 @@ def main(argv=None):
     def sync(host=True):
         if hasattr(optimizer, "_dear"):
             optimizer._dear.synchronize(host=host)
-        elif hasattr(optimizer, "synchronize") and method == "dear-rb":
-            optimizer.synchronize()
+        elif hasattr(optimizer, "synchronize") and method in ("dear-rb", "bytescheduler"):
+            optimizer.synchronize()            # bytescheduler: deferred per-layer updates + its scheduler thread
         if cuda and host:
             torch.cuda.synchronize()
 

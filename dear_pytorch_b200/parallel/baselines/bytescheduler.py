@@ -65,7 +65,12 @@ class _ByteSchedulerOptimizer(torch.optim.Optimizer):
         if not runtime.is_initialized():
             runtime.init()
         self._rank, self._world, self._device = runtime.rank(), runtime.size(), runtime.device()
+        # the scheduler thread issues collectives while the main thread runs user code: they travel on a communicator
+        # of their own (as ByteScheduler's / Horovod's do), so a user collective on the default group — a metric
+        # all-reduce, a barrier — can never interleave differently on two ranks
         self._pg = runtime.group()
+        if self._world > 1 and self._pg is None:
+            self._pg = dist.new_group(ranks=list(range(self._world)))
         self.partition = int(partition if partition is not None else os.environ.get("BYTESCHEDULER_PARTITION", 4000000))
         self.credit = int(credit if credit is not None else os.environ.get("BYTESCHEDULER_CREDIT", 16000000))
         self._cuda = self._device.type == "cuda"
