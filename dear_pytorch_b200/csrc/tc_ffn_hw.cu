@@ -25,7 +25,7 @@
 // weight as stored) against 25.3 / 29.5 us for cuBLAS + elementwise kernels; multicast clusters of 2 / 4 change nothing
 // (27.8 / 28.4 us): the operand traffic is not the limiter.  ncu (prof_tc_ffn_hw_cl1_summary.md): tensor
 // pipe 29 % active — two serialized ~10 us epilogues per CTA (256 tiles on 148 SMs), not the mainloop, set the pace.  The
-// kernel is opt-in (DEAR_TC_FFN_IMPL=hw); the default FFN stays cuBLAS + the fused bias/GELU kernels of ln_fused.cu.
+// kernel is opt-in (bench.py --tc-ffn 1, BertConfig tc_ffn); the default FFN stays cuBLAS + the fused bias/GELU kernels of ln_fused.cu.
 // Every mbarrier wait is bounded and traps instead of spinning forever.
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/cuda/CUDAGuard.h>
