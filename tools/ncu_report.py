@@ -44,4 +44,6 @@ def main(rep, out):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) != 3:
+        sys.exit("usage: tools/ncu_report.py <report.ncu-rep> <summary.md>")
     main(sys.argv[1], sys.argv[2])
