@@ -178,3 +178,16 @@ class Comm:
 
     def barrier(self) -> None:
         runtime.barrier()
+
+    # ---- life cycle (reference Communicator::destroy / reload, communicator.cpp:43-83) ---------------
+    def destroy(self) -> None:
+        """Drain this communicator's streams.  The reference tears its NCCL communicators down here; the symmetric-memory
+        runtime is shared by every ``Comm`` of the process and is released by ``dear.shutdown()``, so nothing is freed."""
+        self.synchronize()
+        self._destroyed = True
+
+    def reload(self) -> None:
+        """Counterpart of ``destroy``: make the communicator usable again (re-attaches to the runtime, which
+        ``dear.shutdown()`` + ``dear.init()`` may have re-created in between)."""
+        self.__init__(self.nstreams)
+        self._destroyed = False

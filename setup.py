@@ -8,7 +8,7 @@ extension links neither.
 import glob
 import os
 
-from setuptools import setup
+from setuptools import find_packages, setup
 from torch.utils.cpp_extension import BuildExtension, CUDAExtension
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -44,7 +44,8 @@ tc_ext = CUDAExtension(
 setup(
     name="dear_pytorch_b200",
     version="0.1.0",
-    packages=["dear_pytorch_b200"],
+    packages=find_packages(include=["dear_pytorch_b200", "dear_pytorch_b200.*", "dear"]),
+    py_modules=["comm_core"],               # drop-in for the reference's native module name
     ext_modules=[ext, tc_ext],
     cmdclass={"build_ext": BuildExtension.with_options(use_ninja=True)},
 )

@@ -228,3 +228,52 @@ def streams_worker(rank, world):
 def test_comm_nstreams_grows_the_native_communicator():
     outs = run_ranks(streams_worker, world=2, backend="emu")
     assert outs[0] == outs[1] == [3.0, 5.0, 7.0]
+
+
+def comm_core_worker(rank, world):
+    """The flows of the reference's smoke script (common/comm_core/tests/test_comm.py:11-65) through the drop-in
+    ``comm_core`` module — with assertions instead of prints."""
+    import comm_core
+    comm_core.init()
+    assert (comm_core.rank(), comm_core.size()) == (rank, world)
+    dev = __import__("dear_pytorch_b200").device()
+    comm = comm_core.Communicator(1)
+    total = float(sum(range(1, world + 1)))
+    # allreduce()
+    t = torch.full((2, 2), float(rank + 1), device=dev)
+    comm.allReduce(t)
+    comm.synchronize()
+    assert torch.equal(t.cpu(), torch.full((2, 2), total))
+    # reducescatter(): RS -> AG reproduces the all-reduce
+    send = torch.arange(16.0, device=dev) * (rank + 1)
+    results = torch.zeros_like(send)
+    recv = send.new_zeros(send.numel() // world)
+    comm.reduceScatter(send, recv)
+    comm.allGather(recv, results)
+    comm.allReduce(send)
+    comm.synchronize()
+    assert float((results - send).norm()) == 0.0
+    # decoupleallreduce(): an odd size through the reduce + broadcast composition
+    a = torch.arange(17.0, device=dev) * (rank + 1)
+    b = a.clone()
+    comm.allReduce(a)
+    comm.allReduceRB(b)
+    comm.synchronize()
+    assert float((a - b).norm()) == 0.0
+    # bcast()
+    x = torch.full((2,), 10.0 if rank == 0 else -1.0, device=dev)
+    comm.bcast(x, 0)
+    comm.synchronize()
+    assert x.tolist() == [10.0, 10.0]
+    comm_core.barriar()
+    comm.destroy()
+    comm.reload()
+    comm.allReduce(x)
+    comm.synchronize()
+    assert x.tolist() == [10.0 * world] * 2
+    return True
+
+
+@pytest.mark.parametrize("backend", ["emu", "gloo"])
+def test_comm_core_drop_in_module(backend):
+    assert all(run_ranks(comm_core_worker, world=2, backend=backend))
