@@ -49,6 +49,14 @@ def add_common_args(ap):
     ap.add_argument("--optimizer", choices=["sgd", "adam", "adamw"], default="sgd",
                     help="adam/adamw: sharded Adam fused into the all-gather kernel (dear methods only)")
     ap.add_argument("--graph", type=int, default=0, help="capture the whole iteration in a CUDA graph")
+    # flags of the reference's baseline drivers (horovod/, bytescheduler/, pytorch-ddp/ imagenet_benchmark.py)
+    ap.add_argument("--fp16-allreduce", action="store_true", default=False,
+                    help="--method horovod: fused buffers travel as fp16 (hvd.Compression.fp16)")
+    ap.add_argument("--use-adasum", action="store_true", default=False,
+                    help="--method horovod: Adasum reduction (hvd.Adasum); like the reference, the lr is then not scaled by "
+                         "the number of ranks")
+    ap.add_argument("--use-zero", type=int, default=0, help="--method ddp: ZeroRedundancyOptimizer (= --method ddp-zero)")
+    ap.add_argument("--partition", type=int, default=None, help="--method bytescheduler: partition size in elements")
     ap.add_argument("--json", type=str, default=None, help="also write the result as JSON to this file")
     return ap
 
@@ -58,6 +66,8 @@ def resolve_method(args):
         return "mgwfbp"
     if args.asc:
         return "asc"
+    if args.method == "ddp" and getattr(args, "use_zero", 0):
+        return "ddp-zero"
     return args.method
 
 
@@ -110,9 +120,12 @@ def wrap_optimizer(method, args, model, optimizer, profile_fn=None):
             seq_layernames=seq, layerwise_times=times, threshold=thr, mgwfbp=(method == "mgwfbp"), asc=(method == "asc"),
             rdma=args.rdma, momentum_correction=getattr(args, "momentum_correction", False))
     if method == "horovod":
-        return model, baselines.HorovodOptimizer(optimizer, model)        # HOROVOD_FUSION_THRESHOLD / HOROVOD_CYCLE_TIME
+        return model, baselines.HorovodOptimizer(                         # HOROVOD_FUSION_THRESHOLD / HOROVOD_CYCLE_TIME
+            optimizer, model, fp16_allreduce=getattr(args, "fp16_allreduce", False),
+            op="adasum" if getattr(args, "use_adasum", False) else "average")
     if method == "bytescheduler":
-        return model, baselines.ByteSchedulerOptimizer(optimizer, model)  # BYTESCHEDULER_PARTITION / BYTESCHEDULER_CREDIT
+        return model, baselines.ByteSchedulerOptimizer(                   # BYTESCHEDULER_PARTITION / BYTESCHEDULER_CREDIT
+            optimizer, model, partition=getattr(args, "partition", None))
     if method in ("ddp", "ddp-zero"):
         kw = dict(optimizer.defaults)
         ddp_model, opt = baselines.wrap_ddp(model, type(optimizer), {k: v for k, v in kw.items() if k in

@@ -47,7 +47,8 @@ def main(argv=None):
         data = data.contiguous(memory_format=torch.channels_last)
     target = torch.randint(0, 1000, (args.batch_size,), device=device)
 
-    optimizer = common.make_base_optimizer(args, model.parameters(), 0.01 * dear.size())
+    lr_scaler = 1 if args.use_adasum else dear.size()          # reference: dear/imagenet_benchmark.py:85
+    optimizer = common.make_base_optimizer(args, model.parameters(), 0.01 * lr_scaler)
 
     def profile():
         from dear_pytorch_b200.utils.profiling import benchmark

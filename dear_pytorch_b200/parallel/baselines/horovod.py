@@ -12,6 +12,11 @@ dear/imagenet_benchmark.py:10-12) are exactly the ones this baseline implements:
   * **response cache** — the negotiation result is cached, so after the first iterations the same tensors are
     fused into the same groups without another negotiation round.
 
+  * **compression / reduction op** — ``hvd.Compression.fp16`` (``--fp16-allreduce`` of horovod/imagenet_benchmark.py:19,81:
+    the fused buffer travels as fp16) and ``op=hvd.Adasum`` (``--use-adasum``, :39,87: scale-insensitive pairwise
+    combination  a (+) b = (1 - a.b / 2|a|^2) a + (1 - a.b / 2|b|^2) b  applied per tensor over log2(P) recursive-doubling
+    rounds; no averaging afterwards and no lr scaling by the world size).
+
 Emulation: during ``negotiation_steps`` warm-up iterations every gradient is all-reduced on its own (cold cache) while
 rank 0 records *when* each gradient hook fired relative to the first one.  Rank 0 then cuts that timeline into
 ``cycle_time_ms`` windows, splits windows at the fusion threshold, and broadcasts the grouping — the cached
@@ -36,6 +41,20 @@ def _flat_dense(t: torch.Tensor) -> torch.Tensor:
     if t.is_contiguous():
         return t.view(-1)
     return torch.as_strided(t, (t.numel(),), (1,), t.storage_offset())
+
+
+def adasum_combine(a: torch.Tensor, b: torch.Tensor, bounds: List[tuple]) -> torch.Tensor:
+    """Adasum of two flat buffers, tensor by tensor (``bounds`` = [(start, end), ...] of the member tensors): orthogonal
+    gradients add, parallel ones average.  Symmetric in (a, b), so both partners of an exchange compute the same bits."""
+    out = torch.empty_like(a)
+    for s0, s1 in bounds:
+        x, y = a[s0:s1], b[s0:s1]
+        xf, yf = x.float(), y.float()
+        dot, xx, yy = torch.dot(xf, yf), torch.dot(xf, xf), torch.dot(yf, yf)
+        cx = torch.where(xx > 0, 1.0 - dot / (2.0 * xx), torch.ones_like(dot))
+        cy = torch.where(yy > 0, 1.0 - dot / (2.0 * yy), torch.ones_like(dot))
+        out[s0:s1] = (cx * xf + cy * yf).to(a.dtype)
+    return out
 
 
 def cycle_groups(arrival_ms: List[float], nbytes: List[int], cycle_time_ms: float, fusion_threshold_bytes: int) -> List[List[int]]:
@@ -65,12 +84,17 @@ def cycle_groups(arrival_ms: List[float], nbytes: List[int], cycle_time_ms: floa
 
 class _HorovodOptimizer(torch.optim.Optimizer):
     def __init__(self, params, named_parameters, fusion_threshold_mb=None, cycle_time_ms=None, negotiation_steps=2,
-                 verbose=True):
+                 verbose=True, fp16_allreduce=False, op="average"):
         super(self.__class__, self).__init__(params)
+        if op not in ("average", "adasum"):
+            raise ValueError("op must be 'average' or 'adasum'")
+        self._fp16, self._adasum = bool(fp16_allreduce), op == "adasum"
         if not runtime.is_initialized():
             runtime.init()
         self._rank, self._world, self._device = runtime.rank(), runtime.size(), runtime.device()
         self._pg = runtime.group()
+        if self._adasum and self._world & (self._world - 1):
+            raise ValueError("Adasum needs a power-of-two number of ranks (recursive doubling), got %d" % self._world)
         if fusion_threshold_mb is None:
             fusion_threshold_mb = float(os.environ.get("HOROVOD_FUSION_THRESHOLD", 64 * 1024 * 1024)) / (1024 * 1024)
         if cycle_time_ms is None:
@@ -91,6 +115,7 @@ class _HorovodOptimizer(torch.optim.Optimizer):
         self._group_of: Dict[str, int] = {}
         self._buffers: Dict[int, torch.Tensor] = {}
         self._offsets: Dict[str, tuple] = {}
+        self._bounds: Dict[int, List[tuple]] = {}
         self._arrived: List[int] = []
         self._launched: Dict[object, object] = {}
         self._verbose = verbose and self._rank == 0
@@ -100,13 +125,34 @@ class _HorovodOptimizer(torch.optim.Optimizer):
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
 
     # ---- comm stream helpers ------------------------------------------------------------------
-    def _allreduce(self, tensor):
+    def _reduce(self, tensor, bounds):
+        """Sum (or Adasum) of ``tensor`` over the ranks, in place; ``bounds`` = member tensors of a fused buffer."""
+        wire = tensor.to(torch.float16) if (self._fp16 and tensor.dtype == torch.float32) else tensor
+        if not self._adasum:
+            dist.all_reduce(wire, group=self._pg)
+        else:
+            d = 1
+            while d < self._world:
+                peer = self._rank ^ d
+                other = torch.empty_like(wire)
+                reqs = dist.batch_isend_irecv([dist.P2POp(dist.isend, wire, peer, group=self._pg),
+                                               dist.P2POp(dist.irecv, other, peer, group=self._pg)])
+                for r in reqs:
+                    r.wait()
+                lo, hi = (wire, other) if self._rank < peer else (other, wire)
+                wire = adasum_combine(lo, hi, bounds)
+                d *= 2
+        if wire is not tensor:
+            tensor.copy_(wire)
+
+    def _allreduce(self, tensor, bounds=None):
+        bounds = bounds if bounds is not None else [(0, tensor.numel())]
         if self._cuda:
             self._stream.wait_stream(torch.cuda.current_stream(self._device))
             with torch.cuda.stream(self._stream):
-                dist.all_reduce(tensor, group=self._pg)
+                self._reduce(tensor, bounds)
         else:
-            dist.all_reduce(tensor, group=self._pg)
+            self._reduce(tensor, bounds)
 
     # ---- backward hook ------------------------------------------------------------------------
     def _on_grad(self, p):
@@ -125,7 +171,7 @@ class _HorovodOptimizer(torch.optim.Optimizer):
         self._buffers[gi][a:b].copy_(p.grad.reshape(-1))
         self._arrived[gi] += 1
         if self._arrived[gi] == len(self.groups[gi]):
-            self._allreduce(self._buffers[gi])
+            self._allreduce(self._buffers[gi], self._bounds[gi])
             self._launched[gi] = True
 
     def _build_groups(self):
@@ -159,6 +205,7 @@ class _HorovodOptimizer(torch.optim.Optimizer):
                 self._offsets[n] = (off, off + k)
                 off += k
             self._buffers[gi] = torch.zeros(off, device=self._device, dtype=self._by_name[g[0]].dtype)
+            self._bounds[gi] = [self._offsets[n] for n in g]
         self._arrived = [0] * len(groups)
         if self._verbose:
             sizes = [sum(self._by_name[n].numel() * self._by_name[n].element_size() for n in g) / 2 ** 20 for g in groups]
@@ -175,20 +222,22 @@ class _HorovodOptimizer(torch.optim.Optimizer):
                     self._allreduce(_flat_dense(p.grad))
             if self._cuda:
                 torch.cuda.current_stream(self._device).wait_stream(self._stream)
-            for p in self._params:
-                if p.grad is not None:
-                    p.grad.div_(self._world)
+            if not self._adasum:
+                for p in self._params:
+                    if p.grad is not None:
+                        p.grad.div_(self._world)
             self._launched.clear()
             self._t_first = None
             return
         for gi in range(len(self.groups)):
             if gi not in self._launched:
-                self._allreduce(self._buffers[gi])
+                self._allreduce(self._buffers[gi], self._bounds[gi])
         if self._cuda:
             torch.cuda.current_stream(self._device).wait_stream(self._stream)
         for gi, g in enumerate(self.groups):
             buf = self._buffers[gi]
-            buf.div_(self._world)
+            if not self._adasum:
+                buf.div_(self._world)
             for n in g:
                 a, b = self._offsets[n]
                 p = self._by_name[n]
@@ -213,12 +262,15 @@ class _HorovodOptimizer(torch.optim.Optimizer):
 
 
 def HorovodOptimizer(optimizer, model: Optional[nn.Module] = None, named_parameters=None, fusion_threshold_mb=None,
-                     cycle_time_ms=None, negotiation_steps: int = 2, verbose: bool = True, **ignored):
-    """``hvd.DistributedOptimizer`` look-alike with cycle-time tensor fusion (see the module docstring)."""
+                     cycle_time_ms=None, negotiation_steps: int = 2, verbose: bool = True, fp16_allreduce: bool = False,
+                     op: str = "average", **ignored):
+    """``hvd.DistributedOptimizer`` look-alike with cycle-time tensor fusion (see the module docstring).
+    ``fp16_allreduce=True`` = ``compression=hvd.Compression.fp16``; ``op="adasum"`` = ``op=hvd.Adasum``."""
     if named_parameters is None:
         if model is None:
             raise ValueError("pass model or named_parameters")
         named_parameters = model.named_parameters()
     cls = type(optimizer.__class__.__name__, (optimizer.__class__,), dict(_HorovodOptimizer.__dict__))
     return cls(optimizer.param_groups, list(named_parameters), fusion_threshold_mb=fusion_threshold_mb,
-               cycle_time_ms=cycle_time_ms, negotiation_steps=negotiation_steps, verbose=verbose)
+               cycle_time_ms=cycle_time_ms, negotiation_steps=negotiation_steps, verbose=verbose,
+               fp16_allreduce=fp16_allreduce, op=op)

@@ -33,6 +33,9 @@ IMAGENET_CASES = [
     ("dear", ("--exclude-parts", "allgather")),
     ("wfbp", ()), ("mgwfbp", ()), ("asc", ()), ("ddp", ()), ("ddp-zero", ()), ("horovod", ()), ("bytescheduler", ()),
     ("single", ()),
+    # flags of the reference's baseline drivers (horovod/, pytorch-ddp/, bytescheduler/ imagenet_benchmark.py)
+    ("horovod", ("--fp16-allreduce",)), ("horovod", ("--use-adasum",)), ("ddp", ("--use-zero", "1")),
+    ("bytescheduler", ("--partition", "100000")),
     ("wfbp", ("--compressor", "eftopk", "--density", "0.01")),
     ("wfbp", ("--compressor", "gtopk", "--density", "0.01", "--momentum", "0.9", "--momentum-correction")),
 ]

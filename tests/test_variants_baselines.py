@@ -170,3 +170,75 @@ def test_sparse_topk_allgather_path_runs():
     outs = run_ranks(sparse_worker, world=2, backend="gloo")
     assert all(torch.equal(a, b) for a, b in zip(outs[0][1], outs[1][1]))
     assert outs[0][0][-1] < outs[0][0][0] + 0.5
+
+
+def _adasum_worker(rank, world, mode):
+    import dear_pytorch_b200 as dear
+    from dear_pytorch_b200.parallel.baselines import HorovodOptimizer
+    torch.manual_seed(0)
+    model = nn.Linear(world, 1, bias=False)
+    with torch.no_grad():
+        model.weight.zero_()
+    opt = HorovodOptimizer(torch.optim.SGD(model.parameters(), lr=1.0), model, op="adasum", negotiation_steps=1, verbose=False)
+    moved = []
+    for step in range(3):                                   # step 0: cold cache (per tensor), later: fused buffer
+        opt.zero_grad()
+        if mode == "orthogonal":
+            x = torch.zeros(1, world); x[0, rank] = 1.0      # d loss / d w = e_rank on every rank
+        else:
+            x = torch.ones(1, world) * 0.5                   # the same gradient on every rank
+        before = model.weight.detach().clone()
+        model(x).sum().backward()
+        opt.step()
+        moved.append((before - model.weight.detach()).flatten())
+    return moved
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_horovod_adasum_adds_orthogonal_and_averages_parallel_gradients(world):
+    for mode, expect in (("orthogonal", torch.ones(world)), ("parallel", torch.full((world,), 0.5))):
+        outs = run_ranks(_adasum_worker, world=world, backend="gloo", args=(mode,))
+        for moved in outs:
+            for m in moved:
+                torch.testing.assert_close(m, expect)
+        assert all(torch.equal(a, b) for a, b in zip(outs[0], outs[-1]))       # bit-identical on every rank
+
+
+def test_adasum_needs_a_power_of_two():
+    def w(rank, world):
+        from dear_pytorch_b200.parallel.baselines import HorovodOptimizer
+        m = nn.Linear(2, 2)
+        try:
+            HorovodOptimizer(torch.optim.SGD(m.parameters(), lr=1.0), m, op="adasum", verbose=False)
+        except ValueError as e:
+            return str(e)
+        return None
+    assert all("power-of-two" in (o or "") for o in run_ranks(w, world=3, backend="gloo"))
+
+
+def _fp16_worker(rank, world):
+    import dear_pytorch_b200 as dear
+    from dear_pytorch_b200.parallel.baselines import HorovodOptimizer
+    model = make_model()
+    model.eval()
+    opt = HorovodOptimizer(torch.optim.SGD(model.parameters(), lr=0.05, **CASE), model, fp16_allreduce=True,
+                           cycle_time_ms=0.2, fusion_threshold_mb=0.002, negotiation_steps=2, verbose=False)
+    dear.broadcast_parameters(model.state_dict(), 0)
+    for t in range(4):
+        x, y = data(t, world * 3)
+        opt.zero_grad()
+        nn.functional.cross_entropy(model(x[rank * 3:(rank + 1) * 3]), y[rank * 3:(rank + 1) * 3]).backward()
+        opt.step()
+    return [p.detach().clone() for p in model.parameters()]
+
+
+def test_horovod_fp16_allreduce_tracks_fp32_within_half_precision():
+    ref = reference_run(CASE, 4, 2, 3)
+    outs = run_ranks(_fp16_worker, world=2, backend="gloo")
+    exact = True
+    for a, b in zip(outs[0], ref):
+        torch.testing.assert_close(a, b, rtol=5e-3, atol=5e-4)
+        exact = exact and torch.equal(a, b)
+    assert not exact                                             # the wire really was fp16
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
