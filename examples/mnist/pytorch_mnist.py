@@ -64,6 +64,12 @@ def main(argv=None):
     ap.add_argument("--use-mixed-precision", action="store_true", default=False,
                     help="autocast forward + scaled loss (reference: train_mixed_precision, pytorch_mnist.py:63-83)")
     ap.add_argument("--loss-scale", type=float, default=128.0, help="static loss scale of the mixed-precision path")
+    # parsed by the reference's example too, where only --use-adasum has an effect (the learning rate is then not scaled
+    # by the number of ranks; the Horovod compression / Adasum / predivide arguments are commented out there,
+    # examples/mnist/pytorch_mnist.py:207-235 of the reference)
+    ap.add_argument("--fp16-allreduce", action="store_true", default=False, help="accepted for command-line parity (no effect)")
+    ap.add_argument("--use-adasum", action="store_true", default=False, help="do not scale the learning rate by the world size")
+    ap.add_argument("--gradient-predivide-factor", type=float, default=1.0, help="accepted for command-line parity (no effect)")
     args = ap.parse_args(argv)
     cuda = not args.no_cuda and torch.cuda.is_available()
 
@@ -79,7 +85,8 @@ def main(argv=None):
 
     model = Net().to(device)
     # scale the learning rate by the number of workers, as the reference example does
-    optimizer = torch.optim.SGD(model.parameters(), lr=args.lr * hvd.size(), momentum=args.momentum)
+    lr_scaler = 1 if args.use_adasum else hvd.size()
+    optimizer = torch.optim.SGD(model.parameters(), lr=args.lr * lr_scaler, momentum=args.momentum)
     optimizer = hvd.DistributedOptimizer(optimizer, model=model, threshold=args.threshold, verbose=hvd.rank() == 0)
     hvd.broadcast_parameters(model.state_dict(), root_rank=0)
 
