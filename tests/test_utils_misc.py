@@ -58,6 +58,27 @@ def test_ncu_launch_list_aggregation():
     assert "dear::rs_kernel" in out and "n=   2" in out and "80.0%" in out
 
 
+def test_ncu_summary_sums_instruction_counters_like_the_reference_extractor():
+    """horovod/extract_profilings.py of the reference: invocations x FP32 instructions, summed over an nvprof dump."""
+    hdr = ('"ID","Process ID","Process Name","Host Name","Kernel Name","Context","Stream","Block Size","Grid Size","Device",'
+           '"CC","Section Name","Metric Name","Metric Unit","Metric Value"\n')
+    row = '"%d","1","python","h","%s","1","7","(256, 1, 1)","(64, 1, 1)","0","10.0","X","%s","%s","%s"\n'
+    csv = hdr + row % (0, "gemm(float*)", "gpu__time_duration.sum", "us", "5.0") \
+        + row % (0, "gemm(float*)", "smsp__sass_thread_inst_executed_op_fp32_pred_on.sum", "inst", "3,000,000,000") \
+        + row % (1, "relu(float*)", "gpu__time_duration.sum", "us", "5.0") \
+        + row % (1, "relu(float*)", "smsp__sass_thread_inst_executed_op_fp32_pred_on.sum", "inst", "1,000,000,000")
+    with tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False) as f:
+        f.write(csv)
+        path = f.name
+    try:
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), path], capture_output=True, text=True,
+                             check=True).stdout
+    finally:
+        os.unlink(path)
+    assert "== gpu__time_duration.sum" in out and "total 10.0 us over 2 launches" in out
+    assert "total 4e+09 inst over 2 launches (4.000 G)" in out and "75.0%" in out
+
+
 def test_prefetcher_upload_delay_is_a_noop_on_cpu():
     from dear_pytorch_b200.utils.data import PinnedPrefetcher, SyntheticImages
     src = SyntheticImages(2, image_size=8, num_classes=5, n_buffers=2)
