@@ -103,3 +103,41 @@ def test_prefetcher_with_delayed_uploads_delivers_every_batch_intact():
         sums.append(x.double().sum())              # consumer work on the current stream
     torch.cuda.synchronize()
     assert [float(s) for s in sums] == [float(i) * (1 << 20) for i in range(12)]
+
+
+def test_reference_utils_helpers():
+    import numpy as np
+    from dear_pytorch_b200.utils import misc
+    assert len(misc.gen_random_id()) == 64 and misc.gen_random_id() != misc.gen_random_id()
+    with tempfile.TemporaryDirectory() as d:
+        p = misc.create_path("a/b", base=d)
+        assert os.path.isdir(p) and misc.create_path("a/b", base=d) == p
+    timers = {}
+    misc.force_insert_item(timers, "w", 0.1)
+    misc.force_insert_item(timers, "w", 0.2)
+    assert timers == {"w": [0.1, 0.2]}
+    idx, vals = misc.topk(np.array([0.1, -5.0, 0.3, 4.0, -0.2]), 2)
+    assert sorted(idx.tolist()) == [1, 3] and sorted(vals.tolist()) == [-5.0, 4.0]
+    assert [misc.get_approximate_sigma_scale(d) for d in (0.9, 0.5, 0.03, 0.001)] == [0.5, 1.5, 2.0, 3.0]
+
+    class Item:
+        size = None
+        def set_fontsize(self, s): self.size = s
+    class Axis:
+        def __init__(self): self.label = Item()
+    class Ax:
+        def __init__(self):
+            self.title, self.xaxis, self.yaxis, self.ticks, self.texts = Item(), Axis(), Axis(), [Item(), Item()], []
+        def get_xticklabels(self): return self.ticks[:1]
+        def get_yticklabels(self): return self.ticks[1:]
+        def text(self, x, y, s, **kw): self.texts.append((x, y, s))
+    class Rect:
+        def get_y(self): return 0.0
+        def get_height(self): return 2.0
+        def get_x(self): return 1.0
+        def get_width(self): return 0.5
+    ax = Ax()
+    misc.update_fontsize(ax, 9)
+    assert ax.title.size == ax.xaxis.label.size == ax.ticks[1].size == 9
+    misc.autolabel([Rect()], ax, "x1.9")
+    assert ax.texts == [(1.25, 2.06, "x1.9")]
