@@ -2,6 +2,8 @@
 import os
 import sys
 
+import pytest
+
 from _mp import run_ranks
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -29,10 +31,11 @@ def mnist_amp_worker(rank, world):
                                "--log-interval", "1000", "--lr", "0.05", "--use-mixed-precision", "--loss-scale", "64"])
 
 
-def test_mnist_mixed_precision_path_with_static_loss_scale():
+@pytest.mark.parametrize("backend", ["gloo", "emu"])
+def test_mnist_mixed_precision_path_with_static_loss_scale(backend):
     """The reference's train_mixed_precision loop (skip_synchronize + scaled loss): the 1/loss_scale un-scaling is folded
     into the reduce-scatter, so training behaves like the unscaled run."""
-    outs = run_ranks(mnist_amp_worker, world=2, backend="gloo", timeout=400)
+    outs = run_ranks(mnist_amp_worker, world=2, backend=backend, timeout=400)     # emu: native runtime + direct wgrad under autocast
     (l0, a0), (l1, a1) = outs
     assert abs(l0 - l1) < 1e-6 and abs(a0 - a1) < 1e-6
     assert a0 > 0.7, "accuracy %.3f: the mixed-precision run did not learn" % a0
