@@ -53,6 +53,21 @@ def test_imagenet_driver_runs_every_method_on_two_ranks(method, extra):
     assert outs[1][1].strip() == "" or "Total" not in outs[1][1]          # only rank 0 logs
 
 
+EMU_CASES = [("dear", ()), ("dear-bo", ()), ("dear-rb", ()), ("dear", ("--dtype", "amp")), ("dear", ("--dtype", "bf16")),
+             ("dear", ("--optimizer", "adam", "--exclude-parts", "reducescatter"))]
+
+
+@pytest.mark.parametrize("method,extra", EMU_CASES, ids=["%s%s" % (m, ("-" + "-".join(a.strip("-") for a in e)) if e else "")
+                                                         for m, e in EMU_CASES])
+def test_imagenet_driver_on_the_native_runtime_host_emulation(method, extra):
+    """Same command lines on DEAR_BACKEND=emu: the C++ runtime a GPU run uses (bucket sets, pack tables, flag protocol,
+    direct wgrad, sharded update), with the kernels emulated on the host; autocast and bf16 parameters included."""
+    outs = run_ranks(_imagenet_worker, world=2, backend="emu", args=(method, extra), timeout=300)
+    res, text = outs[0]
+    assert res["total"] > 0
+    assert "backend: emu" in text and text.strip().split("\n")[-1].startswith("Total img/sec on 2 CPU(s): ")
+
+
 def _bert_worker(rank, world, method, cfg_path):
     import bert_benchmark as drv
     buf = io.StringIO()
