@@ -24,6 +24,7 @@ B200-first redesign:
 """
 from __future__ import annotations
 
+import math
 import os
 from typing import Dict, List, Optional
 
@@ -92,6 +93,10 @@ class DearEngine:
         for p in model.parameters():
             if p.requires_grad and p.device.type != self.device.type:
                 raise RuntimeError("model parameters live on %s but the runtime device is %s" % (p.device, self.device))
+        # Adam / AdamW: updates a parameter did NOT take part in (no gradient on any rank).  torch.optim keeps the step
+        # count per parameter, the kernels keep one per bucket set: _refresh_hyper folds the difference into the
+        # parameter's hyper segment (see _adam_lag_adjust)
+        self._lag: Dict[nn.Parameter, int] = {}
         self.group_of: Dict[nn.Parameter, int] = {}
         for gi, grp in enumerate(optimizer.param_groups):
             for p in grp["params"]:
@@ -323,15 +328,34 @@ class DearEngine:
             self._next_rs -= 1
 
     # ------------------------------------------------------------------ hyper-parameters
+    @staticmethod
+    def _adam_lag_adjust(k, t: int, lag: int):
+        """Hyper-parameters that make the kernel's update with the GLOBAL step count ``t`` equal to Adam's update with
+        the parameter's own count ``s = t - lag`` (torch.optim counts steps per parameter and skips a parameter without
+        gradient):   lr/bc1(s) * m / (sqrt(v)/sqrt(bc2(s)) + eps)  ==  lr'/bc1(t) * m / (sqrt(v)/sqrt(bc2(t)) + eps')
+        with  r = sqrt(bc2(s)/bc2(t)),  eps' = eps r,  lr' = lr r bc1(t)/bc1(s);  AdamW's decoupled decay keeps
+        lr' wd' = lr wd."""
+        lr, wd, b1, damp, nest, opt, b2, eps = k
+        s = t - lag
+        r = math.sqrt((1.0 - b2 ** s) / (1.0 - b2 ** t)) if b2 < 1.0 else 1.0
+        lr2 = lr * r * ((1.0 - b1 ** t) / (1.0 - b1 ** s) if 0.0 < b1 < 1.0 else 1.0)
+        wd2 = wd * lr / lr2 if (opt == OPT_ADAMW and lr2 != 0.0) else wd
+        return (lr2, wd2, b1, damp, nest, opt, b2, eps * r)
+
     def _refresh_hyper(self):
         key_all = self._hyper_key_now()
+        t = self.num_updates + 1                     # the step count the kernels will use for the coming update
         for b in self.plan.buckets:
             absent = self._absent[b.index]
-            key = (key_all, absent)
+            lags = None
+            if self.opt_kind != OPT_SGD and self._lag:
+                lags = tuple(self._lag.get(sl.param, 0) for sl in b.slots)
+                lags = (t, lags) if any(lags) else None
+            key = (key_all, absent, lags)
             if self._hyper_key[b.index] == key:
                 continue
             segs = []
-            if not absent:
+            if not absent and lags is None:
                 for end, gi in self.plan.hyper_segments(b.index, self.group_of):
                     segs.append((int(end),) + key_all[gi])
             else:
@@ -341,14 +365,17 @@ class DearEngine:
                 gone, prev = set(absent), None
                 for i, sl in enumerate(b.slots):
                     gi, skip = self.group_of[sl.param], i in gone
+                    lag = lags[1][i] if (lags is not None and not skip) else 0
                     end = b.slots[i + 1].start if i + 1 < len(b.slots) else b.padded_numel
                     k = key_all[gi]
+                    if lag and t - lag >= 1:
+                        k = self._adam_lag_adjust(k, t, lag)
                     seg = (int(end),) + k[:4] + (int(k[4]) | (HYPER_SKIP if skip else 0),) + k[5:]
-                    if prev == (gi, skip):
+                    if prev == (gi, skip, lag) and not lag:
                         segs[-1] = seg
                     else:
                         segs.append(seg)
-                    prev = (gi, skip)
+                    prev = (gi, skip, lag)
             self.backend.set_hyper(b.index, HyperSpec(segs))
             self._hyper_key[b.index] = key
 
@@ -372,6 +399,9 @@ class DearEngine:
     def refresh_hyper_outside_graph(self):
         """An LR scheduler changed ``param_groups`` while the step is replayed from a CUDA graph:
         re-upload the device hyper-parameter tables and order the replay after the upload."""
+        # a replayed graph advances the device step counter on its own; a per-parameter correction computed here for
+        # one value of it would go stale, so under graphs Adam's bias correction follows the global count
+        self._lag.clear()
         self._refresh_hyper()
         self.backend.wait_all()
 
@@ -412,6 +442,12 @@ class DearEngine:
             self._any_pending = True
             self._mom_initialised = True
             self.num_updates += 1
+            if self.opt_kind != OPT_SGD:
+                for g in range(nb):
+                    if self._absent[g]:
+                        slots = self.plan.buckets[g].slots
+                        for i in self._absent[g]:
+                            self._lag[slots[i].param] = self._lag.get(slots[i].param, 0) + 1
         else:
             # time-breakdown mode (no all-gather): peers may still be pulling from this rank's
             # gradient buckets, so rendezvous on the device before the next backward reuses them

@@ -55,7 +55,8 @@ def optimizer_state_dict(optimizer) -> dict:
         ent = {}
         if eng.opt_kind != 0:              # Adam / AdamW: torch.optim.Adam state layout
             if s.name in carry["momentum"]:
-                ent["step"] = torch.tensor(float(carry["num_updates"]))
+                # torch.optim.Adam counts steps per parameter: updates this one sat out (no gradient) are not counted
+                ent["step"] = torch.tensor(float(carry["num_updates"] - eng._lag.get(s.param, 0)))
                 ent["exp_avg"] = carry["momentum"][s.name].reshape(s.param.shape).clone()
                 ent["exp_avg_sq"] = carry["var"][s.name].reshape(s.param.shape).clone()
         elif s.name in carry["momentum"] and carry["mom_init"]:
@@ -87,6 +88,7 @@ def load_optimizer_state_dict(optimizer, sd: dict) -> None:
     meta = sd.get("dear") or {}
     carry = {"momentum": {}, "master": {}, "var": {}, "mom_init": False,
              "num_updates": int(meta.get("num_updates", eng.num_updates))}
+    adam_steps = {}
     for s in eng.plan.slots:
         ent = sd["state"].get(index[s.param])
         if ent is None:
@@ -100,10 +102,16 @@ def load_optimizer_state_dict(optimizer, sd: dict) -> None:
         if ent.get("exp_avg") is not None:
             carry["momentum"][s.name] = ent["exp_avg"].to(eng.device, torch.float32).reshape(-1)
             carry["var"][s.name] = ent["exp_avg_sq"].to(eng.device, torch.float32).reshape(-1)
-            carry["num_updates"] = int(float(ent.get("step", carry["num_updates"])))
+            if ent.get("step") is not None:
+                adam_steps[s.param] = int(float(ent["step"]))
         mp = ent.get("master_param")
         if mp is not None:
             carry["master"][s.name] = mp.to(eng.device, torch.float32).reshape(-1)
+    if adam_steps:
+        # the kernels keep ONE step count (the largest); parameters behind it get their bias correction adjusted
+        # through their hyper segment (DearEngine._adam_lag_adjust)
+        carry["num_updates"] = max(adam_steps.values())
+        eng._lag = {p: carry["num_updates"] - v for p, v in adam_steps.items() if v < carry["num_updates"]}
     eng._restore_state(carry)
     eng.backend.set_step(eng.num_updates)
     eng._hyper_key = [None] * len(eng._hyper_key)

@@ -108,3 +108,66 @@ def test_adam_on_gpu(world):
                             extra_env={"DEAR_SPIN_TIMEOUT_S": "15"}, timeout=300):
         for a, b in zip(params, ref):
             torch.testing.assert_close(a, b, rtol=2e-4, atol=5e-6)
+
+
+class _Branchy(nn.Module):
+    """``side`` only takes part in odd steps: torch.optim.Adam then counts ITS steps separately (and leaves it alone
+    otherwise)."""
+
+    def __init__(self):
+        super().__init__()
+        torch.manual_seed(3)
+        self.a, self.side, self.b = nn.Linear(10, 16), nn.Linear(16, 16), nn.Linear(16, 4)
+
+    def forward(self, x, use_side):
+        h = torch.tanh(self.a(x))
+        if use_side:
+            h = h + torch.relu(self.side(h))
+        return self.b(h)
+
+
+def _branchy_data(t, n):
+    g = torch.Generator().manual_seed(900 + t)
+    return torch.randn(n, 10, generator=g), torch.randint(0, 4, (n,), generator=g)
+
+
+def _branchy_reference(kind, kw, steps, n):
+    m = _Branchy()
+    opt = make_opt(kind, m.parameters(), kw)
+    for t in range(steps):
+        x, y = _branchy_data(t, n)
+        opt.zero_grad()
+        nn.functional.cross_entropy(m(x, t % 3 == 2), y).backward()
+        opt.step()
+    return [p.detach().clone() for p in m.parameters()], {i: int(st["step"]) for i, st in opt.state_dict()["state"].items()}
+
+
+def _branchy_worker(rank, world, kind, kw, steps, per, reload_at):
+    import dear_pytorch_b200 as dear
+    m = _Branchy()
+    opt = dear.DistributedOptimizer(make_opt(kind, m.parameters(), kw), m, threshold=0.0005, verbose=False)
+    dear.broadcast_parameters(m.state_dict(), 0)
+    for t in range(steps):
+        x, y = _branchy_data(t, world * per)
+        opt.zero_grad()
+        nn.functional.cross_entropy(m(x[rank * per:(rank + 1) * per], t % 3 == 2), y[rank * per:(rank + 1) * per]).backward()
+        opt.step()
+        if t == reload_at:                           # the per-parameter counts survive a state-dict round trip
+            opt.load_state_dict(opt.state_dict())
+    opt.synchronize()
+    sd = opt.state_dict()
+    return [p.detach().clone() for p in m.parameters()], {i: int(float(e["step"])) for i, e in sd["state"].items() if "step" in e}
+
+
+@pytest.mark.parametrize("backend", ["gloo", "emu"])
+@pytest.mark.parametrize("kind,kw", [("adam", dict(lr=1e-2, weight_decay=1e-2)), ("adamw", dict(lr=1e-2, weight_decay=5e-2))])
+def test_adam_counts_steps_per_parameter_like_torch(backend, kind, kw):
+    steps, world, per = 7, 2, 2
+    ref, ref_steps = _branchy_reference(kind, kw, steps, world * per)
+    assert sorted(set(ref_steps.values())) == [2, 7]           # `side` took part in steps 2 and 5 only
+    for reload_at in (-1, 3):
+        outs = run_ranks(_branchy_worker, world=world, backend=backend, args=(kind, kw, steps, per, reload_at))
+        for params, counts in outs:
+            for a, b in zip(params, ref):
+                torch.testing.assert_close(a, b, rtol=2e-4, atol=2e-6)
+            assert counts == ref_steps
