@@ -349,7 +349,10 @@ class DearEngine:
             absent = self._absent[b.index]
             lags = None
             if self.opt_kind != OPT_SGD and self._lag:
-                lags = tuple(self._lag.get(sl.param, 0) for sl in b.slots)
+                # (a parameter that sits this step out as well needs no correction now: no table churn for a branch
+                # that never runs)
+                gone_now = set(absent)
+                lags = tuple(0 if i in gone_now else self._lag.get(sl.param, 0) for i, sl in enumerate(b.slots))
                 lags = (t, lags) if any(lags) else None
             key = (key_all, absent, lags)
             if self._hyper_key[b.index] == key:
