@@ -163,6 +163,7 @@ class _ReduceBroadcastOptimizer(torch.optim.Optimizer):
                 self._gbuf.append(gb)
         nb = len(self._plan.buckets)
         self._arrived = [0] * nb
+        self._got = set()                  # parameters that received a gradient in the current step
         self._reduce_handle = [None] * nb
         self._bcast_handle = [None] * nb
         self._hooks = []
@@ -182,6 +183,7 @@ class _ReduceBroadcastOptimizer(torch.optim.Optimizer):
             gv.copy_(p.grad)
             p.grad = gv
         self._arrived[g] += 1
+        self._got.add(p)
         if self._arrived[g] == len(self._plan.buckets[g].slots) and not self._exclude_reduce:
             self._reduce_handle[g] = self._comm.reduce(self._gbuf[g], self.ROOT, 1.0 / self._world)
 
@@ -211,7 +213,20 @@ class _ReduceBroadcastOptimizer(torch.optim.Optimizer):
                 self._comm.waitStream(self._reduce_handle[g])
                 self._reduce_handle[g] = None
         if self._rank == self.ROOT:
+            # a parameter whose gradient is a bucket view always "has" a gradient; torch.optim skips parameters WITHOUT
+            # one (no weight decay, no momentum decay).  Hide the views of parameters that received nothing here and
+            # whose reduced gradient is zero as well (= unused on every rank) for the duration of the update.
+            hidden = []
+            if len(self._got) != len(self._plan.slots):
+                for sl in self._plan.slots:
+                    q = sl.param
+                    if q not in self._got and q.grad is not None and not bool(q.grad.any()):
+                        hidden.append((q, q.grad))
+                        q.grad = None
             super(self.__class__, self).step()          # the user's optimizer, on the averaged gradients
+            for q, gview in hidden:
+                q.grad = gview
+        self._got.clear()
         for g in range(len(self._plan.buckets)):
             self._gbuf[g].zero_()
             self._arrived[g] = 0
