@@ -242,3 +242,39 @@ def test_horovod_fp16_allreduce_tracks_fp32_within_half_precision():
     assert not exact                                             # the wire really was fp16
     for a, b in zip(outs[0], outs[1]):
         assert torch.equal(a, b)
+
+
+def _rb_unused_worker(rank, world, steps, per_rank):
+    import dear_pytorch_b200 as dear
+    from dear_pytorch_b200.parallel import variants
+    from test_stress_order import Tangled, batch
+    m = Tangled(depth=3)
+    opt = variants.ReduceBroadcastDistributedOptimizer(torch.optim.SGD(m.parameters(), lr=0.05, momentum=0.9, weight_decay=1e-3),
+                                                       m, threshold=0.002, verbose=False)
+    dear.broadcast_parameters(m.state_dict(), 0)
+    for t in range(steps):
+        x, y = batch(t, world * per_rank)
+        opt.zero_grad()
+        nn.functional.cross_entropy(m(x[rank * per_rank:(rank + 1) * per_rank]), y[rank * per_rank:(rank + 1) * per_rank]).backward()
+        opt.step()
+    opt.synchronize()
+    return {k: v.detach().clone() for k, v in m.state_dict().items()}
+
+
+def test_reduce_broadcast_variant_leaves_unused_parameters_alone():
+    """``Tangled.unused`` never runs: with weight decay + momentum torch.optim does not touch it (its gradient is None);
+    the variant's bucket-view gradients are all zeros there and must not be treated as a gradient."""
+    from test_stress_order import Tangled, batch
+    steps, world, per = 4, 2, 2
+    ref = Tangled(depth=3)
+    opt = torch.optim.SGD(ref.parameters(), lr=0.05, momentum=0.9, weight_decay=1e-3)
+    w0 = ref.unused.weight.detach().clone()
+    for t in range(steps):
+        x, y = batch(t, world * per)
+        opt.zero_grad()
+        nn.functional.cross_entropy(ref(x), y).backward()
+        opt.step()
+    assert torch.equal(ref.unused.weight, w0)
+    for sd in run_ranks(_rb_unused_worker, world=world, backend="gloo", args=(steps, per)):
+        for k, v in ref.state_dict().items():
+            torch.testing.assert_close(sd[k], v, rtol=3e-5, atol=3e-6)
