@@ -305,7 +305,10 @@ class DearEngine:
                 for i, ok in enumerate(self._arrived[g]):
                     if ok:
                         continue
-                    late = self.plan.buckets[g].slots[i].param.grad if self.passes_per_step > 1 else None
+                    # (bucket-view mode keeps p.grad alive between steps: whether autograd produced anything in THIS
+                    # step is what the hook counted)
+                    q = self.plan.buckets[g].slots[i].param
+                    late = q.grad if (self.passes_per_step > 1 and self._passes_seen.get(q, 0) > 0) else None
                     if late is not None:
                         # accumulated over fewer passes than passes_per_step (unused in some): still a gradient
                         p = self.plan.buckets[g].slots[i].param

@@ -134,3 +134,40 @@ def test_second_backward_without_accumulation_is_an_error():
             return "backward_passes_per_step" in str(e)
         return False
     assert all(run_ranks(w, world=1, backend="gloo"))
+
+
+def _intermittent_worker(rank, world, steps, k, per):
+    import dear_pytorch_b200 as dear
+    from test_adam import _Branchy, _branchy_data
+    m = _Branchy()
+    opt = dear.DistributedOptimizer(torch.optim.SGD(m.parameters(), lr=0.05, momentum=0.9, weight_decay=1e-2), m,
+                                    threshold=0.0005, backward_passes_per_step=k, verbose=False)
+    dear.broadcast_parameters(m.state_dict(), 0)
+    for t in range(steps):
+        opt.zero_grad()
+        for a in range(k):
+            x, y = _branchy_data(t * k + a, world * per)
+            (nn.functional.cross_entropy(m(x[rank * per:(rank + 1) * per], (t * k + a) % 5 == 1), y[rank * per:(rank + 1) * per]) / k).backward()
+        opt.step()
+    opt.synchronize()
+    return [p.detach().clone() for p in m.parameters()]
+
+
+@pytest.mark.parametrize("backend", ["gloo", "emu"])
+def test_accumulation_with_a_branch_that_skips_whole_steps(backend):
+    """k = 3 passes per step, the side branch runs in passes 1 and 6 only: step 0 and step 2 accumulate its gradient
+    over fewer passes than k, step 1 has none at all — there torch.optim leaves the parameter (and its momentum) alone.
+    In bucket-view mode ``p.grad`` stays allocated between steps, so "no gradient" has to come from the hook count."""
+    from test_adam import _Branchy, _branchy_data
+    steps, k, world, per = 3, 3, 2, 2
+    ref = _Branchy()
+    opt = torch.optim.SGD(ref.parameters(), lr=0.05, momentum=0.9, weight_decay=1e-2)
+    for t in range(steps):
+        opt.zero_grad()
+        for a in range(k):
+            x, y = _branchy_data(t * k + a, world * per)
+            (nn.functional.cross_entropy(ref(x, (t * k + a) % 5 == 1), y) / k).backward()
+        opt.step()
+    for params in run_ranks(_intermittent_worker, world=world, backend=backend, args=(steps, k, per)):
+        for a, b in zip(params, ref.parameters()):
+            torch.testing.assert_close(a, b.detach(), rtol=3e-5, atol=3e-6)
