@@ -249,6 +249,69 @@ class BertPretrainingCriterion(nn.Module):
         return mlm + nsp
 
 
+# ---- checkpoints of the reference's model -----------------------------------------------------------------------------
+# The reference trains transformers' ``BertForPreTraining`` (dear/bert_benchmark.py:72-83).  Same architecture, different
+# module tree: the three attention projections are one [3H, H] GEMM here, the sub-module names are flatter.
+
+_HF_LAYER = [("attention.output.dense", "attn_out"), ("attention.output.LayerNorm", "attn_norm"),
+             ("intermediate.dense", "intermediate"), ("output.dense", "output"), ("output.LayerNorm", "out_norm")]
+_HF_TOP = [("bert.pooler.dense", "bert.pooler"), ("cls.predictions.transform.dense", "cls.transform"),
+           ("cls.predictions.transform.LayerNorm", "cls.transform_norm"), ("cls.seq_relationship", "cls.seq_relationship")]
+
+
+def from_hf_state_dict(hf: dict, num_layers: int, vocab_size: int = None) -> dict:
+    """State dict of this module tree from one of ``transformers.BertForPreTraining`` (vocabulary rows are zero-padded to
+    ``vocab_size`` when the model pads its embedding table to a multiple of 8)."""
+    out = {}
+    for k in ("word_embeddings.weight", "position_embeddings.weight", "token_type_embeddings.weight", "LayerNorm.weight",
+              "LayerNorm.bias"):
+        out["bert.embeddings." + k] = hf["bert.embeddings." + k]
+    for i in range(num_layers):
+        src, dst = "bert.encoder.layer.%d." % i, "bert.layers.%d." % i
+        for wb in ("weight", "bias"):
+            out[dst + "attention.qkv." + wb] = torch.cat([hf[src + "attention.self.%s.%s" % (n, wb)]
+                                                          for n in ("query", "key", "value")], 0)
+            for a, b in _HF_LAYER:
+                out[dst + b + "." + wb] = hf[src + a + "." + wb]
+    for a, b in _HF_TOP:
+        for wb in ("weight", "bias"):
+            out[b + "." + wb] = hf[a + "." + wb]
+    out["cls.decoder_bias"] = hf["cls.predictions.bias"]
+    if vocab_size is not None:
+        for k in ("bert.embeddings.word_embeddings.weight", "cls.decoder_bias"):
+            t = out[k]
+            if t.shape[0] < vocab_size:
+                out[k] = torch.cat([t, t.new_zeros((vocab_size - t.shape[0],) + tuple(t.shape[1:]))], 0)
+    return {k: v.clone() for k, v in out.items()}
+
+
+def to_hf_state_dict(sd: dict, num_layers: int, vocab_size: int = None) -> dict:
+    """The inverse: a state dict ``transformers.BertForPreTraining.load_state_dict`` accepts."""
+    out = {}
+    for k in ("word_embeddings.weight", "position_embeddings.weight", "token_type_embeddings.weight", "LayerNorm.weight",
+              "LayerNorm.bias"):
+        out["bert.embeddings." + k] = sd["bert.embeddings." + k]
+    for i in range(num_layers):
+        src, dst = "bert.layers.%d." % i, "bert.encoder.layer.%d." % i
+        for wb in ("weight", "bias"):
+            q, k_, v = sd[src + "attention.qkv." + wb].chunk(3, 0)
+            for n, t in (("query", q), ("key", k_), ("value", v)):
+                out[dst + "attention.self.%s.%s" % (n, wb)] = t
+            for a, b in _HF_LAYER:
+                out[dst + a + "." + wb] = sd[src + b + "." + wb]
+    for a, b in _HF_TOP:
+        for wb in ("weight", "bias"):
+            out[a + "." + wb] = sd[b + "." + wb]
+    emb, bias = sd["bert.embeddings.word_embeddings.weight"], sd["cls.decoder_bias"]
+    if vocab_size is not None:
+        emb, bias = emb[:vocab_size], bias[:vocab_size]
+    out["bert.embeddings.word_embeddings.weight"] = emb
+    out["cls.predictions.decoder.weight"] = emb                      # tied
+    out["cls.predictions.bias"] = bias
+    out["cls.predictions.decoder.bias"] = bias
+    return {k: v.clone() for k, v in out.items()}
+
+
 def bert_large(**kw): return BertForPreTraining(BERT_LARGE, **kw)
 def bert_base(**kw): return BertForPreTraining(BERT_BASE, **kw)
 

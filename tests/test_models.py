@@ -52,3 +52,38 @@ def test_fused_variants_keep_the_state_dict():
     with torch.device("meta"):
         large = bert.BertForPreTraining(bert.BERT_LARGE)
     assert sum(p.numel() for p in large.parameters()) == 336_232_258      # the count bench.py reports for BERT-large
+
+
+def test_bert_matches_transformers_bert_for_pretraining():
+    """Same architecture as the model the reference trains (dear/bert_benchmark.py:72-83): load the weights of a small
+    ``transformers.BertForPreTraining`` through the converter and compare both heads, with and without key padding; the
+    converter round-trips."""
+    transformers = pytest.importorskip("transformers")
+    from dear_pytorch_b200.models import bert as B
+    cfg = dict(vocab_size=90, hidden_size=32, num_hidden_layers=3, num_attention_heads=4, intermediate_size=64,
+               max_position_embeddings=24)
+    torch.manual_seed(0)
+    hf = transformers.BertForPreTraining(transformers.BertConfig(**cfg)).eval()
+    with torch.no_grad():                                  # the zero-initialised biases / unit LayerNorms prove nothing
+        for p in hf.parameters():
+            p.add_(0.05 * torch.randn_like(p))
+    ours = B.BertForPreTraining(B.BertConfig(**cfg)).eval()
+    assert ours.vocab_size == 96                           # padded to a multiple of 8 like the reference does (:77-78)
+    ours.load_state_dict(B.from_hf_state_dict(hf.state_dict(), cfg["num_hidden_layers"], ours.vocab_size))
+    ids = torch.randint(0, 90, (3, 20))
+    types = torch.randint(0, 2, (3, 20))
+    mask = torch.ones(3, 20, dtype=torch.long)
+    mask[1, 13:] = 0
+    mask[2, 5:] = 0
+    with torch.no_grad():
+        for m in (None, mask):
+            ref = hf(input_ids=ids, token_type_ids=types, attention_mask=m)
+            scores, nsp = ours(ids, types, m)
+            torch.testing.assert_close(scores[..., :90], ref.prediction_logits, rtol=1e-4, atol=1e-4)
+            torch.testing.assert_close(nsp, ref.seq_relationship_logits, rtol=1e-4, atol=1e-4)
+    back = B.to_hf_state_dict(ours.state_dict(), cfg["num_hidden_layers"], 90)
+    missing = hf.load_state_dict(back, strict=False)
+    assert not missing.unexpected_keys and all("position_ids" in k for k in missing.missing_keys)
+    for k, v in hf.state_dict().items():
+        if k in back:
+            assert torch.equal(back[k], v), k
