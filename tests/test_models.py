@@ -87,3 +87,68 @@ def test_bert_matches_transformers_bert_for_pretraining():
     for k, v in hf.state_dict().items():
         if k in back:
             assert torch.equal(back[k], v), k
+
+
+@pytest.mark.parametrize("name", ["resnet18", "resnet50", "vgg11", "densenet121"])
+def test_cnn_matches_torchvision(name):
+    """The reference benchmarks torchvision's models by name (dear/imagenet_benchmark.py:78-82): same parameters, same
+    function.  ResNet / VGG even share the state-dict keys; DenseNet's module tree is flatter here, with the tensors in
+    the same order."""
+    tv = pytest.importorskip("torchvision")
+    torch.manual_seed(0)
+    ref = getattr(tv.models, name)()
+    with torch.no_grad():
+        for m in ref.modules():                            # non-trivial BatchNorm statistics and affine parameters
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.normal_(0, 0.1); m.running_var.uniform_(0.5, 1.5); m.weight.uniform_(0.5, 1.5); m.bias.normal_(0, 0.1)
+    ours = create(name)
+    src = ref.state_dict()
+    if set(src) == set(ours.state_dict()):
+        ours.load_state_dict(src)
+    else:
+        mine = ours.state_dict()
+        assert [tuple(v.shape) for v in mine.values()] == [tuple(v.shape) for v in src.values()]
+        ours.load_state_dict(dict(zip(mine.keys(), src.values())))
+    x = torch.randn(2, 3, 64, 64)
+    ref.eval(); ours.eval()
+    with torch.no_grad():
+        torch.testing.assert_close(ours(x), ref(x), rtol=1e-4, atol=1e-4)
+    ref.train(); ours.train()
+    if name.startswith("vgg"):
+        torch.manual_seed(1); a = ours(x)
+        torch.manual_seed(1); b = ref(x)                   # same dropout masks
+    else:
+        a, b = ours(x), ref(x)
+    torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-4)
+    for (ka, va), (kb, vb) in zip(ours.state_dict().items(), ref.state_dict().items()):
+        if "running" in ka:
+            torch.testing.assert_close(va, vb, rtol=1e-5, atol=1e-6)      # the training forward updated the same statistics
+
+
+def test_inceptionv4_matches_the_reference_file():
+    """The reference ships its own Inception-v4 (dear/inceptionv4.py, the Cadene implementation).  When the reference arm
+    is installed (baseline/_ref, used by `bench.py --impl reference`), load its class next to ours: the tensors line up one
+    to one (896, same order and shapes) and the function is the same."""
+    import glob
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    found = glob.glob(os.path.join(root, "baseline", "_ref", "dear", "inceptionv4.py"))
+    if not found:
+        pytest.skip("reference arm not installed (baseline/_ref)")
+    spec = importlib.util.spec_from_file_location("_ref_inceptionv4", found[0])
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    torch.manual_seed(0)
+    ref = mod.InceptionV4(num_classes=1000).eval()
+    with torch.no_grad():
+        for m in ref.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.normal_(0, 0.1); m.running_var.uniform_(0.5, 1.5); m.weight.uniform_(0.5, 1.5); m.bias.normal_(0, 0.1)
+    ours = create("inceptionv4").eval()
+    mine, src = ours.state_dict(), ref.state_dict()
+    assert [tuple(v.shape) for v in mine.values()] == [tuple(v.shape) for v in src.values()]
+    ours.load_state_dict(dict(zip(mine.keys(), src.values())))
+    x = torch.randn(1, 3, 299, 299)
+    with torch.no_grad():
+        torch.testing.assert_close(ours(x), ref(x), rtol=1e-3, atol=1e-3)
