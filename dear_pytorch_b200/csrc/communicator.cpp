@@ -553,6 +553,7 @@ void BucketSet::upload(Bucket& b, bool is_pack, const void* host, size_t bytes, 
       }
       if (err == cudaSuccess) err = cudaStreamSynchronize(S(upload_stream_));
       if (pin) cudaFreeHost(pin);
+      if (err != cudaSuccess && dtab != nullptr) { cudaFree(dtab); dtab = nullptr; }   // nothing leaks on the error path
       cudaThreadExchangeStreamCaptureMode(&mode);
     }
     DEAR_CUDA(err);
