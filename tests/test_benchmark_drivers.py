@@ -119,3 +119,13 @@ def test_batch_runner_dry_run_lists_the_reference_matrix():
     assert len(cmds) == 6 * 7                                  # tasks x methods (reference benchmarks.py:21,10-19)
     assert any("bert_benchmark.py --model bert --batch-size 32 --method dear" in c and "--sentence-len 64" in c for c in cmds)
     assert any("imagenet_benchmark.py --model vgg16 --batch-size 64 --method bytescheduler" in c for c in cmds)
+
+
+def test_launch_script_env_flags():
+    """scripts/launch.sh keeps the reference launcher's environment "flags" (dear/horovod_mpi_cj.sh:2-29): a compressor
+    selects the sparse WFBP baseline with density 0.001 and one 64 Mi-element group."""
+    env = dict(os.environ, DEAR_BACKEND="gloo", dnn="resnet18", bs="1", nworkers="2", compressor="eftopk", PY=sys.executable)
+    out = subprocess.run([os.path.join(ROOT, "scripts", "launch.sh"), "--fused-bn", "0", "--image-size", "64"] + TINY[2:],
+                         capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "Method: wfbp" in out.stdout and "Total img/sec on 2 CPU(s): " in out.stdout
