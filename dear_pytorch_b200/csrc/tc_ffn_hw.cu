@@ -4,7 +4,7 @@
 //     ffn_dgelu_hw : dZ = (dY Wt^T) * gelu'(Z)        dY [M,K], Wt [N,K] (= transposed down-projection weight), Z [M,N]
 //   (one kernel template, two epilogue modes; both operands K-major)
 //
-// Why this kernel exists: the CUTLASS-collective variants (tc_gemm.h) run the same op but are
+// Why this kernel exists: the CUTLASS-collective variants of round 1 (removed from the tree since) ran the same op but were
 // epilogue-issue-bound — ncu (profiles/prof_bert_ops_summary.md) shows the tensor pipe falling from 59 %
 // to 28 % when the GELU moves into the epilogue, because their 4 epilogue warps (one per SM sub-partition)
 // cannot hide the MUFU/FMA latency of 16 k erf-GELUs per tile.  Here the epilogue has 8 warps: warps w and
@@ -197,7 +197,7 @@ constexpr uint32_t kInstrDesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cas
 constexpr uint32_t kInstrDescBMN = kInstrDesc | (1u << 16);            // B operand MN-major
 
 // ------------------------------------------------------------------------------------------ GELU
-// Phi(-|x|) by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7), as in tc_gemm.h: 2 MUFU + ~12 FMA per element
+// Phi(-|x|) by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7): 2 MUFU + ~12 FMA per element
 __device__ __forceinline__ float gelu_fast(float x) {
   const float ax = fabsf(x);
   const float e = __expf(-0.5f * x * x);
