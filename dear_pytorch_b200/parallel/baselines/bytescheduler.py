@@ -78,6 +78,8 @@ class _ByteSchedulerOptimizer(torch.optim.Optimizer):
         self._params = [p for p in model.parameters() if p.requires_grad]
         self._prio = {p: i for i, p in enumerate(self._params)}          # forward order: 0 = needed first
         self._group_of = {p: g for g in self.param_groups for p in g["params"]}
+        self._gidx = {p: i for i, g in enumerate(self.param_groups) for p in g["params"]}
+        self._hyper_of = {}                 # deferred parameter -> hyper-parameters as of the step() that deferred it
         self._lazy = isinstance(self, (torch.optim.SGD, torch.optim.Adam, torch.optim.AdamW))
         self._heap: List[_Chunk] = []
         self._inflight = collections.deque()                               # chunks committed to the comm stream
@@ -221,7 +223,9 @@ class _ByteSchedulerOptimizer(torch.optim.Optimizer):
     # ---- per-parameter updates (ByteScheduler's _sgd / _adam) ---------------------------------------
     @torch.no_grad()
     def _update_one(self, p):
-        g = self._group_of[p]
+        # a deferred update belongs to the step() that scheduled it: an LR scheduler may have moved on since
+        snap = self._hyper_of.pop(p, None)
+        g = snap[self._gidx[p]] if snap is not None else self._group_of[p]
         d = p.grad
         st = self.state[p]
         if isinstance(self, torch.optim.SGD):
@@ -294,7 +298,10 @@ class _ByteSchedulerOptimizer(torch.optim.Optimizer):
             return loss
         # lazy: every parameter with a gradient in flight is updated when its module next runs (or at synchronize())
         del self.launch_log[:-4096]
+        snap = [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups]
         self._deferred = set(self._chunks)
+        for p in self._deferred:            # (a module that does not run next iteration keeps ITS step's values)
+            self._hyper_of.setdefault(p, snap)
         for p in self._params:                      # a gradient that never went through the hook (no peers to wait for)
             if p.grad is not None and p not in self._chunks:
                 self._update_one(p)

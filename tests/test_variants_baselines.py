@@ -278,3 +278,38 @@ def test_reduce_broadcast_variant_leaves_unused_parameters_alone():
     for sd in run_ranks(_rb_unused_worker, world=world, backend="gloo", args=(steps, per)):
         for k, v in ref.state_dict().items():
             torch.testing.assert_close(sd[k], v, rtol=3e-5, atol=3e-6)
+
+
+def _bsc_sched_worker(rank, world, steps, per_rank):
+    import dear_pytorch_b200 as dear
+    from dear_pytorch_b200.parallel.baselines import ByteSchedulerOptimizer
+    model = make_model()
+    model.eval()
+    opt = ByteSchedulerOptimizer(torch.optim.SGD(model.parameters(), lr=0.05, **CASE), model, partition=100, credit=250, verbose=False)
+    sched = torch.optim.lr_scheduler.StepLR(opt, 1, 0.5)
+    dear.broadcast_parameters(model.state_dict(), 0)
+    for t in range(steps):
+        x, y = data(t, world * per_rank)
+        opt.zero_grad()
+        nn.functional.cross_entropy(model(x[rank * per_rank:(rank + 1) * per_rank]), y[rank * per_rank:(rank + 1) * per_rank]).backward()
+        opt.step()
+        sched.step()                 # changes the lr BEFORE the deferred per-layer updates of this step are applied
+    opt.synchronize()
+    return [p.detach().clone() for p in model.parameters()]
+
+
+def test_bytescheduler_deferred_updates_use_the_lr_of_their_own_step():
+    steps, per_rank, world = 4, 3, 2
+    model = make_model()
+    model.eval()
+    opt = torch.optim.SGD(model.parameters(), lr=0.05, **CASE)
+    sched = torch.optim.lr_scheduler.StepLR(opt, 1, 0.5)
+    for t in range(steps):
+        x, y = data(t, world * per_rank)
+        opt.zero_grad()
+        nn.functional.cross_entropy(model(x), y).backward()
+        opt.step()
+        sched.step()
+    for params in run_ranks(_bsc_sched_worker, world=world, backend="gloo", args=(steps, per_rank)):
+        for a, b in zip(params, model.parameters()):
+            torch.testing.assert_close(a, b.detach(), rtol=3e-5, atol=3e-6)

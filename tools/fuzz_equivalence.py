@@ -8,7 +8,7 @@ on the host) or ``gloo`` backend, and compares every parameter with the oracle t
 how the per-parameter Adam step count, the accumulation / bucket-view and the reduce-broadcast "unused parameter"
 deviations were found.
 
-    python tools/fuzz_equivalence.py --seed 1 --trials 40 [--variants dear,naive,wt,rb,bo]
+    python tools/fuzz_equivalence.py --seed 1 --trials 40 [--variants dear,naive,wt,rb,bo,wfbp,horovod,bytescheduler]
 """
 from __future__ import annotations
 
@@ -106,6 +106,15 @@ def worker(rank, world, cfg):
         opt = variants.WaitTimeDistributedOptimizer(base, m, cycle_time_ms=0.05, warmup_steps=2, verbose=False)
     elif v == "rb":
         opt = variants.ReduceBroadcastDistributedOptimizer(base, m, threshold=cfg["thr"] or 0.002, verbose=False)
+    elif v in ("wfbp", "horovod", "bytescheduler"):
+        from dear_pytorch_b200.parallel import baselines
+        if v == "wfbp":
+            opt = baselines.WFBPDistributedOptimizer(base, model=m, threshold=cfg["elems"], verbose=False)
+        elif v == "horovod":
+            opt = baselines.HorovodOptimizer(base, m, cycle_time_ms=cfg["cycle"], fusion_threshold_mb=0.002, negotiation_steps=2,
+                                             verbose=False)
+        else:
+            opt = baselines.ByteSchedulerOptimizer(base, m, partition=cfg["elems"] or 100000, credit=cfg["credit"], verbose=False)
     else:
         kw = dict(threshold=cfg["thr"]) if cfg["thr"] else dict(threshold=None, num_nearby_layers=cfg["nearby"])
         if v == "bo":
@@ -133,7 +142,7 @@ def worker(rank, world, cfg):
 
 def draw(rnd, variants_allowed):
     v = rnd.choice(variants_allowed)
-    engine = v in ("dear", "bo", "naive", "wt")
+    engine = v in ("dear", "bo", "naive", "wt", "wfbp", "horovod", "bytescheduler")
     cfg = dict(variant=v, seed=rnd.randint(0, 99), depth=rnd.randint(1, 5), width=rnd.choice([8, 17, 32]), tie=rnd.random() < 0.3,
                branch=rnd.random() < 0.5, mod=rnd.choice([2, 3, 5]),
                opt=rnd.choice(["sgd", "sgdm", "nesterov", "adam", "adamw"] if engine else ["sgd", "sgdm", "nesterov"]),
@@ -142,7 +151,10 @@ def draw(rnd, variants_allowed):
                thr=rnd.choice([None, 0.0005, 0.002, 0.01]), nearby=rnd.choice([1, 2, 3, -1]),
                accum=rnd.choice([1, 1, 2, 3]) if v == "dear" else 1, rebucket=rnd.choice([0, 0, 1, 2]),
                thr2=rnd.choice([0.0004, 0.003, 1.0]), ckpt=rnd.choice([0, 0, 1, 2]), backend=rnd.choice(["emu", "emu", "gloo"]),
-               pipe=rnd.random() < 0.25)
+               pipe=rnd.random() < 0.25, elems=rnd.choice([0, 50, 300, 5000]), cycle=rnd.choice([0.0, 0.2, 5.0]),
+               credit=rnd.choice([100, 1000, 10 ** 7]))
+    if v in ("wfbp", "horovod", "bytescheduler"):
+        cfg.update(backend="gloo", tie=False)             # NCCL-style baselines: torch.distributed only; modules own their weights
     if v == "bo" and not cfg["thr"]:
         cfg["thr"] = 0.002
     return cfg
@@ -165,7 +177,7 @@ def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--trials", type=int, default=20)
-    ap.add_argument("--variants", default="dear,dear,dear,bo,naive,wt,rb")
+    ap.add_argument("--variants", default="dear,dear,dear,bo,naive,wt,rb,wfbp,horovod,bytescheduler")
     ap.add_argument("--quiet", action="store_true")
     args = ap.parse_args(argv)
     rnd = random.Random(args.seed)
