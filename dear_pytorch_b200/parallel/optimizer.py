@@ -385,7 +385,21 @@ class DearEngine:
             self.backend.set_hyper(b.index, HyperSpec(segs))
             self._hyper_key[b.index] = key
 
+    def freeze_hyper(self):
+        """A loop that DEFERS ``step()`` past the point where the user's code may change ``param_groups`` (the rotated
+        ``TrainStep``: the update of call t runs at the start of call t+1, after ``scheduler.step()``) snapshots the
+        hyper-parameters when the gradients are complete; the deferred update then uses the snapshot, like
+        ``optimizer.step(); scheduler.step()`` would have."""
+        self._frozen_hyper = self._hyper_key_live()
+
+    def unfreeze_hyper(self):
+        self._frozen_hyper = None
+
     def _hyper_key_now(self):
+        frozen = getattr(self, "_frozen_hyper", None)
+        return frozen if frozen is not None else self._hyper_key_live()
+
+    def _hyper_key_live(self):
         """Per param group: (lr, wd, momentum|beta1, dampening, nesterov, opt, beta2, eps)."""
         keys = []
         for g in self.opt.param_groups:

@@ -14,9 +14,10 @@ in eager mode — the decoupling the whole method is about would be lost inside 
 all-gathers are the FIRST nodes of the graph and the forward's per-bucket waits let them overlap
 layer by layer.  Every call still performs one forward/backward and (from the second call on) one
 parameter update; ``finish()`` — also run by ``optimizer.synchronize()`` / ``state_dict()`` — applies
-the last pending update, so nothing is dropped at the end of training.  One visible difference: the
-update for batch *t* runs at the start of call *t+1*, so a learning-rate scheduler stepped between the
-two calls applies its new value one update earlier than in the natural loop.
+the last pending update, so nothing is dropped at the end of training.  The update for batch *t* runs at the
+start of call *t+1*, i.e. after the user's ``scheduler.step()``; it nevertheless uses the hyper-parameters that were
+in force at the end of call *t* (``DearEngine.freeze_hyper``; a snapshot of ``param_groups`` for other optimizers), so
+``step(x, y); scheduler.step()`` trains exactly like the natural loop (tests/test_train_step.py).
 
 With ``bo_tuning=True`` the wrapper stays eager while the tuner explores (its timing and re-bucketing live
 in Python hooks) and captures the graph once the final bucket layout is in place.
@@ -97,12 +98,31 @@ class TrainStep:
             self.opt.step()
             return loss
         if self._pending_update:
-            self.opt.step()                               # update from the previous call's gradients
+            self._deferred_step()                         # update from the previous call's gradients
         loss = self._forward_backward(*batch)
         if self._engine is not None:
             self._engine.flush_reduce_scatter()           # incomplete buckets (unused parameters) too
+            self._engine.freeze_hyper()                   # the deferred update belongs to THIS call's learning rate
+        else:
+            self._frozen_groups = [{k: v for k, v in g.items() if k != "params"} for g in self.opt.param_groups]
         self._pending_update = True
         return loss
+
+    def _deferred_step(self):
+        """``optimizer.step()`` for the gradients of the previous call, with the hyper-parameters that were in force when
+        that call ended (an LR scheduler stepped by the user in between must not leak into it)."""
+        frozen = getattr(self, "_frozen_groups", None)
+        if self._engine is not None or frozen is None:
+            self.opt.step()                               # (the DeAR engine holds its own snapshot: freeze_hyper)
+            return
+        live = [{k: g[k] for k in f} for g, f in zip(self.opt.param_groups, frozen)]
+        try:
+            for g, f in zip(self.opt.param_groups, frozen):
+                g.update(f)
+            self.opt.step()
+        finally:
+            for g, v in zip(self.opt.param_groups, live):
+                g.update(v)
 
     def _tuning_active(self) -> bool:
         tuner = getattr(self.opt, "tuner", None)
@@ -114,7 +134,10 @@ class TrainStep:
         """Rotated mode: apply the update of the last call's gradients (no-op otherwise)."""
         if self._pending_update:
             self._pending_update = False
-            self.opt.step()
+            self._deferred_step()
+            if self._engine is not None:
+                self._engine.unfreeze_hyper()
+            self._frozen_groups = None
 
     def _log(self, msg):
         if self._debug:
@@ -187,4 +210,6 @@ class TrainStep:
         if eng is not None:
             eng.num_steps += 1          # the replay ran the step; Python-side callbacks (tuner) do not run
             eng.num_updates += 1        # mirrors the device-resident Adam step counter (checkpointing)
+            if self.overlap_update:
+                eng.freeze_hyper()      # the update that opens the NEXT replay uses the values in force now
         return self._static_loss

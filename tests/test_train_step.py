@@ -56,3 +56,61 @@ def test_rotated_loop_with_a_plain_torch_optimizer():
         outs.append([p.detach().clone() for p in model.parameters()])
     for a, b in zip(*outs):
         assert torch.equal(a, b)
+
+
+def _sched_worker(rank, world, overlap, steps):
+    import dear_pytorch_b200 as dear
+    from dear_pytorch_b200.utils.train import TrainStep
+    model = make_model(); model.eval()
+    opt = dear.DistributedOptimizer(torch.optim.SGD(model.parameters(), lr=0.05, momentum=0.9), model, threshold=0.001, verbose=False)
+    sched = torch.optim.lr_scheduler.StepLR(opt, step_size=1, gamma=0.7)          # the LR changes after EVERY step
+    dear.broadcast_parameters(model.state_dict(), 0)
+    step = TrainStep(model, opt, nn.functional.cross_entropy, overlap_update=overlap)
+    losses = []
+    for t in range(steps):
+        x, y = data(t, world * 2)
+        losses.append(float(step(x[rank * 2:(rank + 1) * 2], y[rank * 2:(rank + 1) * 2])))
+        sched.step()
+        if t == 2:
+            opt.synchronize()                # applies the pending update with the LR of step 2, not the scheduler's new one
+    opt.synchronize()
+    return losses, [p.detach().clone() for p in model.parameters()]
+
+
+@pytest.mark.parametrize("backend", ["gloo", "emu"])
+def test_rotated_loop_with_a_per_step_lr_schedule_matches_torch(backend):
+    """The rotated body applies the update of call t at the start of call t+1 — after the user's ``scheduler.step()``.
+    It must still use call t's learning rate (``DearEngine.freeze_hyper``): same result as the plain
+    ``optimizer.step(); scheduler.step()`` loop of torch."""
+    steps, world = 6, 2
+    model = make_model(); model.eval()
+    opt = torch.optim.SGD(model.parameters(), lr=0.05, momentum=0.9)
+    sched = torch.optim.lr_scheduler.StepLR(opt, step_size=1, gamma=0.7)
+    for t in range(steps):
+        x, y = data(t, world * 2)
+        opt.zero_grad(); nn.functional.cross_entropy(model(x), y).backward(); opt.step(); sched.step()
+    natural = run_ranks(_sched_worker, world=world, backend=backend, args=(False, steps))
+    rotated = run_ranks(_sched_worker, world=world, backend=backend, args=(True, steps))
+    for (ln, pn), (lr, pr) in zip(natural, rotated):
+        assert ln == lr
+        for a, b, c in zip(pr, pn, model.parameters()):
+            assert torch.equal(a, b)
+            torch.testing.assert_close(a, c.detach(), rtol=2e-5, atol=2e-6)
+
+
+def test_rotated_loop_with_a_plain_torch_optimizer_and_scheduler():
+    from dear_pytorch_b200.utils.train import TrainStep
+    outs = []
+    for overlap in (False, True):
+        model = make_model(); model.eval()
+        opt = torch.optim.SGD(model.parameters(), lr=0.05, momentum=0.9)
+        sched = torch.optim.lr_scheduler.StepLR(opt, step_size=1, gamma=0.5)
+        step = TrainStep(model, opt, nn.functional.cross_entropy, overlap_update=overlap)
+        for t in range(4):
+            step(*data(t, 8))
+            sched.step()
+        step.finish()
+        assert opt.param_groups[0]["lr"] == pytest.approx(0.05 * 0.5 ** 4)        # the live schedule is untouched
+        outs.append([p.detach().clone() for p in model.parameters()])
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
