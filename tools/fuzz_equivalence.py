@@ -123,7 +123,18 @@ def worker(rank, world, cfg):
     sched = torch.optim.lr_scheduler.StepLR(opt, 2, 0.5) if cfg["sched"] else None
     dear.broadcast_parameters(m.state_dict(), 0)
     per = cfg["per"]
+    train_step = None
+    if cfg["trainstep"]:
+        # the packaged iteration (utils/train.py), natural or rotated body; the branch flag travels as an input
+        train_step = dear.TrainStep(m, opt, lambda out, y: nn.functional.cross_entropy(out, y), use_graph=False,
+                                    overlap_update=cfg["rot"])
     for t in range(cfg["steps"]):
+        if train_step is not None:
+            x, y = batch(t, world * per)
+            train_step(x[rank * per:(rank + 1) * per], use_side(cfg, t, 0), y[rank * per:(rank + 1) * per])
+            if sched:
+                sched.step()
+            continue
         opt.zero_grad()
         for a in range(k):
             x, y = batch(t * k + a, world * per)
@@ -136,7 +147,10 @@ def worker(rank, world, cfg):
             opt.engine.rebucket(("threshold", cfg["thr2"]))
         if v in ("dear", "bo") and cfg["ckpt"] and t == cfg["ckpt"]:
             opt.load_state_dict(opt.state_dict())
-    opt.synchronize()
+    if train_step is not None:
+        train_step.finish()
+    if hasattr(opt, "synchronize"):
+        opt.synchronize()
     return [p.detach().clone() for p in m.parameters()]
 
 
@@ -153,6 +167,10 @@ def draw(rnd, variants_allowed):
                thr2=rnd.choice([0.0004, 0.003, 1.0]), ckpt=rnd.choice([0, 0, 1, 2]), backend=rnd.choice(["emu", "emu", "gloo"]),
                pipe=rnd.random() < 0.25, elems=rnd.choice([0, 50, 300, 5000]), cycle=rnd.choice([0.0, 0.2, 5.0]),
                credit=rnd.choice([100, 1000, 10 ** 7]))
+    cfg["trainstep"] = rnd.random() < 0.3
+    cfg["rot"] = rnd.random() < 0.6
+    if cfg["trainstep"]:
+        cfg.update(accum=1, rebucket=0, ckpt=0)
     if v in ("wfbp", "horovod", "bytescheduler"):
         cfg.update(backend="gloo", tie=False)             # NCCL-style baselines: torch.distributed only; modules own their weights
     if v == "bo" and not cfg["thr"]:
@@ -187,7 +205,7 @@ def main(argv=None):
         try:
             run_trial(cfg)
             if not args.quiet:
-                print(i, "ok", {k: cfg[k] for k in ("variant", "opt", "world", "backend", "accum", "branch", "tie", "split", "rebucket", "ckpt")},
+                print(i, "ok", {k: cfg[k] for k in ("variant", "opt", "world", "backend", "accum", "branch", "tie", "split", "sched", "rebucket", "ckpt", "trainstep", "rot")},
                       flush=True)
         except Exception as e:      # noqa: BLE001 - report and continue
             failures.append((cfg, str(e)[-800:]))
