@@ -97,6 +97,10 @@ class DearEngine:
         # count per parameter, the kernels keep one per bucket set: _refresh_hyper folds the difference into the
         # parameter's hyper segment (see _adam_lag_adjust)
         self._lag: Dict[nn.Parameter, int] = {}
+        # SGD with momentum AND dampening: torch initialises a parameter's momentum buffer with its first gradient
+        # (undampened); the kernels know one global "first step".  Parameters that start later get dampening 0 in
+        # their hyper segment for that one update (buf = m * 0 + 1 * g).  Filled below, empties after the first steps.
+        self._virgin = set()
         self.group_of: Dict[nn.Parameter, int] = {}
         for gi, grp in enumerate(optimizer.param_groups):
             for p in grp["params"]:
@@ -121,6 +125,8 @@ class DearEngine:
         if self.verbose:
             print("# of parameters: ", self.plan.num_parameters)
         self._check_plan_consistency()
+        if self.opt_kind == OPT_SGD and any(g.get("momentum", 0) != 0 and g.get("dampening", 0) != 0 for g in optimizer.param_groups):
+            self._virgin = {s.param for s in self.plan.slots}
         self._build(initial=True)
         self._register_hooks()
         _LIVE_ENGINES.add(self)
@@ -357,11 +363,15 @@ class DearEngine:
                 gone_now = set(absent)
                 lags = tuple(0 if i in gone_now else self._lag.get(sl.param, 0) for i, sl in enumerate(b.slots))
                 lags = (t, lags) if any(lags) else None
-            key = (key_all, absent, lags)
+            fresh = ()
+            if self._virgin and self._mom_initialised and self.opt_kind == OPT_SGD:
+                gone_now = set(absent)
+                fresh = tuple(i for i, sl in enumerate(b.slots) if i not in gone_now and sl.param in self._virgin)
+            key = (key_all, absent, lags, fresh)
             if self._hyper_key[b.index] == key:
                 continue
             segs = []
-            if not absent and lags is None:
+            if not absent and lags is None and not fresh:
                 for end, gi in self.plan.hyper_segments(b.index, self.group_of):
                     segs.append((int(end),) + key_all[gi])
             else:
@@ -376,12 +386,15 @@ class DearEngine:
                     k = key_all[gi]
                     if lag and t - lag >= 1:
                         k = self._adam_lag_adjust(k, t, lag)
+                    first_own = i in fresh
+                    if first_own:
+                        k = k[:3] + (0.0,) + k[4:]          # this parameter's first gradient: buf = g
                     seg = (int(end),) + k[:4] + (int(k[4]) | (HYPER_SKIP if skip else 0),) + k[5:]
-                    if prev == (gi, skip, lag) and not lag:
+                    if prev == (gi, skip, lag, first_own) and not lag:
                         segs[-1] = seg
                     else:
                         segs.append(seg)
-                    prev = (gi, skip, lag)
+                    prev = (gi, skip, lag, first_own)
             self.backend.set_hyper(b.index, HyperSpec(segs))
             self._hyper_key[b.index] = key
 
@@ -462,6 +475,12 @@ class DearEngine:
             self._any_pending = True
             self._mom_initialised = True
             self.num_updates += 1
+            if self._virgin:
+                for g in range(nb):
+                    gone = set(self._absent[g])
+                    for i, sl in enumerate(self.plan.buckets[g].slots):
+                        if i not in gone:
+                            self._virgin.discard(sl.param)
             if self.opt_kind != OPT_SGD:
                 for g in range(nb):
                     if self._absent[g]:
@@ -557,6 +576,7 @@ class DearEngine:
     def _restore_state(self, carry: dict):
         be = self.backend
         self._mom_initialised = bool(carry.get("mom_init", False))
+
         self.num_updates = int(carry.get("num_updates", self.num_updates))
         for b in self.plan.buckets:
             g = b.index

@@ -59,7 +59,8 @@ def optimizer_state_dict(optimizer) -> dict:
                 ent["step"] = torch.tensor(float(carry["num_updates"] - eng._lag.get(s.param, 0)))
                 ent["exp_avg"] = carry["momentum"][s.name].reshape(s.param.shape).clone()
                 ent["exp_avg_sq"] = carry["var"][s.name].reshape(s.param.shape).clone()
-        elif s.name in carry["momentum"] and carry["mom_init"]:
+        elif s.name in carry["momentum"] and carry["mom_init"] and s.param not in eng._virgin:
+            # (torch.optim.SGD has no buffer yet for a parameter that never received a gradient)
             ent["momentum_buffer"] = carry["momentum"][s.name].reshape(s.param.shape).clone()
         if s.name in carry["master"]:
             ent["master_param"] = carry["master"][s.name].reshape(s.param.shape).clone()
@@ -89,6 +90,9 @@ def load_optimizer_state_dict(optimizer, sd: dict) -> None:
     carry = {"momentum": {}, "master": {}, "var": {}, "mom_init": False,
              "num_updates": int(meta.get("num_updates", eng.num_updates))}
     adam_steps = {}
+    track_first = eng.opt_kind == 0 and any(g.get("momentum", 0) != 0 and g.get("dampening", 0) != 0
+                                            for g in optimizer.param_groups)
+    eng._virgin = {s.param for s in eng.plan.slots} if track_first else set()
     for s in eng.plan.slots:
         ent = sd["state"].get(index[s.param])
         if ent is None:
@@ -99,6 +103,7 @@ def load_optimizer_state_dict(optimizer, sd: dict) -> None:
         if mb is not None:
             carry["momentum"][s.name] = mb.to(eng.device, torch.float32).reshape(-1)
             carry["mom_init"] = True
+            eng._virgin.discard(s.param)
         if ent.get("exp_avg") is not None:
             carry["momentum"][s.name] = ent["exp_avg"].to(eng.device, torch.float32).reshape(-1)
             carry["var"][s.name] = ent["exp_avg_sq"].to(eng.device, torch.float32).reshape(-1)

@@ -152,3 +152,39 @@ def test_parameters_without_gradient_are_not_updated(backend):
     for out in run_ranks(_skip_worker, world=2, backend=backend):
         for n, a, b in out:
             torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-6, msg=lambda m: "%s: %s" % (n, m))
+
+
+def _late_start_worker(rank, world, steps):
+    import dear_pytorch_b200 as dear
+    from test_adam import _Branchy, _branchy_data
+    m = _Branchy()
+    opt = dear.DistributedOptimizer(torch.optim.SGD(m.parameters(), lr=0.05, momentum=0.8, dampening=0.3, weight_decay=5e-3), m,
+                                    threshold=0.0005, verbose=False)
+    dear.broadcast_parameters(m.state_dict(), 0)
+    for t in range(steps):
+        x, y = _branchy_data(t, 4)
+        opt.zero_grad()
+        nn.functional.cross_entropy(m(x[rank * 2:(rank + 1) * 2], t % 3 == 2), y[rank * 2:(rank + 1) * 2]).backward()
+        opt.step()
+        if t == 0:
+            opt.load_state_dict(opt.state_dict())       # "never had a gradient" survives a state-dict round trip
+    opt.synchronize()
+    return [p.detach().clone() for p in m.parameters()]
+
+
+@pytest.mark.parametrize("backend", ["gloo", "emu"])
+def test_momentum_buffer_of_a_late_starting_parameter_with_dampening(backend):
+    """torch.optim.SGD initialises a momentum buffer with the parameter's FIRST gradient, undampened — also when that
+    gradient arrives in step 2 (the side branch) rather than in the global first step."""
+    from test_adam import _Branchy, _branchy_data
+    steps = 7
+    ref = _Branchy()
+    opt = torch.optim.SGD(ref.parameters(), lr=0.05, momentum=0.8, dampening=0.3, weight_decay=5e-3)
+    for t in range(steps):
+        x, y = _branchy_data(t, 4)
+        opt.zero_grad()
+        nn.functional.cross_entropy(ref(x, t % 3 == 2), y).backward()
+        opt.step()
+    for params in run_ranks(_late_start_worker, world=2, backend=backend, args=(steps,)):
+        for a, b in zip(params, ref.parameters()):
+            torch.testing.assert_close(a, b.detach(), rtol=3e-5, atol=3e-6)

@@ -56,6 +56,8 @@ def make_opt(kind, groups):
         return torch.optim.SGD(groups, lr=0.05, momentum=0.9, weight_decay=1e-3)
     if kind == "nesterov":
         return torch.optim.SGD(groups, lr=0.05, momentum=0.8, nesterov=True, weight_decay=1e-2)
+    if kind == "damp":
+        return torch.optim.SGD(groups, lr=0.05, momentum=0.8, dampening=0.3, weight_decay=5e-3)
     if kind == "adam":
         return torch.optim.Adam(groups, lr=0.01, weight_decay=1e-3)
     return torch.optim.AdamW(groups, lr=0.01, weight_decay=1e-2)
@@ -159,7 +161,7 @@ def draw(rnd, variants_allowed):
     engine = v in ("dear", "bo", "naive", "wt", "wfbp", "horovod", "bytescheduler")
     cfg = dict(variant=v, seed=rnd.randint(0, 99), depth=rnd.randint(1, 5), width=rnd.choice([8, 17, 32]), tie=rnd.random() < 0.3,
                branch=rnd.random() < 0.5, mod=rnd.choice([2, 3, 5]),
-               opt=rnd.choice(["sgd", "sgdm", "nesterov", "adam", "adamw"] if engine else ["sgd", "sgdm", "nesterov"]),
+               opt=rnd.choice(["sgd", "sgdm", "nesterov", "damp", "adam", "adamw"] if engine else ["sgd", "sgdm", "nesterov", "damp"]),
                split=rnd.random() < 0.5, world=rnd.choice([2, 3, 4]), per=rnd.choice([1, 2]),
                steps=rnd.randint(6, 12) if v == "bo" else rnd.randint(3, 6), sched=rnd.random() < 0.3,
                thr=rnd.choice([None, 0.0005, 0.002, 0.01]), nearby=rnd.choice([1, 2, 3, -1]),
