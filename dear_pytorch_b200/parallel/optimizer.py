@@ -405,6 +405,28 @@ class DearEngine:
         ``optimizer.step(); scheduler.step()`` would have."""
         self._frozen_hyper = self._hyper_key_live()
 
+    @torch.no_grad()
+    def _clip_reduced_gradients(self):
+        """Global-norm clipping of the AVERAGED gradients, ``torch.nn.utils.clip_grad_norm_`` semantics (the reference's
+        WFBP optimizer clips per tensor after its all-reduce, wfbp/dopt.py:855-862; its DeAR factory accepts ``norm_clip``
+        and ignores it).  After the reduce-scatters every rank holds 1/P of the averaged gradient exactly once, so the
+        norm is one pass over the fp32 shards plus a one-element all-reduce; the shards are scaled in place before the
+        update kernels read them.  Costs the overlap of the first updates with the last reduce-scatters (the norm needs
+        all of them), no host synchronisation.  Eager steps only."""
+        be = self.backend
+        if self.device.type == "cuda" and torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("norm_clip is not supported inside a CUDA-graph capture (TrainStep(use_graph=True))")
+        from .collectives import allreduce_
+        be.wait_all()                                    # the current stream now follows every reduce-scatter
+        shards = [s for s in be.grad_shard if s is not None]
+        sq = torch.stack([s.pow(2).sum() for s in shards]).sum().reshape(1)
+        allreduce_(sq, average=False)
+        total = sq.sqrt()
+        coef = (float(self.norm_clip) / (total + 1e-6)).clamp(max=1.0)
+        for s in shards:
+            s.mul_(coef)
+        self.last_grad_norm = total                      # device tensor (before clipping), for logging
+
     def unfreeze_hyper(self):
         self._frozen_hyper = None
 
@@ -467,6 +489,8 @@ class DearEngine:
             self._drain_rs(force=True)
         if not self.exclude_allgather:
             self._refresh_hyper()
+            if getattr(self, "norm_clip", None) is not None and not self.exclude_reducescatter:
+                self._clip_reduced_gradients()
             be.fence()
             first = not self._mom_initialised
             for g in range(nb):
@@ -717,7 +741,9 @@ def DistributedOptimizer(optimizer, model, compression=None, is_sparse=False, de
     policy (``k=1`` is "DeAR without tensor fusion").  ``bo_tuning=True`` enables the Bayesian
     buffer-size tuner (the reference's separate ``dopt_rsag_bo`` module).  ``backward_passes_per_step=k``
     (Horovod's name; not in the reference) accumulates gradients locally over k backward passes and
-    reduce-scatters them during the k-th; call ``step()`` once per k passes.
+    reduce-scatters them during the k-th; call ``step()`` once per k passes.  ``norm_clip=c`` (accepted and ignored by the
+    reference's DeAR factory) clips the global norm of the averaged gradient to ``c`` like
+    ``torch.nn.utils.clip_grad_norm_`` before the update (``DearEngine._clip_reduced_gradients``).
     """
     if threshold in (None, 0) and num_nearby_layers is None:
         threshold = float(os.environ.get("DEAR_THRESHOLD_MB", THRESHOLD))
@@ -728,6 +754,10 @@ def DistributedOptimizer(optimizer, model, compression=None, is_sparse=False, de
               num_nearby_layers=num_nearby_layers if num_nearby_layers is not None else NUM_NEARBY_LAYERS,
               exclude_parts=exclude_parts, policy=policy, verbose=verbose,
               backward_passes_per_step=backward_passes_per_step)
+    if norm_clip is not None:
+        if norm_clip <= 0:
+            raise ValueError("norm_clip must be positive")
+        opt._dear.norm_clip = float(norm_clip)      # global-norm clipping of the averaged gradients (eager steps)
     if loss_scale is not None:
         opt.set_loss_scale(loss_scale)
     if bo_tuning:

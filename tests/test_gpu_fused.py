@@ -287,10 +287,14 @@ def sched_worker(rank, world, use_graph, overlap):
 _SCHED_EAGER = []
 
 
-@pytest.mark.parametrize("overlap", [False, True])
-def test_cuda_graph_with_lr_scheduler_and_eager_interruption(overlap):
+def test_cuda_graph_with_lr_scheduler_and_eager_interruption():
     """Advisor finding (round 1): an LR change after capture must not clobber the table a captured kernel reads, and an
-    eager step between replays must not leave the graph with the eager step's gradient addresses."""
+    eager step between replays must not leave the graph with the eager step's gradient addresses.  (The rotated body with
+    its frozen hyper-parameters: tests/test_zz_post_budget_gpu.py — written after the round's last GPU session.)"""
+    check_graph_with_lr_scheduler(False)
+
+
+def check_graph_with_lr_scheduler(overlap):
     if not _SCHED_EAGER:          # the eager oracle is the same for both parametrisations: run it once
         _SCHED_EAGER.append(run_ranks(sched_worker, world=1, backend="b200", args=(False, False), extra_env=_env(), timeout=300))
     eager = _SCHED_EAGER[0]
