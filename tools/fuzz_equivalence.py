@@ -90,6 +90,8 @@ def oracle(cfg):
         for a in range(k):
             x, y = batch(t * k + a, cfg["world"] * cfg["per"])
             (nn.functional.cross_entropy(m(x, use_side(cfg, t, a)), y) / k).backward()
+        if cfg["clip"]:
+            torch.nn.utils.clip_grad_norm_(m.parameters(), cfg["clip"])
         opt.step()
         if sched:
             sched.step()
@@ -121,7 +123,7 @@ def worker(rank, world, cfg):
         kw = dict(threshold=cfg["thr"]) if cfg["thr"] else dict(threshold=None, num_nearby_layers=cfg["nearby"])
         if v == "bo":
             kw.update(bo_tuning=True, bo_kwargs=dict(bound=(0.0003, 0.02), max_num_steps=3, interval=2))
-        opt = dear.DistributedOptimizer(base, m, verbose=False, backward_passes_per_step=k, **kw)
+        opt = dear.DistributedOptimizer(base, m, verbose=False, backward_passes_per_step=k, norm_clip=cfg["clip"] or None, **kw)
     sched = torch.optim.lr_scheduler.StepLR(opt, 2, 0.5) if cfg["sched"] else None
     dear.broadcast_parameters(m.state_dict(), 0)
     per = cfg["per"]
@@ -169,6 +171,7 @@ def draw(rnd, variants_allowed):
                thr2=rnd.choice([0.0004, 0.003, 1.0]), ckpt=rnd.choice([0, 0, 1, 2]), backend=rnd.choice(["emu", "emu", "gloo"]),
                pipe=rnd.random() < 0.25, elems=rnd.choice([0, 50, 300, 5000]), cycle=rnd.choice([0.0, 0.2, 5.0]),
                credit=rnd.choice([100, 1000, 10 ** 7]))
+    cfg["clip"] = rnd.choice([0, 0, 0.3, 2.0]) if v == "dear" else 0
     cfg["trainstep"] = rnd.random() < 0.3
     cfg["rot"] = rnd.random() < 0.6
     if cfg["trainstep"]:
@@ -207,7 +210,7 @@ def main(argv=None):
         try:
             run_trial(cfg)
             if not args.quiet:
-                print(i, "ok", {k: cfg[k] for k in ("variant", "opt", "world", "backend", "accum", "branch", "tie", "split", "sched", "rebucket", "ckpt", "trainstep", "rot")},
+                print(i, "ok", {k: cfg[k] for k in ("variant", "opt", "world", "backend", "accum", "branch", "tie", "split", "sched", "rebucket", "ckpt", "trainstep", "rot", "clip")},
                       flush=True)
         except Exception as e:      # noqa: BLE001 - report and continue
             failures.append((cfg, str(e)[-800:]))
