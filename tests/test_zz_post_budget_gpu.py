@@ -119,3 +119,28 @@ def test_prefetcher_with_delayed_uploads_delivers_every_batch_intact():
         sums.append(x.double().sum())              # consumer work on the current stream
     torch.cuda.synchronize()
     assert [float(s) for s in sums] == [float(i) * (1 << 20) for i in range(12)]
+
+
+# ---- NCCL-style baselines through the command-line driver (own process group of the ByteScheduler thread, Horovod options) ---------
+def _driver_gpu_worker(rank, world, method, extra):
+    import contextlib
+    import io
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "benchmarks"))
+    import imagenet_benchmark as drv
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        res = drv.main(["--model", "resnet18", "--image-size", "64", "--batch-size", "4", "--num-warmup-batches", "2",
+                        "--num-batches-per-iter", "2", "--num-iters", "2", "--method", method] + list(extra))
+    return res["total"], buf.getvalue()
+
+
+@pytest.mark.parametrize("method,extra", [("bytescheduler", ()), ("horovod", ()), ("horovod", ("--fp16-allreduce",)),
+                                          ("horovod", ("--use-adasum",)), ("dear-rb", ()), ("wfbp", ("--compressor", "gtopk", "--density", "0.01"))])
+def test_baseline_methods_of_the_driver_over_nccl(method, extra):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("NCCL needs one GPU per rank")
+    outs = run_ranks(_driver_gpu_worker, world=2, backend="nccl", args=(method, extra), extra_env=ENV, timeout=600)
+    total, text = outs[0]
+    assert total > 0 and "Total img/sec on 2 GPU(s): " in text
