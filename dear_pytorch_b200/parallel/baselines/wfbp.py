@@ -372,7 +372,7 @@ class _DistributedOptimizer(torch.optim.Optimizer):
                 gi = self._group_of[n]
                 zc = self._compression.zero_conditions.get("group-%d" % gi)
                 buf = self.state[p].get("momentum_buffer")
-                if zc is not None and buf is not None:
+                if zc is not None and buf is not None and self._density < 1:     # (reference: "and density < 1", :948)
                     a, b = self._offsets[n]
                     buf.view(-1).mul_(zc[a:b].to(buf.dtype))
 

@@ -313,3 +313,29 @@ def test_bytescheduler_deferred_updates_use_the_lr_of_their_own_step():
     for params in run_ranks(_bsc_sched_worker, world=world, backend="gloo", args=(steps, per_rank)):
         for a, b in zip(params, model.parameters()):
             torch.testing.assert_close(a, b.detach(), rtol=3e-5, atol=3e-6)
+
+
+def _lossless_sparse_worker(rank, world, comp, mc):
+    import dear_pytorch_b200 as dear
+    from dear_pytorch_b200.parallel.baselines import WFBPDistributedOptimizer
+    m = make_model(); m.eval()
+    opt = WFBPDistributedOptimizer(torch.optim.SGD(m.parameters(), lr=0.05, momentum=0.9), model=m, compression=comp, is_sparse=True,
+                                   density=1.0, threshold=600, momentum_correction=mc, verbose=False)
+    dear.broadcast_parameters(m.state_dict(), 0)
+    for t in range(4):
+        x, y = data(t, 4)
+        opt.zero_grad()
+        nn.functional.cross_entropy(m(x[rank * 2:(rank + 1) * 2]), y[rank * 2:(rank + 1) * 2]).backward()
+        opt.step()
+    return [p.detach().clone() for p in m.parameters()]
+
+
+@pytest.mark.parametrize("mc", [False, True])
+@pytest.mark.parametrize("comp", ["topk", "eftopk", "gtopk", "gtopkef"])
+def test_sparse_path_at_density_one_is_the_dense_optimizer(comp, mc):
+    """Invariant: selecting every element loses nothing, so the sparse all-gather / gTop-k path — with or without momentum
+    correction, whose factor masking only applies below density 1 (wfbp/dopt.py:948) — must reproduce momentum SGD."""
+    ref = reference_run(dict(momentum=0.9), 4, 2, 2)
+    for params in run_ranks(_lossless_sparse_worker, world=2, backend="gloo", args=(comp, mc)):
+        for a, b in zip(params, ref):
+            torch.testing.assert_close(a, b, rtol=3e-5, atol=3e-6)
