@@ -164,7 +164,7 @@ def draw(rnd, variants_allowed):
     cfg = dict(variant=v, seed=rnd.randint(0, 99), depth=rnd.randint(1, 5), width=rnd.choice([8, 17, 32]), tie=rnd.random() < 0.3,
                branch=rnd.random() < 0.5, mod=rnd.choice([2, 3, 5]),
                opt=rnd.choice(["sgd", "sgdm", "nesterov", "damp", "adam", "adamw"] if engine else ["sgd", "sgdm", "nesterov", "damp"]),
-               split=rnd.random() < 0.5, world=rnd.choice([2, 3, 4]), per=rnd.choice([1, 2]),
+               split=rnd.random() < 0.5, world=rnd.choice([1, 2, 3, 4]), per=rnd.choice([1, 2]),
                steps=rnd.randint(6, 12) if v == "bo" else rnd.randint(3, 6), sched=rnd.random() < 0.3,
                thr=rnd.choice([None, 0.0005, 0.002, 0.01]), nearby=rnd.choice([1, 2, 3, -1]),
                accum=rnd.choice([1, 1, 2, 3]) if v == "dear" else 1, rebucket=rnd.choice([0, 0, 1, 2]),
