@@ -167,9 +167,9 @@ class _ReduceBroadcastOptimizer(torch.optim.Optimizer):
         self._reduce_handle = [None] * nb
         self._bcast_handle = [None] * nb
         self._hooks = []
+        for s in self._plan.slots:             # (single process too: the hook records which parameters got a gradient)
+            self._hooks.append(s.param.register_post_accumulate_grad_hook(self._on_grad))
         if self._world > 1:
-            for s in self._plan.slots:
-                self._hooks.append(s.param.register_post_accumulate_grad_hook(self._on_grad))
             for mi, m in enumerate(self._plan.modules):
                 self._hooks.append(m.register_forward_pre_hook(self._make_pre_hook(mi)))
         if verbose and self._rank == 0:
@@ -184,6 +184,8 @@ class _ReduceBroadcastOptimizer(torch.optim.Optimizer):
             p.grad = gv
         self._arrived[g] += 1
         self._got.add(p)
+        if self._world == 1:
+            return
         if self._arrived[g] == len(self._plan.buckets[g].slots) and not self._exclude_reduce:
             self._reduce_handle[g] = self._comm.reduce(self._gbuf[g], self.ROOT, 1.0 / self._world)
 
@@ -203,7 +205,16 @@ class _ReduceBroadcastOptimizer(torch.optim.Optimizer):
             with torch.enable_grad():
                 loss = closure()
         if self._world == 1:
+            hidden = [(sl.param, sl.param.grad) for sl in self._plan.slots if sl.param not in self._got]
+            for q, _ in hidden:                         # no gradient this step: torch.optim leaves the parameter alone
+                q.grad = None
             super(self.__class__, self).step()
+            for q, gview in hidden:
+                q.grad = gview
+            for g, gb in enumerate(self._gbuf):         # gradients are bucket views and zero_grad() is a no-op
+                gb.zero_()
+                self._arrived[g] = 0
+            self._got.clear()
             return loss
         for g, b in enumerate(self._plan.buckets):
             if self._reduce_handle[g] is None and not self._exclude_reduce:
