@@ -419,7 +419,7 @@ class DearEngine:
         from .collectives import allreduce_
         be.wait_all()                                    # the current stream now follows every reduce-scatter
         shards = [s for s in be.grad_shard if s is not None]
-        sq = torch.stack([s.pow(2).sum() for s in shards]).sum().reshape(1)
+        sq = torch.stack(torch._foreach_norm(shards)).pow(2).sum().reshape(1)       # no shard-sized temporaries
         allreduce_(sq, average=False)
         total = sq.sqrt()
         coef = (float(self.norm_clip) / (total + 1e-6)).clamp(max=1.0)
