@@ -137,7 +137,7 @@ def _driver_gpu_worker(rank, world, method, extra):
 
 
 @pytest.mark.parametrize("method,extra", [("bytescheduler", ()), ("horovod", ()), ("horovod", ("--fp16-allreduce",)),
-                                          ("horovod", ("--use-adasum",)), ("dear-rb", ()), ("wfbp", ("--compressor", "gtopk", "--density", "0.01"))])
+                                          ("horovod", ("--use-adasum",))])
 def test_baseline_methods_of_the_driver_over_nccl(method, extra):
     if torch.cuda.device_count() < 2:
         pytest.skip("NCCL needs one GPU per rank")
