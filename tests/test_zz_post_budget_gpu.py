@@ -144,3 +144,18 @@ def test_baseline_methods_of_the_driver_over_nccl(method, extra):
     outs = run_ranks(_driver_gpu_worker, world=2, backend="nccl", args=(method, extra), extra_env=ENV, timeout=600)
     total, text = outs[0]
     assert total > 0 and "Total img/sec on 2 GPU(s): " in text
+
+
+# ---- a slice of the randomised equivalence fuzzer on the fused kernels -----------------------------------------------------------
+def test_fuzz_slice_on_the_fused_kernels():
+    """tools/fuzz_equivalence.py with ``--backends b200``: random models / optimizers / bucketing / accumulation / re-bucketing /
+    state-dict round trips / TrainStep bodies on the GPU data path against single-process torch.optim on the CPU."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("fuzz_equivalence_gpu", os.path.join(root, "tools", "fuzz_equivalence.py"))
+    fuzz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fuzz)
+    failures = fuzz.main(["--seed", "5", "--trials", "6", "--backends", "b200", "--max-world", "2", "--quiet",
+                          "--variants", "dear,dear,dear,bo,naive,wt,rb"])
+    assert not failures, failures[0]

@@ -101,7 +101,8 @@ def oracle(cfg):
 def worker(rank, world, cfg):
     import dear_pytorch_b200 as dear
     from dear_pytorch_b200.parallel import variants
-    m = Net(cfg["seed"], cfg["depth"], cfg["width"], cfg["tie"])
+    dev = dear.device()                                  # cpu for emu / gloo, cuda:LOCAL_RANK for b200 / nccl
+    m = Net(cfg["seed"], cfg["depth"], cfg["width"], cfg["tie"]).to(dev)
     base = make_opt(cfg["opt"], param_groups(m, cfg["split"]))
     v, k = cfg["variant"], cfg["accum"]
     if v == "naive":
@@ -135,15 +136,15 @@ def worker(rank, world, cfg):
     for t in range(cfg["steps"]):
         if train_step is not None:
             x, y = batch(t, world * per)
-            train_step(x[rank * per:(rank + 1) * per], use_side(cfg, t, 0), y[rank * per:(rank + 1) * per])
+            train_step(x[rank * per:(rank + 1) * per].to(dev), use_side(cfg, t, 0), y[rank * per:(rank + 1) * per].to(dev))
             if sched:
                 sched.step()
             continue
         opt.zero_grad()
         for a in range(k):
             x, y = batch(t * k + a, world * per)
-            (nn.functional.cross_entropy(m(x[rank * per:(rank + 1) * per], use_side(cfg, t, a)),
-                                         y[rank * per:(rank + 1) * per]) / k).backward()
+            (nn.functional.cross_entropy(m(x[rank * per:(rank + 1) * per].to(dev), use_side(cfg, t, a)),
+                                         y[rank * per:(rank + 1) * per].to(dev)) / k).backward()
         opt.step()
         if sched:
             sched.step()
@@ -155,10 +156,10 @@ def worker(rank, world, cfg):
         train_step.finish()
     if hasattr(opt, "synchronize"):
         opt.synchronize()
-    return [p.detach().clone() for p in m.parameters()]
+    return [p.detach().float().cpu().clone() for p in m.parameters()]
 
 
-def draw(rnd, variants_allowed):
+def draw(rnd, variants_allowed, backends=None, max_world=4):
     v = rnd.choice(variants_allowed)
     engine = v in ("dear", "bo", "naive", "wt", "wfbp", "horovod", "bytescheduler")
     cfg = dict(variant=v, seed=rnd.randint(0, 99), depth=rnd.randint(1, 5), width=rnd.choice([8, 17, 32]), tie=rnd.random() < 0.3,
@@ -176,8 +177,12 @@ def draw(rnd, variants_allowed):
     cfg["rot"] = rnd.random() < 0.6
     if cfg["trainstep"]:
         cfg.update(accum=1, rebucket=0, ckpt=0)
+    if backends:
+        cfg["backend"] = rnd.choice(backends)
+    cfg["world"] = min(cfg["world"], max_world)
     if v in ("wfbp", "horovod", "bytescheduler"):
-        cfg.update(backend="gloo", tie=False)             # NCCL-style baselines: torch.distributed only; modules own their weights
+        # NCCL-style baselines: torch.distributed only; modules own their weights
+        cfg.update(backend="nccl" if cfg["backend"] in ("b200", "nccl") else "gloo", tie=False)
     if v == "bo" and not cfg["thr"]:
         cfg["thr"] = 0.002
     return cfg
@@ -185,9 +190,14 @@ def draw(rnd, variants_allowed):
 
 def run_trial(cfg):
     env = {"DEAR_RS_ALGO": "pipe", "DEAR_STRIPE_MB": "0.001"} if (cfg["pipe"] and cfg["backend"] == "emu") else None
+    gpu = cfg["backend"] in ("b200", "nccl")
+    if gpu:
+        env = dict(env or {}, DEAR_SPIN_TIMEOUT_S="15")
     ref = oracle(cfg)
-    outs = run_ranks(worker, world=cfg["world"], backend=cfg["backend"], args=(cfg,), timeout=180, extra_env=env)
+    outs = run_ranks(worker, world=cfg["world"], backend=cfg["backend"], args=(cfg,), timeout=300 if gpu else 180, extra_env=env)
     tol = dict(rtol=1e-3, atol=5e-5) if cfg["opt"].startswith("adam") else dict(rtol=5e-5, atol=5e-6)
+    if gpu:                                                # other reduction orders in the GEMMs than the CPU oracle
+        tol = dict(rtol=2e-3, atol=1e-4)
     for params in outs:
         for a, b in zip(params, ref):
             torch.testing.assert_close(a, b, **tol)
@@ -202,11 +212,13 @@ def main(argv=None):
     ap.add_argument("--trials", type=int, default=20)
     ap.add_argument("--variants", default="dear,dear,dear,bo,naive,wt,rb,wfbp,horovod,bytescheduler")
     ap.add_argument("--quiet", action="store_true")
+    ap.add_argument("--backends", default=None, help="comma list; default emu,emu,gloo.  b200 runs the fused kernels (GPU box)")
+    ap.add_argument("--max-world", type=int, default=4)
     args = ap.parse_args(argv)
     rnd = random.Random(args.seed)
     failures = []
     for i in range(args.trials):
-        cfg = draw(rnd, args.variants.split(","))
+        cfg = draw(rnd, args.variants.split(","), args.backends.split(",") if args.backends else None, args.max_world)
         try:
             run_trial(cfg)
             if not args.quiet:
