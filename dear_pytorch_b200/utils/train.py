@@ -106,6 +106,9 @@ class TrainStep:
         else:
             self._frozen_groups = [{k: v for k, v in g.items() if k != "params"} for g in self.opt.param_groups]
         self._pending_update = True
+        # the update of this call is deferred, not skipped, and will use this call's hyper-parameters: an LR scheduler
+        # stepped now must not warn that it runs "before optimizer.step()" (torch checks this flag)
+        self.opt._opt_called = True
         return loss
 
     def _deferred_step(self):
