@@ -112,3 +112,18 @@ def test_flags_and_hyper_segments():
     assert segs[-1][0] == plan.buckets[0].padded_numel
     ends = [e for e, _ in segs]
     assert ends == sorted(ends)
+
+
+def test_reference_bucket_sizes_densenet201_and_bert_embeddings():
+    """DenseNet-201 -> 4 buckets [25.0, 24.7, 19.3, 7.3] MB; the first BERT bucket is the embedding table
+    (89.4 MB for BERT-base, 119.3 MB for BERT-large).  (This BERT's fused QKV projection is one 12.6 MB module where
+    transformers has three, so the remaining BERT-large buckets are 16.8 MB instead of ~24 MB: DESIGN.md, known gaps.)"""
+    import torch
+    from dear_pytorch_b200.models.registry import create
+    with torch.device("meta"):
+        p = BucketPlan(create("densenet201"), 8).group_by_threshold(25)
+        assert [round(b.size_mb, 1) for b in p.buckets] == [25.0, 24.7, 19.3, 7.3]
+        base = BucketPlan(create("bert_base"), 8).group_by_threshold(25)
+        large = BucketPlan(create("bert"), 8).group_by_threshold(25)
+    assert abs(base.buckets[0].size_mb - 89.4) < 0.1 and abs(large.buckets[0].size_mb - 119.3) < 0.15
+    assert max(b.size_mb for b in large.buckets[1:]) < 25.0
